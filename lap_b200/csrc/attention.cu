@@ -1,0 +1,266 @@
+// K11 + the softmax halves of K1/K2: attention-mask / position construction (bit-exact integer work) and the
+// masked-softmax forward/backward that sit between the two tcgen05 attention GEMMs (S = Q K^T, O = P V).
+//
+//   mask_build      OP/models/pi0.py:19-44 (make_attn_mask), lap.py:303-377 (prefix/action masks, positions),
+//                   lap.py:641-654 (inference suffix rows)
+//   attn_softmax    gemma.py:258-261: where(mask, logits, -2.3819763e38) -> softmax fp32 -> bf16
+//   vit_softmax     flax MultiHeadDotProductAttention softmax evaluated in bf16 (siglip.py:88-93)
+#include "../../include/lapb200.h"
+#include "common.cuh"
+#include "host_util.h"
+
+namespace lapb {
+
+typedef __nv_bfloat16 bf16;
+#define BIG_NEG (-2.3819763e38f)
+
+// ------------------------------------------------------------------------------------------------
+// mask + positions. One CTA per sample.
+//   prefix rows i<P:   allowed(i,j) = j<P & pm[i] & pm[j] & cumP[j] <= cumP[i]
+//   suffix rows i>=P:  input = [pma | sm], ar = [0.. | sar];  allowed = in[i] & in[j] & cum[j] <= cum[i]
+//                      (infer_rows: prefix part is pm[j] alone, lap.py:644)
+//   positions: prefix cumsum(pm)-1 ; suffix sum(pma) + cumsum(sm) - 1
+// bits[b, i - row_begin, w] bit k  <->  key j = 32w + k
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mask_build_kernel(const uint8_t* __restrict__ pm, const uint8_t* __restrict__ par, const uint8_t* __restrict__ pma,
+                  const uint8_t* __restrict__ sm, const uint8_t* __restrict__ sar, uint32_t* __restrict__ bits,
+                  int* __restrict__ positions, int P, int A, int W32, int row_begin, int infer_rows) {
+  extern __shared__ int sh[];
+  int T = P + A;
+  int* cum = sh;            // [T]  cumsum of ar for prefix rows' view (prefix part) / suffix view (suffix part)
+  int* valid_p = sh + T;    // [T]  pm (prefix view); suffix part = 0
+  int* valid_a = sh + 2 * T;  // [T] pma | sm (action view)
+  int* pos = sh + 3 * T;    // [T]
+  int b = blockIdx.x;
+  const uint8_t* pmb = pm + (long)b * P;
+  const uint8_t* parb = par + (long)b * P;
+  const uint8_t* pmab = pma ? pma + (long)b * P : pmb;
+  if (threadIdx.x == 0) {
+    int c = 0, pc = 0, na = 0;
+    for (int j = 0; j < P; ++j) {
+      c += parb[j] ? 1 : 0;
+      cum[j] = c;
+      valid_p[j] = pmb[j] ? 1 : 0;
+      valid_a[j] = pmab[j] ? 1 : 0;
+      pc += valid_p[j];
+      pos[j] = pc - 1;
+      na += valid_a[j];
+    }
+    int cs = 0, sc = 0;
+    for (int j = 0; j < A; ++j) {
+      cs += sar[(long)b * A + j] ? 1 : 0;
+      cum[P + j] = cs;
+      valid_p[P + j] = 0;
+      valid_a[P + j] = sm[(long)b * A + j] ? 1 : 0;
+      sc += valid_a[P + j];
+      pos[P + j] = na + sc - 1;
+    }
+  }
+  __syncthreads();
+  int nrows = T - row_begin;
+  for (int i = row_begin + threadIdx.x; i < T; i += 256) positions[(long)b * nrows + (i - row_begin)] = pos[i];
+  long total = (long)nrows * W32;
+  for (long idx = threadIdx.x; idx < total; idx += 256) {
+    int i = row_begin + (int)(idx / W32), w = (int)(idx % W32);
+    uint32_t word = 0;
+    for (int k = 0; k < 32; ++k) {
+      int j = w * 32 + k;
+      if (j >= T) break;
+      bool ok;
+      if (i < P) {
+        ok = (j < P) && valid_p[i] && valid_p[j] && (cum[j] <= cum[i]);
+      } else {
+        int cj = (j < P) ? 0 : cum[j];
+        if (infer_rows && j < P)
+          ok = valid_p[j] != 0;
+        else
+          ok = valid_a[i] && valid_a[j] && (cj <= cum[i]);
+      }
+      word |= (ok ? 1u : 0u) << k;
+    }
+    bits[((long)b * nrows + (i - row_begin)) * W32 + w] = word;
+  }
+}
+
+// expand packed bits to a dense uint8 mask (tests / debugging): dense[b,i,j]
+__global__ void mask_expand_kernel(const uint32_t* __restrict__ bits, uint8_t* __restrict__ dense, long rows, int S,
+                                   int W32) {
+  long total = rows * S;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    long r = idx / S;
+    int j = idx % S;
+    dense[idx] = (bits[r * W32 + (j >> 5)] >> (j & 31)) & 1u;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Gemma masked softmax. S fp32 [B, R, ld] (R = Tq*G rows, G query heads share a mask row), one warp per row.
+// P bf16 [B, R, ld] gets zeros in the pad columns [S_len, ld).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+attn_softmax_fwd_kernel(const float* __restrict__ S, const uint32_t* __restrict__ bits, bf16* __restrict__ Pout,
+                        long rows_per_batch, int G, int S_len, int ld, int W32, long total_rows) {
+  long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  long b = row / rows_per_batch, r = row % rows_per_batch;
+  const uint32_t* mrow = bits + (b * (rows_per_batch / G) + r / G) * W32;
+  const float* s = S + row * ld;
+  int nw = ld / 32;
+  float v[32];
+  float mx = -3.4e38f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < nw) {
+      int c = i * 32 + lane;
+      float x = BIG_NEG;
+      bool in = c < S_len;
+      if (in) {
+        uint32_t w = mrow[i];
+        x = ((w >> lane) & 1u) ? s[c] : BIG_NEG;
+        mx = fmaxf(mx, x);
+      }
+      v[i] = x;
+    }
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < nw) {
+      int c = i * 32 + lane;
+      float e = (c < S_len) ? __expf(v[i] - mx) : 0.f;
+      v[i] = e;
+      sum += e;
+    }
+  }
+  sum = warp_sum(sum);
+  float inv = 1.0f / sum;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) {
+    if (i < nw) Pout[row * ld + i * 32 + lane] = __float2bfloat16_rn(v[i] * inv);
+  }
+}
+
+// dS = P * (dP - sum_j P_j dP_j);  P, dP, dS bf16 [rows, ld]; one warp per row (in place on dP allowed)
+__global__ void __launch_bounds__(256)
+softmax_bwd_kernel(const bf16* __restrict__ P, const bf16* __restrict__ dP, bf16* __restrict__ dS, int ld,
+                   long total_rows) {
+  long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  const bf16* p = P + row * ld;
+  const bf16* d = dP + row * ld;
+  float dot = 0.f;
+  for (int c = lane * 2; c < ld; c += 64) {
+    float2 pv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p + c));
+    float2 dv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + c));
+    dot += pv.x * dv.x + pv.y * dv.y;
+  }
+  dot = warp_sum(dot);
+  for (int c = lane * 2; c < ld; c += 64) {
+    float2 pv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(p + c));
+    float2 dv = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(d + c));
+    *reinterpret_cast<uint32_t*>(dS + row * ld + c) = pack_bf16x2(pv.x * (dv.x - dot), pv.y * (dv.y - dot));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// SigLIP softmax in bf16 arithmetic (in place), one warp per row of `n` columns (n % 2 == 0):
+//   e = bf16(exp(bf16(x - max)));  p = bf16(e / bf16(sum e))          [mode 0: as written in jax.nn.softmax on bf16]
+//   p = bf16(softmax_fp32(x))                                          [mode 1]
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vit_softmax_fwd_kernel(bf16* __restrict__ S, int n, int ld, long total_rows, int mode) {
+  long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (row >= total_rows) return;
+  int lane = threadIdx.x & 31;
+  bf16* s = S + row * ld;
+  float mx = -3.4e38f;
+  for (int c = lane * 2; c < n; c += 64) {
+    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
+    mx = fmaxf(mx, fmaxf(x.x, x.y));
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int c = lane * 2; c < n; c += 64) {
+    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
+    float e0, e1;
+    if (mode == 0) {
+      e0 = bf16r(__expf(bf16r(x.x - mx)));
+      e1 = bf16r(__expf(bf16r(x.y - mx)));
+    } else {
+      e0 = __expf(x.x - mx);
+      e1 = __expf(x.y - mx);
+    }
+    sum += e0 + e1;
+  }
+  sum = warp_sum(sum);
+  if (mode == 0) sum = bf16r(sum);
+  for (int c = lane * 2; c < n; c += 64) {
+    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
+    float e0, e1;
+    if (mode == 0) {
+      e0 = bf16r(__expf(bf16r(x.x - mx)));
+      e1 = bf16r(__expf(bf16r(x.y - mx)));
+    } else {
+      e0 = __expf(x.x - mx);
+      e1 = __expf(x.y - mx);
+    }
+    *reinterpret_cast<uint32_t*>(s + c) = pack_bf16x2(e0 / sum, e1 / sum);
+  }
+}
+
+}  // namespace lapb
+
+using namespace lapb;
+#define STREAM(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int lapb200_mask_build(const uint8_t* pm, const uint8_t* par, const uint8_t* pma, const uint8_t* sm,
+                       const uint8_t* sar, uint32_t* bits, int32_t* positions, int64_t B, int64_t P, int64_t A,
+                       int64_t W32, int64_t row_begin, int64_t infer_rows, lapb_stream_t s) {
+  LAPB_REQUIRE(W32 * 32 >= P + A, "mask_build: W32 too small");
+  LAPB_REQUIRE(A == 0 || (sm && sar), "mask_build: suffix masks missing");
+  size_t smem = 4 * (size_t)(P + A) * sizeof(int);
+  LAPB_REQUIRE(smem <= 48 * 1024, "mask_build: sequence too long (%ld tokens)", (long)(P + A));
+  mask_build_kernel<<<(unsigned)B, 256, smem, STREAM(s)>>>(pm, par, pma, sm, sar, bits, positions, (int)P, (int)A,
+                                                          (int)W32, (int)row_begin, (int)infer_rows);
+  LAPB_LAUNCH_OK("mask_build");
+  return 0;
+}
+
+int lapb200_mask_expand(const uint32_t* bits, uint8_t* dense, int64_t rows, int64_t S, int64_t W32, lapb_stream_t s) {
+  mask_expand_kernel<<<148 * 4, 256, 0, STREAM(s)>>>(bits, dense, rows, (int)S, (int)W32);
+  LAPB_LAUNCH_OK("mask_expand");
+  return 0;
+}
+
+int lapb200_attn_softmax_fwd(const float* S, const uint32_t* bits, void* P, int64_t B, int64_t rows_per_batch,
+                             int64_t G, int64_t S_len, int64_t ld, int64_t W32, lapb_stream_t s) {
+  LAPB_REQUIRE(ld % 32 == 0 && ld <= 1024, "attn_softmax: ld must be a multiple of 32 and <= 1024 (got %ld)", (long)ld);
+  LAPB_REQUIRE(rows_per_batch % G == 0, "attn_softmax: rows_per_batch %% G != 0");
+  long total = B * rows_per_batch;
+  attn_softmax_fwd_kernel<<<cdiv(total, 8), 256, 0, STREAM(s)>>>(S, bits, (bf16*)P, rows_per_batch, (int)G,
+                                                                (int)S_len, (int)ld, (int)W32, total);
+  LAPB_LAUNCH_OK("attn_softmax_fwd");
+  return 0;
+}
+
+int lapb200_softmax_bwd(const void* P, const void* dP, void* dS, int64_t rows, int64_t ld, lapb_stream_t s) {
+  LAPB_REQUIRE(ld % 2 == 0, "softmax_bwd: ld must be even");
+  softmax_bwd_kernel<<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((const bf16*)P, (const bf16*)dP, (bf16*)dS, (int)ld, rows);
+  LAPB_LAUNCH_OK("softmax_bwd");
+  return 0;
+}
+
+int lapb200_vit_softmax_fwd(void* S, int64_t rows, int64_t n, int64_t ld, int64_t mode, lapb_stream_t s) {
+  LAPB_REQUIRE(n % 2 == 0 && ld % 2 == 0, "vit_softmax: n, ld must be even");
+  vit_softmax_fwd_kernel<<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((bf16*)S, (int)n, (int)ld, rows, (int)mode);
+  LAPB_LAUNCH_OK("vit_softmax_fwd");
+  return 0;
+}
+
+}  // extern "C"

@@ -42,6 +42,7 @@ struct GemmKArgs {
   long ldc2;
   int q_cols;
   float q_div;
+  int a_bi, a_bo, b_bi, b_bo;  // 1 if the operand really has that batch dimension, 0 = broadcast
 };
 
 template <int BN, bool DUAL>
@@ -147,7 +148,10 @@ __device__ __forceinline__ void epilogue_vec8(const GemmKArgs& a, long row, int 
       load_bf16x8(a.resid + r_boff + row * a.ldr + col, r);
       load_bf16x8(a.gate + (row / a.gate_rows) * a.ldg + col, gt);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) x[j] = r[j] + bf16r(bf16r(x[j]) * gt[j]);
+      for (int j = 0; j < 8; ++j) x[j] = bf16r(x[j]);
+      if (a.C2) store_bf16x8(a.C2 + c_boff + row * a.ldc2 + col, x);  // branch output y (needed by dgate)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) x[j] = r[j] + bf16r(x[j] * gt[j]);
       break;
     }
     case LAPB_EPI_QSCALE: {
@@ -239,12 +243,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
           mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
           uint8_t* sa = smem_a + stage * Cfg::A_BYTES;
           uint8_t* sb = smem_b + stage * (Cfg::NB * Cfg::B_BYTES);
+          const int abi = bi * a.a_bi, abo = bo * a.a_bo, bbi = bi * a.b_bi, bbo = bo * a.b_bo;
           if (!A_MN) {
-            tma_load_4d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, bi, bo);
+            tma_load_4d(sa, &tmA, &full_bar[stage], kb * BK, m_blk * BM, abi, abo);
           } else {
 #pragma unroll
             for (int t = 0; t < BM / 64; ++t)
-              tma_load_4d(sa + t * (64 * BK * 2), &tmA, &full_bar[stage], m_blk * BM + t * 64, kb * BK, bi, bo);
+              tma_load_4d(sa + t * (64 * BK * 2), &tmA, &full_bar[stage], m_blk * BM + t * 64, kb * BK, abi, abo);
           }
 #pragma unroll
           for (int d = 0; d < Cfg::NB; ++d) {
@@ -252,11 +257,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             int n0 = n_blk * BN + d * a.N;
             uint8_t* sbd = sb + d * Cfg::B_BYTES;
             if (!B_MN) {
-              tma_load_4d(sbd, &tmB, &full_bar[stage], kb * BK, n0, bi, bo);
+              tma_load_4d(sbd, &tmB, &full_bar[stage], kb * BK, n0, bbi, bbo);
             } else {
 #pragma unroll
               for (int t = 0; t < BN / 64; ++t)
-                tma_load_4d(sbd + t * (64 * BK * 2), &tmB, &full_bar[stage], n0 + t * 64, kb * BK, bi, bo);
+                tma_load_4d(sbd + t * (64 * BK * 2), &tmB, &full_bar[stage], n0 + t * 64, kb * BK, bbi, bbo);
             }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -462,18 +467,24 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
   ka.C2 = reinterpret_cast<__nv_bfloat16*>(p->C2); ka.ldc2 = p->ldc2;
   ka.q_cols = p->q_cols; ka.q_div = p->q_div != 0.f ? p->q_div : 1.f;
 
+  // a batch dimension with stride 0 is a broadcast: the tensor map gets extent 1 and the kernel passes coordinate 0
+  ka.a_bi = (bi > 1 && p->a_bs_i != 0) ? 1 : 0;
+  ka.a_bo = (bo > 1 && p->a_bs_o != 0) ? 1 : 0;
+  ka.b_bi = (bi > 1 && p->b_bs_i != 0) ? 1 : 0;
+  ka.b_bo = (bo > 1 && p->b_bs_o != 0) ? 1 : 0;
+  const int a_di = ka.a_bi ? bi : 1, a_do = ka.a_bo ? bo : 1, b_di = ka.b_bi ? bi : 1, b_do = ka.b_bo ? bo : 1;
   CUtensorMap tmA, tmB;
   int rc;
   if (p->a_major == 0)
-    rc = make_tmap_bf16_4d(&tmA, p->A, p->K, p->M, bi, bo, p->lda, p->a_bs_i, p->a_bs_o, BK, BM);
+    rc = make_tmap_bf16_4d(&tmA, p->A, p->K, p->M, a_di, a_do, p->lda, p->a_bs_i, p->a_bs_o, BK, BM);
   else
-    rc = make_tmap_bf16_4d(&tmA, p->A, p->M, p->K, bi, bo, p->lda, p->a_bs_i, p->a_bs_o, 64, BK);
+    rc = make_tmap_bf16_4d(&tmA, p->A, p->M, p->K, a_di, a_do, p->lda, p->a_bs_i, p->a_bs_o, 64, BK);
   if (rc) return rc;
   const uint64_t b_rows = dual ? 2ull * p->N : (uint64_t)p->N;
   if (p->b_major == 0)
-    rc = make_tmap_bf16_4d(&tmB, p->B, p->K, b_rows, bi, bo, p->ldb, p->b_bs_i, p->b_bs_o, BK, BN);
+    rc = make_tmap_bf16_4d(&tmB, p->B, p->K, b_rows, b_di, b_do, p->ldb, p->b_bs_i, p->b_bs_o, BK, BN);
   else
-    rc = make_tmap_bf16_4d(&tmB, p->B, p->N, p->K, bi, bo, p->ldb, p->b_bs_i, p->b_bs_o, 64, BK);
+    rc = make_tmap_bf16_4d(&tmB, p->B, p->N, p->K, b_di, b_do, p->ldb, p->b_bs_i, p->b_bs_o, 64, BK);
   if (rc) return rc;
 
   long total = (long)ka.num_m * ka.num_n * bi * bo;

@@ -1,0 +1,852 @@
+"""LAP model engine: the reference's `LAP` module surface backed by liblapb200.so kernels.
+
+Public surface (same names / argument meaning as the reference):
+  LAP.compute_loss(rng, observation, actions, *, train=False, ...) -> (loss, metrics)   src/lap/models/lap.py:380-602
+  LAP.sample_actions(rng, observation, *, num_steps=10, noise=None) -> actions           src/lap/models/lap.py:605-675
+plus explicit `noise=` / `time=` overrides on compute_loss (jax.random's threefry stream cannot be matched).
+
+Everything that computes runs in hand-written sm_100a kernels through the C ABI (lap_b200/ops.py); torch is the
+allocator / stream owner only.  The forward keeps the activations the hand-written backward needs (no autograd, no
+remat: 180 GB of HBM holds them at B=32); `forward_backward` fills a flat fp32 gradient buffer laid out like the
+parameters (lap_b200/params.py).
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import ops
+from . import params as P
+from .config import LAPConfig
+from .observation import CoTObservation, Observation, to_numpy
+
+BF16, F32 = torch.bfloat16, torch.float32
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+def _bf16_round(x: float) -> float:
+    return float(torch.tensor(x, dtype=torch.float32).to(torch.bfloat16).to(torch.float32))
+
+
+@dataclass
+class Staged:
+    """Device-side inputs of one step."""
+
+    B: int
+    images: list[torch.Tensor]
+    tokens: torch.Tensor  # [B, L] int32
+    pm: torch.Tensor  # [B, P] uint8 prefix input mask
+    par: torch.Tensor  # [B, P] uint8 prefix ar mask
+    pma: torch.Tensor  # [B, P] uint8 prefix mask seen by action rows
+    sm: torch.Tensor | None  # [B, A] uint8
+    sar: torch.Tensor | None  # [B, A] uint8
+    actions: torch.Tensor | None = None
+    noise: torch.Tensor | None = None
+    time: torch.Tensor | None = None
+    # language-loss rows (host-computed from the host masks)
+    ce_rows: torch.Tensor | None = None  # [R] int64 row index into the [B*P] prefix rows
+    ce_targets: torch.Tensor | None = None  # [R] int32
+    ce_weights: torch.Tensor | None = None  # [R] fp32  (gradient / loss weight of each row)
+    ce_sample: torch.Tensor | None = None  # [R] int64 sample of each row (metrics)
+    ce_inv_count: torch.Tensor | None = None  # [R] fp32 1/max(n_b,1) (metrics)
+    R: int = 0
+    n_active: float = 1.0
+    n_action: float = 1.0
+    sample_mask: torch.Tensor | None = None  # [B] fp32
+    h2d_bytes: int = 0
+
+
+class LAP:
+    EOS_TOKEN = 1
+    # expose for bench / tests
+    last_h2d_bytes = 0
+
+    def __init__(self, config: LAPConfig, seed: int = 0, init: bool = True, device: str | None = None,
+                 reference_zero_init: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("lap_b200.LAP needs a CUDA device (sm_100a); there is no CPU fallback")
+        ops.check_device()
+        self.config = config
+        self.cfg = config
+        self.device = torch.device(device or f"cuda:{torch.cuda.current_device()}")
+        cfg = config
+        if not (cfg.pi05 and cfg.enable_action_training and cfg.enable_langact_training):
+            raise NotImplementedError("engine implements the pi05 + action + lang-action configuration (LAP-3B)")
+        if cfg.enable_vqa_training or cfg.enable_prediction_training:
+            raise NotImplementedError("vqa / prediction loss heads are outside the hot path (SURVEY §8)")
+        self.layout = P.FlatLayout(cfg)
+        self.P = torch.zeros(self.layout.total, dtype=F32, device=self.device)
+        self.W16 = torch.zeros(self.layout.total, dtype=BF16, device=self.device)
+        D = cfg.gemma.width
+        self.E_split = torch.zeros(cfg.vocab_size, 2 * D, dtype=BF16, device=self.device)
+        self.G: torch.Tensor | None = None  # flat grads, allocated by the trainer
+        self._bufs: dict[str, torch.Tensor] = {}
+        hd = cfg.gemma.head_dim
+        ts = (10_000.0 ** ((2.0 / hd) * torch.arange(hd // 2, dtype=torch.float32))).to(self.device)
+        self.timescale = ts
+        self.ones = torch.ones(max(4096, 64), dtype=F32, device=self.device)
+        self.training_saved = False
+        if init:
+            self.init_random(seed, reference_zero_init=reference_zero_init)
+
+    # ------------------------------------------------------------------------------------------
+    # parameters
+    # ------------------------------------------------------------------------------------------
+    def init_random(self, seed: int, reference_zero_init: bool = True) -> None:
+        """Random init straight into the flat device buffer (same distributions as params.init_reference_params)."""
+        cfg = self.cfg
+        if self.layout.total < 50_000_000:
+            ref = P.init_reference_params(cfg, seed, reference_zero_init=reference_zero_init)
+            self.load_params(ref)
+            return
+        gen = torch.Generator(device=self.device).manual_seed(seed)
+        lay = self.layout
+        for name, shape in lay.shapes.items():
+            v = lay.view(self.P, name)
+            if name == "g.embed":
+                v.normal_(0.0, 0.01, generator=gen)
+            elif name in lay.kernel_names:
+                fan_in = shape[-1]
+                if name == "img.head_w" or name == "e.mod_w":
+                    if reference_zero_init:
+                        v.zero_()
+                    else:
+                        v.normal_(0.0, 0.02, generator=gen)
+                elif name.startswith("img."):
+                    lim = math.sqrt(6.0 / (shape[-1] + shape[-2]))
+                    v.uniform_(-lim, lim, generator=gen)
+                else:
+                    v.normal_(0.0, 1.0 / math.sqrt(fan_in), generator=gen)
+            elif name == "img.pos":
+                v.normal_(0.0, 1.0 / math.sqrt(shape[-1]), generator=gen)
+            elif name in ("img.ln0_s", "img.ln1_s", "img.enc_s"):
+                v.fill_(1.0)
+            else:
+                v.zero_()
+        self.refresh_compute_copy()
+
+    def load_params(self, tree: dict) -> None:
+        """Load a reference-layout tree ('/'-joined keys or nested dicts; torch or numpy leaves)."""
+        flat = tree if all(isinstance(k, str) and not isinstance(v, dict) for k, v in tree.items()) else P.from_nested(tree)
+        flat = {k: (v if isinstance(v, torch.Tensor) else torch.from_numpy(np.asarray(v))).to(torch.float32) for k, v in flat.items()}
+        want = P.reference_shapes(self.cfg)
+        missing = [k for k in want if k not in flat]
+        if missing:
+            raise ValueError(f"parameter tree is missing {len(missing)} keys, e.g. {missing[:3]}")
+        for k, s in want.items():
+            if tuple(flat[k].shape) != tuple(s):
+                raise ValueError(f"shape mismatch for {k}: got {tuple(flat[k].shape)}, expected {tuple(s)}")
+        eng = P.reference_to_engine(self.cfg, flat)
+        for name in self.layout.shapes:
+            self.layout.view(self.P, name).copy_(eng[name])
+        self.refresh_compute_copy()
+
+    def params_reference(self, flat: torch.Tensor | None = None) -> dict[str, torch.Tensor]:
+        """Reference-layout (CPU) view of a flat buffer (default: the master params)."""
+        flat = self.P if flat is None else flat
+        eng = {k: v.detach().float().cpu() for k, v in P.engine_from_flat(self.layout, flat).items()}
+        return P.engine_to_reference(self.cfg, eng)
+
+    def refresh_compute_copy(self) -> None:
+        """bf16 compute copy of the master params + hi/lo split of the fp32 embedding table."""
+        ops.cast_f32_bf16(self.P, self.W16)
+        self.refresh_embed_split()
+
+    def refresh_embed_split(self) -> None:
+        ops.split_hi_lo(self.p("g.embed"), self.E_split, self.cfg.vocab_size, self.cfg.gemma.width)
+
+    def p(self, name: str, l: int | None = None) -> torch.Tensor:
+        v = self.layout.view(self.P, name)
+        return v if l is None else v[l]
+
+    def w(self, name: str, l: int | None = None) -> torch.Tensor:
+        v = self.layout.view(self.W16, name)
+        return v if l is None else v[l]
+
+    def g(self, name: str, l: int | None = None) -> torch.Tensor:
+        v = self.layout.view(self.G, name)
+        return v if l is None else v[l]
+
+    def buf(self, name: str, shape, dtype=BF16, zero: bool = False) -> torch.Tensor:
+        shape = tuple(int(s) for s in shape)
+        t = self._bufs.get(name)
+        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+            t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
+            self._bufs[name] = t
+        return t
+
+    # ------------------------------------------------------------------------------------------
+    # input staging (host -> device); masks are tiny and are assembled on the host
+    # ------------------------------------------------------------------------------------------
+    def _stage(self, obs: Observation, actions=None, noise=None, time=None, *, with_loss: bool,
+               global_counts: tuple[float, float] | None = None) -> Staged:
+        cfg = self.cfg
+        dev = self.device
+        nbytes = 0
+
+        def up(x, dtype=None):
+            nonlocal nbytes
+            if isinstance(x, torch.Tensor):
+                t = x
+            else:
+                t = torch.from_numpy(np.ascontiguousarray(x))
+            if dtype is not None and t.dtype != dtype:
+                t = t.to(dtype)
+            if t.device != dev:
+                nbytes += t.numel() * t.element_size()
+                if not t.is_cuda and not t.is_pinned():
+                    t = t.pin_memory()
+                t = t.to(dev, non_blocking=True)
+            return t.contiguous()
+
+        images = []
+        for k in cfg.image_keys:
+            im = obs.images[k]
+            im_t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
+            if im_t.dtype != torch.uint8:
+                im_t = im_t.to(torch.float32)
+            if tuple(im_t.shape[1:3]) != (cfg.image_size, cfg.image_size):
+                raise ValueError(f"image {k} has resolution {tuple(im_t.shape[1:3])}; resize_with_pad is outside the "
+                                 f"hot path (model_adapter.py:113-116) — provide {cfg.image_size}x{cfg.image_size}")
+            images.append(up(im_t))
+        B = images[0].shape[0]
+        Np, L, C = cfg.num_patches, cfg.max_token_len, len(cfg.image_keys)
+        tokens = to_numpy(obs.tokenized_prompt).astype(np.int32)
+        prompt_mask = to_numpy(obs.tokenized_prompt_mask).astype(bool)
+        la = getattr(obs, "tokenized_langact_mask", None)
+        la = None if la is None else to_numpy(la).astype(bool)
+        img_masks = []
+        for k in cfg.image_keys:
+            m = obs.image_masks.get(k) if obs.image_masks is not None else None
+            m = np.ones(B, dtype=bool) if m is None else to_numpy(m).astype(bool)
+            img_masks.append(np.repeat(m[:, None], Np, axis=1))
+        pm = np.concatenate(img_masks + [prompt_mask], axis=1)  # lap.py:134-151
+        par = np.concatenate([np.zeros((B, C * Np), bool), la if la is not None else np.zeros((B, L), bool)], axis=1)
+        if la is not None:  # lap.py:303-325
+            pma = pm & ~np.concatenate([np.zeros((B, C * Np), bool), la], axis=1)
+        else:
+            pma = pm
+        A = cfg.action_horizon
+        st = Staged(B=B, images=images, tokens=up(tokens), pm=up(pm.astype(np.uint8)), par=up(par.astype(np.uint8)),
+                    pma=up(pma.astype(np.uint8)),
+                    sm=up(np.ones((B, A), np.uint8)), sar=up(np.tile(np.array([1] + [0] * (A - 1), np.uint8), (B, 1))))
+        if actions is not None:
+            st.actions = up(to_numpy(actions).astype(np.float32))
+        if noise is not None:
+            st.noise = up(to_numpy(noise).astype(np.float32))
+        if time is not None:
+            st.time = up(to_numpy(time).astype(np.float32))
+        if with_loss:
+            if la is None:
+                raise ValueError("compute_loss needs tokenized_langact_mask (lap.py:232)")
+            loss_mask_in = getattr(obs, "token_loss_mask", None)
+            tlm = np.ones((B, L), bool) if loss_mask_in is None else to_numpy(loss_mask_in).astype(bool)
+            sm_in = getattr(obs, "sample_mask", None)
+            smask = np.ones(B, bool) if sm_in is None else to_numpy(sm_in).astype(bool)
+            lm = la[:, 1:] & prompt_mask[:, 1:] & tlm[:, 1:] & smask[:, None]  # lap.py:231-237
+            n_b = np.maximum(lm.sum(-1), 1).astype(np.float32)
+            n_active_local = float(smask.sum()) if sm_in is not None else float(B)
+            n_active, n_action = global_counts if global_counts is not None else (n_active_local, float(B))
+            n_active = max(n_active, 1.0)
+            bb, jj = np.nonzero(lm)
+            R = len(bb)
+            Rp = max(_round_up(R, 128), 128)
+            rows = np.zeros(Rp, np.int64)
+            tgt = np.zeros(Rp, np.int32)
+            wts = np.zeros(Rp, np.float32)
+            smp = np.zeros(Rp, np.int64)
+            inv = np.zeros(Rp, np.float32)
+            rows[:R] = bb * cfg.prefix_len + C * Np + jj  # pre_logits[:, :-1][:, -(L-1):] -> prefix position C*Np + j
+            tgt[:R] = tokens[bb, jj + 1]
+            wts[:R] = cfg.language_loss_weight / (n_b[bb] * n_active)
+            smp[:R] = bb
+            inv[:R] = 1.0 / n_b[bb]
+            st.ce_rows, st.ce_targets, st.ce_weights = up(rows), up(tgt), up(wts)
+            st.ce_sample, st.ce_inv_count = up(smp), up(inv)
+            st.R = Rp
+            st.n_active, st.n_action = n_active, max(n_action, 1.0)
+            st.sample_mask = up(smask.astype(np.float32))
+        st.h2d_bytes = nbytes
+        LAP.last_h2d_bytes = nbytes
+        return st
+
+    # ------------------------------------------------------------------------------------------
+    # GEMM helpers.  Weights are [out, in] (K-major B of the forward GEMM).
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _dgrad(dY, W, dX, M, N, K, **kw):
+        """dX[M,K] = dY[M,N] @ W[N,K]  (B operand read MN-major)."""
+        ops.gemm(dY, W, dX, M=M, N=K, K=N, b_major=1, lda=N, ldb=K, ldc=K, **kw)
+
+    @staticmethod
+    def _wgrad(dY, X, dW, M, N, K, ldx=None, lddy=None, accumulate=False):
+        """dW[N,K] = dY[M,N]^T @ X[M,K]  (both operands read MN-major, fp32 out)."""
+        ops.gemm(dY, X, dW, M=N, N=K, K=M, a_major=1, b_major=1, lda=lddy if lddy is not None else N,
+                 ldb=ldx if ldx is not None else K, ldc=K, accumulate=accumulate)
+
+    # ------------------------------------------------------------------------------------------
+    # SigLIP tower (OP/models/siglip.py), all cameras in one pass, rows ordered (b, cam, patch)
+    # ------------------------------------------------------------------------------------------
+    def _siglip_fwd(self, st: Staged, X0: torch.Tensor, rows_per_sample: int, softmax_mode: int = 0) -> None:
+        cfg, s = self.cfg, self.cfg.siglip
+        B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
+        D = cfg.gemma.width
+        Ni, Ms = B * C, B * C * Np
+        pk = s.patch_size * s.patch_size * 3
+        patches = self.buf("img.patches", (Ms, pk), F32)
+        ops.patchify(st.images, patches, B, C, cfg.image_size, cfg.image_size, s.patch_size)
+        x = self.buf("img.x.0", (Ms, W))
+        ops.sgemm(patches, self.p("img.patch_w"), x, Ms, W, pk, pk, 1, pk, 1, ldc=W, bias=self.p("img.patch_b"),
+                  table=self.p("img.pos"), table_rows=Np)
+        q_div = _bf16_round(math.sqrt(hd))
+        for l in range(s.depth):
+            y0 = self.buf(f"img.y0.{l}", (Ms, W))
+            mean0, rstd0 = self.buf(f"img.mean0.{l}", (Ms,), F32), self.buf(f"img.rstd0.{l}", (Ms,), F32)
+            ops.layernorm_fwd(x, self.p("img.ln0_s", l), self.p("img.ln0_b", l), y0, mean0, rstd0, Ms, W)
+            qkv = self.buf(f"img.qkv.{l}", (Ms, 3 * W))
+            ops.gemm(y0, self.w("img.qkv_w", l), qkv, M=Ms, N=3 * W, K=W, bias=self.p("img.qkv_b", l),
+                     epi=ops.EPI_QSCALE, q_cols=W, q_div=q_div)
+            Pm = self.buf(f"img.P.{l}", (Ni, nh, Np, Np))
+            qf = qkv.view(-1)
+            ops.gemm(qf, qf[W:], Pm, M=Np, N=Np, K=hd, lda=3 * W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                     a_bs=(hd, Np * 3 * W), b_bs=(hd, Np * 3 * W), c_bs=(Np * Np, nh * Np * Np))
+            ops.vit_softmax_fwd(Pm, Ni * nh * Np, Np, Np, softmax_mode)
+            o = self.buf(f"img.o.{l}", (Ms, W))
+            ops.gemm(Pm, qf[2 * W:], o, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=W, batch_i=nh, batch_o=Ni,
+                     a_bs=(Np * Np, nh * Np * Np), b_bs=(hd, Np * 3 * W), c_bs=(hd, Np * W))
+            x1 = self.buf(f"img.x1.{l}", (Ms, W))
+            ops.gemm(o, self.w("img.out_w", l), x1, M=Ms, N=W, K=W, bias=self.p("img.out_b", l), epi=ops.EPI_RESID,
+                     resid=x)
+            y1 = self.buf(f"img.y1.{l}", (Ms, W))
+            mean1, rstd1 = self.buf(f"img.mean1.{l}", (Ms,), F32), self.buf(f"img.rstd1.{l}", (Ms,), F32)
+            ops.layernorm_fwd(x1, self.p("img.ln1_s", l), self.p("img.ln1_b", l), y1, mean1, rstd1, Ms, W)
+            hpre, hact = self.buf(f"img.hpre.{l}", (Ms, F)), self.buf(f"img.hact.{l}", (Ms, F))
+            ops.gemm(y1, self.w("img.fc1_w", l), hact, M=Ms, N=F, K=W, bias=self.p("img.fc1_b", l),
+                     epi=ops.EPI_BIAS_GELU, C2=hpre, ldc2=F)
+            x2 = self.buf(f"img.x.{l + 1}", (Ms, W))
+            ops.gemm(hact, self.w("img.fc2_w", l), x2, M=Ms, N=W, K=F, bias=self.p("img.fc2_b", l), epi=ops.EPI_RESID,
+                     resid=x1)
+            x = x2
+        yenc = self.buf("img.yenc", (Ms, W))
+        ops.layernorm_fwd(x, self.p("img.enc_s"), self.p("img.enc_b"), yenc, self.buf("img.mean_e", (Ms,), F32),
+                          self.buf("img.rstd_e", (Ms,), F32), Ms, W)
+        # head Dense -> image tokens written straight into the prefix rows [b, cam*Np + t]
+        ops.gemm(yenc, self.w("img.head_w"), X0, M=Np, N=D, K=W, bias=self.p("img.head_b"), batch_i=C, batch_o=B,
+                 a_bs=(Np * W, C * Np * W), c_bs=(Np * D, rows_per_sample * D), ldc=D)
+
+    def _siglip_bwd(self, st: Staged, dX0: torch.Tensor, rows_per_sample: int) -> None:
+        cfg, s = self.cfg, self.cfg.siglip
+        B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
+        D = cfg.gemma.width
+        Ni, Ms = B * C, B * C * Np
+        pk = s.patch_size * s.patch_size * 3
+        q_div = _bf16_round(math.sqrt(hd))
+        # image rows of dX0 -> contiguous [Ms, D]
+        dximg = self.buf("img.dximg", (Ms, D))
+        dximg.view(B, C * Np * D).copy_(dX0.view(B, rows_per_sample * D)[:, : C * Np * D])
+        yenc = self._bufs["img.yenc"]
+        self._wgrad(dximg, yenc, self.g("img.head_w"), Ms, D, W)
+        ops.colsum(dximg, D, self.g("img.head_b"), Ms, D)
+        dy = self.buf("img.dy", (Ms, W))
+        self._dgrad(dximg, self.w("img.head_w"), dy, Ms, D, W)
+        dx = self.buf("img.dx", (Ms, W))
+        ops.layernorm_bwd(dy, self._bufs[f"img.x.{s.depth}"], self.p("img.enc_s"), self._bufs["img.mean_e"],
+                          self._bufs["img.rstd_e"], None, dx, self.g("img.enc_s"), self.g("img.enc_b"), Ms, W)
+        dh = self.buf("img.dh", (Ms, F))
+        dqkv = self.buf("img.dqkv", (Ms, 3 * W))
+        do = self.buf("img.do", (Ms, W))
+        dP = self.buf("img.dP", (Ni, nh, Np, Np))
+        for l in reversed(range(s.depth)):
+            g = lambda n: self.g(n, l)
+            hact, hpre, y1, x1 = (self._bufs[f"img.{n}.{l}"] for n in ("hact", "hpre", "y1", "x1"))
+            # fc2
+            self._wgrad(dx, hact, g("img.fc2_w"), Ms, W, F)
+            ops.colsum(dx, W, g("img.fc2_b"), Ms, W)
+            self._dgrad(dx, self.w("img.fc2_w", l), dh, Ms, W, F)
+            ops.gelu_bwd(dh, hpre, Ms * F)
+            # fc1
+            self._wgrad(dh, y1, g("img.fc1_w"), Ms, F, W)
+            ops.colsum(dh, F, g("img.fc1_b"), Ms, F)
+            self._dgrad(dh, self.w("img.fc1_w", l), dy, Ms, F, W)
+            ops.layernorm_bwd(dy, x1, self.p("img.ln1_s", l), self._bufs[f"img.mean1.{l}"], self._bufs[f"img.rstd1.{l}"],
+                              dx, dx, g("img.ln1_s"), g("img.ln1_b"), Ms, W)
+            # out projection
+            o, qkv, Pm = (self._bufs[f"img.{n}.{l}"] for n in ("o", "qkv", "P"))
+            self._wgrad(dx, o, g("img.out_w"), Ms, W, W)
+            ops.colsum(dx, W, g("img.out_b"), Ms, W)
+            self._dgrad(dx, self.w("img.out_w", l), do, Ms, W, W)
+            # attention backward, batched over (image, head)
+            qf, dqf, dof = qkv.view(-1), dqkv.view(-1), do.view(-1)
+            bs_qkv, bs_o, bs_p = (hd, Np * 3 * W), (hd, Np * W), (Np * Np, nh * Np * Np)
+            # dP = dO V^T
+            ops.gemm(dof, qf[2 * W:], dP, M=Np, N=Np, K=hd, lda=W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                     a_bs=bs_o, b_bs=bs_qkv, c_bs=bs_p)
+            # dV = P^T dO
+            ops.gemm(Pm, dof, dqf[2 * W:], M=Np, N=hd, K=Np, a_major=1, b_major=1, lda=Np, ldb=W, ldc=3 * W,
+                     batch_i=nh, batch_o=Ni, a_bs=bs_p, b_bs=bs_o, c_bs=bs_qkv)
+            ops.softmax_bwd(Pm, dP, dP, Ni * nh * Np, Np)
+            # dQ_pre = (dS K) / q_div
+            ops.gemm(dP, qf[W:], dqf, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=3 * W, batch_i=nh, batch_o=Ni,
+                     a_bs=bs_p, b_bs=bs_qkv, c_bs=bs_qkv, epi=ops.EPI_QSCALE, q_cols=hd, q_div=q_div)
+            # dK = dS^T Q_scaled
+            ops.gemm(dP, qf, dqf[W:], M=Np, N=hd, K=Np, a_major=1, b_major=1, lda=Np, ldb=3 * W, ldc=3 * W,
+                     batch_i=nh, batch_o=Ni, a_bs=bs_p, b_bs=bs_qkv, c_bs=bs_qkv)
+            y0, x = self._bufs[f"img.y0.{l}"], self._bufs[f"img.x.{l}"]
+            self._wgrad(dqkv, y0, g("img.qkv_w"), Ms, 3 * W, W)
+            ops.colsum(dqkv, 3 * W, g("img.qkv_b"), Ms, 3 * W)
+            self._dgrad(dqkv, self.w("img.qkv_w", l), dy, Ms, 3 * W, W)
+            ops.layernorm_bwd(dy, x, self.p("img.ln0_s", l), self._bufs[f"img.mean0.{l}"], self._bufs[f"img.rstd0.{l}"],
+                              dx, dx, g("img.ln0_s"), g("img.ln0_b"), Ms, W)
+        # patch embedding: pos (sum over images), bias, kernel (fp32)
+        ops.colsum(dx, Np * W, self.g("img.pos"), Ni, Np * W)
+        ops.colsum(dx, W, self.g("img.patch_b"), Ms, W)
+        patches = self._bufs["img.patches"]
+        ops.sgemm(dx, patches, self.g("img.patch_w"), W, pk, Ms, 1, W, 1, pk, ldc=pk)
+
+    # ------------------------------------------------------------------------------------------
+    # suffix (flow-matching) embedding — fp32 (OP/models/pi0.py:139-186, lap.py:185-207)
+    # ------------------------------------------------------------------------------------------
+    def _suffix_embed(self, st: Staged, x_t: torch.Tensor | None, time: torch.Tensor, XE: torch.Tensor) -> None:
+        """action_in_proj(x_t) -> XE (bf16); time MLP -> cond (fp32) and cond16 (bf16).  If x_t is None it is
+        built from (actions, noise, time) together with u_t."""
+        cfg = self.cfg
+        B, A, ad, D1 = st.B, cfg.action_horizon, cfg.action_dim, cfg.expert.width
+        te = self.buf("suf.te", (B, D1), F32)
+        if x_t is None:
+            x_t = self.buf("suf.x_t", (B, A * ad), F32)
+            u_t = self.buf("suf.u_t", (B, A * ad), F32)
+            ops.suffix_inputs(st.actions, st.noise, time, x_t, u_t, te, B, A * ad, D1)
+        else:
+            ops.suffix_inputs(None, None, time, None, None, te, B, A * ad, D1)
+        ops.sgemm(x_t, self.p("action_in_w"), XE, B * A, D1, ad, ad, 1, ad, 1, ldc=D1, bias=self.p("action_in_b"))
+        z1, s1 = self.buf("suf.z1", (B, D1), F32), self.buf("suf.s1", (B, D1), F32)
+        z2, cond = self.buf("suf.z2", (B, D1), F32), self.buf("suf.cond", (B, D1), F32)
+        cond16 = self.buf("suf.cond16", (B, D1))
+        ops.sgemm(te, self.p("time_in_w"), z1, B, D1, D1, D1, 1, D1, 1, bias=self.p("time_in_b"))
+        ops.swish_fwd(z1, s1, None, B * D1)
+        ops.sgemm(s1, self.p("time_out_w"), z2, B, D1, D1, D1, 1, D1, 1, bias=self.p("time_out_b"))
+        ops.swish_fwd(z2, cond, cond16, B * D1)
+        # all 2L+1 adaRMS modulation Dense layers in one GEMM: mod[b, i*3D1 : (i+1)*3D1]
+        nm = P.n_mod(cfg)
+        mod = self.buf("suf.mod", (B, nm * 3 * D1))
+        ops.gemm(cond16, self.w("e.mod_w"), mod, M=B, N=nm * 3 * D1, K=D1, bias=self.p("e.mod_b").view(-1))
+
+    # ------------------------------------------------------------------------------------------
+    # Gemma multi-expert transformer (src/lap/models/backbones/gemma.py:455-531)
+    # ------------------------------------------------------------------------------------------
+    def _gemma_fwd(self, B: int, X, XE, bits, positions, *, save: bool, kv_cache=None, write_cache=None,
+                   tag: str = "g"):
+        """Runs the depth-L stack.  X: prefix rows [B*P, D] or None; XE: suffix rows [B*A, D1] or None.
+        kv_cache=(K,V) [L,B,Tpad,hd] already holding the prefix (suffix-only pass); write_cache=(K,V) to fill
+        (prefix-only pass).  Returns (X_out, XE_out) — the residual streams BEFORE the final norm."""
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        Pn = cfg.prefix_len if (X is not None or kv_cache is not None) else 0
+        A = cfg.action_horizon if XE is not None else 0
+        T = Pn + A
+        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 32)
+        W32 = Tpad // 32
+        D, D1, hd, NH = g.width, e.width, g.head_dim, g.num_heads
+        QKV = (NH + 2) * hd
+        F, F1 = g.mlp_dim, e.mlp_dim
+        Mg, Me = B * Pn if X is not None else 0, B * A
+        t_begin = Pn if X is None else 0
+        Tq = T - t_begin
+        nm3 = P.n_mod(cfg) * 3 * D1
+        mod = self._bufs.get("suf.mod")
+        sv = (lambda n, l: f"{tag}.{n}.{l}") if save else (lambda n, l: f"{tag}.{n}.tmp")
+        qscale = hd ** -0.5
+        for l in range(g.depth):
+            if kv_cache is not None:
+                Kc, Vc = kv_cache[0][l], kv_cache[1][l]
+            elif write_cache is not None:
+                Kc, Vc = write_cache[0][l], write_cache[1][l]
+            else:
+                Kc = self.buf(sv("Kc", l), (B, Tpad, hd), zero=True)
+                Vc = self.buf(sv("Vc", l), (B, Tpad, hd), zero=True)
+            qkv0 = qkv1 = None
+            if X is not None:
+                h = self.buf(sv("h", l), (Mg, D))
+                rstd = self.buf(sv("rstd", l), (Mg,), F32)
+                ops.rmsnorm_fwd(X, h, rstd, Mg, D, scale=self.p("g.attn_norm_s", l))
+                qkv0 = self.buf(f"{tag}.qkv0", (Mg, QKV))
+                ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
+            if XE is not None:
+                hE = self.buf(sv("hE", l), (Me, D1))
+                rstdE = self.buf(sv("rstdE", l), (Me,), F32)
+                ops.rmsnorm_fwd(XE, hE, rstdE, Me, D1, mod=mod.view(-1)[(2 * l) * 3 * D1:], ldmod=nm3, rows_per_sample=A)
+                qkv1 = self.buf(f"{tag}.qkv1", (Me, QKV))
+                ops.gemm(hE, self.w("e.qkv_w", l), qkv1, M=Me, N=QKV, K=D1)
+            Q = self.buf(sv("Q", l), (B, Tq, NH, hd))
+            ops.rope_fwd(qkv0, qkv1, positions, self.timescale, Q, Kc, Vc, B, Pn, A, Tpad, NH, hd, t_begin, qscale)
+            R = Tq * NH
+            S = self.buf(f"{tag}.S", (B, R, Tpad), F32)
+            ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
+                     c_bs=(R * Tpad, 0))
+            Pm = self.buf(sv("P", l), (B, R, Tpad))
+            ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, T, Tpad, W32)
+            Oc = self.buf(f"{tag}.Oc", (B, R, hd))
+            ops.gemm(Pm, Vc, Oc, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                     a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
+            if X is not None:
+                O0 = self.buf(sv("O0", l), (Mg, NH * hd))
+                O0.view(B, Pn * NH * hd).copy_(Oc.view(B, R * hd)[:, : Pn * NH * hd])
+                X1 = self.buf(sv("X1", l), (Mg, D))
+                ops.gemm(O0, self.w("g.o_w", l), X1, M=Mg, N=D, K=NH * hd, epi=ops.EPI_RESID, resid=X)
+                h2 = self.buf(sv("h2", l), (Mg, D))
+                rstd2 = self.buf(sv("rstd2", l), (Mg,), F32)
+                ops.rmsnorm_fwd(X1, h2, rstd2, Mg, D, scale=self.p("g.ffn_norm_s", l))
+                act = self.buf(f"{tag}.act", (Mg, F))
+                GU = self.buf(sv("GU", l), (Mg, 2 * F))
+                ops.gemm(h2, self.w("g.gu_w", l), act, M=Mg, N=F, K=D, epi=ops.EPI_GEGLU, C2=GU, ldc2=2 * F)
+                X2 = self.buf(sv("X", l + 1), (Mg, D))
+                ops.gemm(act, self.w("g.down_w", l), X2, M=Mg, N=D, K=F, epi=ops.EPI_RESID, resid=X1)
+                X = X2
+            if XE is not None:
+                O1 = self.buf(sv("O1", l), (Me, NH * hd))
+                if X is not None or Pn == 0 or t_begin == 0:
+                    O1.view(B, A * NH * hd).copy_(Oc.view(B, R * hd)[:, (Tq - A) * NH * hd:])
+                else:
+                    O1 = Oc.view(Me, NH * hd)
+                gate_a = mod.view(-1)[(2 * l) * 3 * D1 + 2 * D1:]
+                gate_f = mod.view(-1)[(2 * l + 1) * 3 * D1 + 2 * D1:]
+                XE1 = self.buf(sv("XE1", l), (Me, D1))
+                yEa = self.buf(sv("yEa", l), (Me, D1))
+                ops.gemm(O1, self.w("e.o_w", l), XE1, M=Me, N=D1, K=NH * hd, epi=ops.EPI_GATED_RESID, resid=XE,
+                         gate=gate_a, ldg=nm3, gate_rows=A, C2=yEa, ldc2=D1)
+                hE2 = self.buf(sv("hE2", l), (Me, D1))
+                rstdE2 = self.buf(sv("rstdE2", l), (Me,), F32)
+                ops.rmsnorm_fwd(XE1, hE2, rstdE2, Me, D1, mod=mod.view(-1)[(2 * l + 1) * 3 * D1:], ldmod=nm3,
+                                rows_per_sample=A)
+                actE = self.buf(sv("actE", l), (Me, F1))
+                GUE = self.buf(sv("GUE", l), (Me, 2 * F1))
+                ops.gemm(hE2, self.w("e.gu_w", l), actE, M=Me, N=F1, K=D1, epi=ops.EPI_GEGLU, C2=GUE, ldc2=2 * F1)
+                XE2 = self.buf(sv("XE", l + 1), (Me, D1))
+                yEf = self.buf(sv("yEf", l), (Me, D1))
+                ops.gemm(actE, self.w("e.down_w", l), XE2, M=Me, N=D1, K=F1, epi=ops.EPI_GATED_RESID, resid=XE1,
+                         gate=gate_f, ldg=nm3, gate_rows=A, C2=yEf, ldc2=D1)
+                XE = XE2
+        return X, XE
+
+    # ------------------------------------------------------------------------------------------
+    # training forward (+ loss)
+    # ------------------------------------------------------------------------------------------
+    def _forward_loss(self, st: Staged, *, save: bool, compute_grad_seed: bool, softmax_mode: int = 0):
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
+        C, Np = len(cfg.image_keys), cfg.num_patches
+        D, D1, ad, V = g.width, e.width, cfg.action_dim, cfg.vocab_size
+        T = Pn + A
+        Tpad = _round_up(T, 32)
+        Mg, Me = B * Pn, B * A
+        sv0 = "g.X.0" if save else "g.X.tmp0"
+        X0 = self.buf(sv0, (Mg, D))
+        self._siglip_fwd(st, X0, Pn, softmax_mode)
+        ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
+        XE0 = self.buf("g.XE.0" if save else "g.XE.tmp0", (Me, D1))
+        self._suffix_embed(st, None, st.time, XE0)
+        bits = self.buf("mask.bits", (B, T, Tpad // 32), torch.int32)
+        positions = self.buf("mask.pos", (B, T), torch.int32)
+        ops.mask_build(st.pm, st.par, st.pma, st.sm, st.sar, bits, positions, B, Pn, A, Tpad // 32)
+        X, XE = self._gemma_fwd(B, X0, XE0, bits, positions, save=save)
+        # ---- language loss: only rows that carry loss go through final norm + LM head (masked rows weigh 0) ----
+        R = st.R
+        pre2 = self.buf("loss.pre2", (R, 2 * D))
+        rstdF = self.buf("loss.rstdF", (R,), F32)
+        ops.rmsnorm_fwd(X, pre2, rstdF, R, D, scale=self.p("g.final_norm_s"), row_idx=st.ce_rows, ldy=2 * D, dup=True)
+        logits = self.buf("loss.logits", (R, V), F32)
+        ops.gemm(pre2, self.E_split, logits, M=R, N=V, K=2 * D)
+        nll = self.buf("loss.nll", (R,), F32)
+        dlogits = self.buf("loss.dlogits", (R, V)) if compute_grad_seed else None
+        ops.ce_fwd_bwd(logits, V, st.ce_targets, st.ce_weights, nll, dlogits, V, R, V)
+        # ---- action loss ----
+        nm3 = P.n_mod(cfg) * 3 * D1
+        mod = self._bufs["suf.mod"]
+        sufout = self.buf("loss.sufout", (Me, D1))
+        rstdEF = self.buf("loss.rstdEF", (Me,), F32)
+        ops.rmsnorm_fwd(XE, sufout, rstdEF, Me, D1, mod=mod.view(-1)[(P.n_mod(cfg) - 1) * 3 * D1:], ldmod=nm3,
+                        rows_per_sample=A)
+        v = self.buf("loss.v", (Me, ad), F32)
+        ops.sgemm(sufout, self.p("action_out_w"), v, Me, ad, D1, D1, 1, D1, 1, ldc=ad, bias=self.p("action_out_b"))
+        aloss = self.buf("loss.aloss", (B,), F32)
+        dv = self.buf("loss.dv", (Me, ad), F32) if compute_grad_seed else None
+        ops.mse_fwd_bwd(v, self._bufs["suf.u_t"], aloss, dv, B, A * ad, cfg.action_loss_weight / st.n_action)
+        loss = self.buf("loss.total", (1,), F32)
+        ops.weighted_sum(nll, st.ce_weights, loss, R, 1.0, False)
+        ops.weighted_sum(aloss, None, loss, B, cfg.action_loss_weight / st.n_action, True)
+        return loss, (X, XE)
+
+    def _metrics(self, st: Staged) -> dict[str, torch.Tensor]:
+        """Scalar metrics of lap.py:260,300,548-554,567 from the per-row nll / per-sample action loss (tiny arrays)."""
+        nll, aloss = self._bufs["loss.nll"], self._bufs["loss.aloss"]
+        per_sample = torch.zeros(st.B, dtype=F32, device=self.device)
+        per_sample.index_add_(0, st.ce_sample, nll * st.ce_inv_count)
+        m = {"lang_loss": per_sample.mean(), "action_loss": aloss.mean()}
+        m["langact_loss"] = (per_sample * st.sample_mask).sum() / st.sample_mask.sum().clamp_min(1.0)
+        return m
+
+    def compute_loss(self, rng, observation: Observation, actions, *, train: bool = False, stage_config=None,
+                     verbose_mode=None, return_augmented_images: bool = False, noise=None, time=None):
+        """lap.py:380-602.  Returns (loss, metrics) — 0-d CUDA tensors.  `noise` [B,A,ad] and `time` [B] replace the
+        reference's jax.random draws (lap.py:193-194); if omitted they are drawn from torch's generator seeded by rng."""
+        cfg = self.cfg
+        if train and cfg.enable_image_augmentation:
+            raise NotImplementedError("augmax image augmentation is a 'next' row (SURVEY §8f N4); "
+                                      "lap_libero runs with enable_image_augmentation=False")
+        B = to_numpy(actions).shape[0] if not isinstance(actions, torch.Tensor) else actions.shape[0]
+        if noise is None or time is None:
+            gen = torch.Generator().manual_seed(int(rng) if rng is not None else 0)
+            if noise is None:
+                noise = torch.randn((B, cfg.action_horizon, cfg.action_dim), generator=gen)
+            if time is None:
+                time = torch.distributions.Beta(1.5, 1.0).sample((B,)) * 0.999 + 0.001
+        st = self._stage(observation, actions, noise, time, with_loss=True)
+        loss, _ = self._forward_loss(st, save=False, compute_grad_seed=False)
+        metrics = self._metrics(st)
+        return loss[0].clone(), metrics
+
+    # ------------------------------------------------------------------------------------------
+    # backward
+    # ------------------------------------------------------------------------------------------
+    def forward_backward(self, st: Staged, *, zero_grads: bool = True, softmax_mode: int = 0):
+        """Forward + hand-written backward; fills self.G (flat fp32 grads).  Returns the loss (device scalar [1])."""
+        assert self.G is not None, "allocate model.G (flat grads) first"
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        lay = self.layout
+        if zero_grads:
+            self.G[lay.small_begin:].zero_()  # atomically-accumulated small tensors; GEMM wgrads overwrite theirs
+        loss, (XL, XEL) = self._forward_loss(st, save=True, compute_grad_seed=True, softmax_mode=softmax_mode)
+        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
+        C, Np = len(cfg.image_keys), cfg.num_patches
+        D, D1, ad, V = g.width, e.width, cfg.action_dim, cfg.vocab_size
+        hd, NH = g.head_dim, g.num_heads
+        QKV = (NH + 2) * hd
+        F, F1 = g.mlp_dim, e.mlp_dim
+        T = Pn + A
+        Tpad = _round_up(T, 32)
+        Mg, Me, R = B * Pn, B * A, st.R
+        Rq = T * NH
+        nm = P.n_mod(cfg)
+        nm3 = nm * 3 * D1
+        mod = self._bufs["suf.mod"]
+        dmod = self.buf("bwd.dmod", (B, nm3), zero=True)
+        dmod.zero_()
+        bufs = self._bufs
+        # ---- action head ----
+        dv, sufout = bufs["loss.dv"], bufs["loss.sufout"]
+        ops.sgemm(dv, sufout, self.g("action_out_w"), ad, D1, Me, 1, ad, 1, D1, ldc=D1)
+        ops.sgemm(self.ones, dv, self.g("action_out_b"), 1, ad, Me, 0, 1, 1, ad, ldc=ad)
+        dsuf = self.buf("bwd.dsuf", (Me, D1))
+        ops.sgemm(dv, self.p("action_out_w"), dsuf, Me, D1, ad, ad, 1, 1, D1, ldc=D1)
+        dXE = self.buf("bwd.dXE", (Me, D1))
+        ops.ada_rmsnorm_bwd(dsuf, XEL, mod.view(-1)[(nm - 1) * 3 * D1:], nm3, bufs["loss.rstdEF"], None, dXE,
+                            dmod.view(-1)[(nm - 1) * 3 * D1:], nm3, B, A, D1)
+        # ---- LM head ----
+        dlogits, pre2 = bufs["loss.dlogits"], bufs["loss.pre2"]
+        dpre = self.buf("bwd.dpre", (R, D))
+        self._dgrad(dlogits, self.w("g.embed"), dpre, R, V, D)
+        self._wgrad(dlogits, pre2, self.g("g.embed"), R, V, D, ldx=2 * D)  # overwrites the whole table gradient
+        dX = self.buf("bwd.dX", (Mg, D))
+        dX.zero_()
+        ops.rmsnorm_bwd(dpre, XL, self.p("g.final_norm_s"), bufs["loss.rstdF"], None, dX, self.g("g.final_norm_s"),
+                        R, D, row_idx=st.ce_rows)
+        # ---- transformer layers ----
+        dact = self.buf("bwd.dact", (Mg, F))
+        dh = self.buf("bwd.dh", (Mg, D))
+        dqkv0 = self.buf("bwd.dqkv0", (Mg, QKV))
+        dO0 = self.buf("bwd.dO0", (Mg, NH * hd))
+        dyE = self.buf("bwd.dyE", (Me, D1))
+        dactE = self.buf("bwd.dactE", (Me, F1))
+        dhE = self.buf("bwd.dhE", (Me, D1))
+        dqkv1 = self.buf("bwd.dqkv1", (Me, QKV))
+        dO1 = self.buf("bwd.dO1", (Me, NH * hd))
+        dOc = self.buf("bwd.dOc", (B, Rq, hd))
+        dP = self.buf("bwd.dP", (B, Rq, Tpad))
+        dQ = self.buf("bwd.dQ", (B, Rq, hd))
+        dKc = self.buf("bwd.dKc", (B, Tpad, hd))
+        dVc = self.buf("bwd.dVc", (B, Tpad, hd))
+        positions = bufs["mask.pos"]
+        qscale = hd ** -0.5
+        for l in reversed(range(g.depth)):
+            sv = lambda n: bufs[f"g.{n}.{l}"]
+            # ===== MLP, prefix expert =====
+            GU, h2, X1 = sv("GU"), sv("h2"), sv("X1")
+            self._dgrad(dX, self.w("g.down_w", l), dact, Mg, D, F)
+            ops.geglu_bwd(dact, GU, Mg, F)  # dact <- act, GU <- [dg|du]
+            self._wgrad(dX, dact, self.g("g.down_w", l), Mg, D, F)
+            self._wgrad(GU, h2, self.g("g.gu_w", l), Mg, 2 * F, D)
+            self._dgrad(GU, self.w("g.gu_w", l), dh, Mg, 2 * F, D)
+            ops.rmsnorm_bwd(dh, X1, self.p("g.ffn_norm_s", l), sv("rstd2"), dX, dX, self.g("g.ffn_norm_s", l), Mg, D)
+            # ===== MLP, action expert =====
+            GUE, hE2, XE1 = sv("GUE"), sv("hE2"), sv("XE1")
+            ops.gated_bwd(dXE, sv("yEf"), mod.view(-1)[(2 * l + 1) * 3 * D1 + 2 * D1:], nm3, dyE,
+                          dmod.view(-1)[(2 * l + 1) * 3 * D1 + 2 * D1:], nm3, B, A, D1)
+            self._dgrad(dyE, self.w("e.down_w", l), dactE, Me, D1, F1)
+            ops.geglu_bwd(dactE, GUE, Me, F1)
+            self._wgrad(dyE, dactE, self.g("e.down_w", l), Me, D1, F1)
+            self._wgrad(GUE, hE2, self.g("e.gu_w", l), Me, 2 * F1, D1)
+            self._dgrad(GUE, self.w("e.gu_w", l), dhE, Me, 2 * F1, D1)
+            ops.ada_rmsnorm_bwd(dhE, XE1, mod.view(-1)[(2 * l + 1) * 3 * D1:], nm3, sv("rstdE2"), dXE, dXE,
+                                dmod.view(-1)[(2 * l + 1) * 3 * D1:], nm3, B, A, D1)
+            # ===== attention output projections =====
+            O0, O1 = sv("O0"), sv("O1")
+            self._wgrad(dX, O0, self.g("g.o_w", l), Mg, D, NH * hd)
+            self._dgrad(dX, self.w("g.o_w", l), dO0, Mg, D, NH * hd)
+            ops.gated_bwd(dXE, sv("yEa"), mod.view(-1)[(2 * l) * 3 * D1 + 2 * D1:], nm3, dyE,
+                          dmod.view(-1)[(2 * l) * 3 * D1 + 2 * D1:], nm3, B, A, D1)
+            self._wgrad(dyE, O1, self.g("e.o_w", l), Me, D1, NH * hd)
+            self._dgrad(dyE, self.w("e.o_w", l), dO1, Me, D1, NH * hd)
+            dOc.view(B, Rq * hd)[:, : Pn * NH * hd].copy_(dO0.view(B, Pn * NH * hd))
+            dOc.view(B, Rq * hd)[:, Pn * NH * hd:].copy_(dO1.view(B, A * NH * hd))
+            # ===== shared attention =====
+            Pm, Q, Kc, Vc = sv("P"), sv("Q"), sv("Kc"), sv("Vc")
+            bsR, bsT, bsP = (Rq * hd, 0), (Tpad * hd, 0), (Rq * Tpad, 0)
+            ops.gemm(dOc, Vc, dP, M=Rq, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=bsR, b_bs=bsT, c_bs=bsP)
+            ops.gemm(Pm, dOc, dVc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                     a_bs=bsP, b_bs=bsR, c_bs=bsT)
+            ops.softmax_bwd(Pm, dP, dP, B * Rq, Tpad)
+            ops.gemm(dP, Kc, dQ, M=Rq, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B, a_bs=bsP,
+                     b_bs=bsT, c_bs=bsR)
+            ops.gemm(dP, Q, dKc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                     a_bs=bsP, b_bs=bsR, c_bs=bsT)
+            ops.rope_bwd(dQ, dKc, dVc, positions, self.timescale, dqkv0, dqkv1, B, Pn, A, Tpad, NH, hd, qscale)
+            # ===== QKV projections + pre-attention norms =====
+            h, X = sv("h"), sv("X")
+            self._wgrad(dqkv0, h, self.g("g.qkv_w", l), Mg, QKV, D)
+            self._dgrad(dqkv0, self.w("g.qkv_w", l), dh, Mg, QKV, D)
+            ops.rmsnorm_bwd(dh, X, self.p("g.attn_norm_s", l), sv("rstd"), dX, dX, self.g("g.attn_norm_s", l), Mg, D)
+            hE, XE = sv("hE"), sv("XE")
+            self._wgrad(dqkv1, hE, self.g("e.qkv_w", l), Me, QKV, D1)
+            self._dgrad(dqkv1, self.w("e.qkv_w", l), dhE, Me, QKV, D1)
+            ops.ada_rmsnorm_bwd(dhE, XE, mod.view(-1)[(2 * l) * 3 * D1:], nm3, sv("rstdE"), dXE, dXE,
+                                dmod.view(-1)[(2 * l) * 3 * D1:], nm3, B, A, D1)
+        # ---- text embedding (scatter-add on top of the LM-head table gradient) ----
+        ops.embed_bwd(st.tokens, dX, self.g("g.embed"), B, L, C * Np, Pn, D, math.sqrt(D))
+        # ---- adaRMS modulation Dense + time MLP + action_in_proj ----
+        cond16 = bufs["suf.cond16"]
+        self._wgrad(dmod, cond16, self.g("e.mod_w").view(nm3, D1), B, nm3, D1)
+        ops.colsum(dmod, nm3, self.g("e.mod_b").view(-1), B, nm3)
+        dcond16 = self.buf("bwd.dcond16", (B, D1))
+        self._dgrad(dmod, self.w("e.mod_w").view(nm3, D1), dcond16, B, nm3, D1)
+        z1, s1, z2, te = bufs["suf.z1"], bufs["suf.s1"], bufs["suf.z2"], bufs["suf.te"]
+        dz2, ds1, dz1 = (self.buf(f"bwd.{n}", (B, D1), F32) for n in ("dz2", "ds1", "dz1"))
+        ops.swish_bwd(z2, None, dcond16, dz2, B * D1)
+        ops.sgemm(dz2, s1, self.g("time_out_w"), D1, D1, B, 1, D1, 1, D1, ldc=D1)
+        ops.sgemm(self.ones, dz2, self.g("time_out_b"), 1, D1, B, 0, 1, 1, D1, ldc=D1)
+        ops.sgemm(dz2, self.p("time_out_w"), ds1, B, D1, D1, D1, 1, 1, D1, ldc=D1)
+        ops.swish_bwd(z1, ds1, None, dz1, B * D1)
+        ops.sgemm(dz1, te, self.g("time_in_w"), D1, D1, B, 1, D1, 1, D1, ldc=D1)
+        ops.sgemm(self.ones, dz1, self.g("time_in_b"), 1, D1, B, 0, 1, 1, D1, ldc=D1)
+        x_t = bufs["suf.x_t"]
+        ops.sgemm(dXE, x_t, self.g("action_in_w"), D1, ad, Me, 1, D1, 1, ad, ldc=ad)
+        ops.colsum(dXE, D1, self.g("action_in_b"), Me, D1)
+        # ---- SigLIP ----
+        self._siglip_bwd(st, dX, Pn)
+        return loss
+
+    # ------------------------------------------------------------------------------------------
+    # inference: prefix pass -> KV cache -> Euler steps  (lap.py:605-675)
+    # ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def sample_actions(self, rng, observation: Observation, *, num_steps: int = 10, noise=None) -> torch.Tensor:
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        st = self._stage(observation, with_loss=False)
+        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
+        C, Np = len(cfg.image_keys), cfg.num_patches
+        D, D1, ad = g.width, e.width, cfg.action_dim
+        T = Pn + A
+        Tpad = _round_up(T, 32)
+        W32 = Tpad // 32
+        if noise is None:
+            gen = torch.Generator().manual_seed(int(rng) if rng is not None else 0)
+            noise = torch.randn((B, A, ad), generator=gen)
+        noise_t = noise if isinstance(noise, torch.Tensor) else torch.from_numpy(np.asarray(noise))
+        x = self.buf("inf.x", (B, A * ad), F32)
+        x.copy_(noise_t.to(torch.float32).reshape(B, A * ad), non_blocking=True)
+        # ---- prefix pass fills the cache ----
+        X0 = self.buf("inf.X0", (B * Pn, D))
+        self._siglip_fwd(st, X0, Pn)
+        ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
+        bits_p = self.buf("inf.bits_p", (B, Pn, W32), torch.int32)
+        pos_p = self.buf("inf.pos_p", (B, Pn), torch.int32)
+        ops.mask_build(st.pm, st.par, None, None, None, bits_p, pos_p, B, Pn, 0, W32)
+        Kc = self.buf("inf.Kc", (g.depth, B, Tpad, g.head_dim), zero=True)
+        Vc = self.buf("inf.Vc", (g.depth, B, Tpad, g.head_dim), zero=True)
+        self._gemma_prefix_only(B, X0, bits_p, pos_p, (Kc, Vc))
+        # ---- suffix rows: mask [B, A, P+A] and positions (lap.py:641-654; prefix part = prefix_mask alone) ----
+        bits_s = self.buf("inf.bits_s", (B, A, W32), torch.int32)
+        pos_s = self.buf("inf.pos_s", (B, A), torch.int32)
+        ops.mask_build(st.pm, st.par, st.pm, st.sm, st.sar, bits_s, pos_s, B, Pn, A, W32, row_begin=Pn, infer_rows=True)
+        dt = -1.0 / num_steps
+        t = 1.0
+        tbuf = self.buf("inf.t", (B,), F32)
+        XE0 = self.buf("inf.XE0", (B * A, D1))
+        sufout = self.buf("inf.sufout", (B * A, D1))
+        rstd = self.buf("inf.rstd", (B * A,), F32)
+        v = self.buf("inf.v", (B * A, ad), F32)
+        nm = P.n_mod(cfg)
+        nm3 = nm * 3 * D1
+        n_iter = 0
+        while t >= -dt / 2:  # lap.py:669-672: exactly num_steps iterations
+            tbuf.fill_(t)
+            self._suffix_embed(st, x, tbuf, XE0)
+            _, XE = self._gemma_fwd(B, None, XE0, bits_s, pos_s, save=False, kv_cache=(Kc, Vc), tag="inf")
+            mod = self._bufs["suf.mod"]
+            ops.rmsnorm_fwd(XE, sufout, rstd, B * A, D1, mod=mod.view(-1)[(nm - 1) * 3 * D1:], ldmod=nm3,
+                            rows_per_sample=A)
+            ops.sgemm(sufout, self.p("action_out_w"), v, B * A, ad, D1, D1, 1, D1, 1, ldc=ad,
+                      bias=self.p("action_out_b"))
+            ops.axpy(x, v, dt, B * A * ad)
+            t += dt
+            n_iter += 1
+        assert n_iter == num_steps
+        return x.view(B, A, ad).clone()
+
+    def _gemma_prefix_only(self, B, X0, bits, positions, cache):
+        """Prefix-only pass (lap.py:627): expert 0 alone, K/V (post-RoPE) written into the cache."""
+        cfg = self.cfg
+        # reuse the generic layer loop with A = 0 by temporarily viewing the sequence as prefix-only
+        self._gemma_fwd_prefix(B, X0, bits, positions, cache)
+
+    def _gemma_fwd_prefix(self, B, X, bits, positions, cache):
+        cfg, g = self.cfg, self.cfg.gemma
+        Pn = cfg.prefix_len
+        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 32)
+        W32 = Tpad // 32
+        D, hd, NH, F = g.width, g.head_dim, g.num_heads, g.mlp_dim
+        QKV = (NH + 2) * hd
+        Mg = B * Pn
+        R = Pn * NH
+        qscale = hd ** -0.5
+        for l in range(g.depth):
+            Kc, Vc = cache[0][l], cache[1][l]
+            h = self.buf("inf.h", (Mg, D))
+            rstd = self.buf("inf.rstdp", (Mg,), F32)
+            ops.rmsnorm_fwd(X, h, rstd, Mg, D, scale=self.p("g.attn_norm_s", l))
+            qkv0 = self.buf("inf.qkv0", (Mg, QKV))
+            ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
+            Q = self.buf("inf.Qp", (B, Pn, NH, hd))
+            ops.rope_fwd(qkv0, None, positions, self.timescale, Q, Kc, Vc, B, Pn, 0, Tpad, NH, hd, 0, qscale)
+            S = self.buf("inf.Sp", (B, R, Tpad), F32)
+            ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
+                     c_bs=(R * Tpad, 0))
+            Pm = self.buf("inf.Pp", (B, R, Tpad))
+            ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, Pn, Tpad, W32)
+            O0 = self.buf("inf.O0", (Mg, NH * hd))
+            ops.gemm(Pm, Vc, O0, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                     a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
+            X1 = self.buf("inf.X1", (Mg, D))
+            ops.gemm(O0, self.w("g.o_w", l), X1, M=Mg, N=D, K=NH * hd, epi=ops.EPI_RESID, resid=X)
+            h2 = self.buf("inf.h2", (Mg, D))
+            ops.rmsnorm_fwd(X1, h2, rstd, Mg, D, scale=self.p("g.ffn_norm_s", l))
+            act = self.buf("inf.act", (Mg, F))
+            ops.gemm(h2, self.w("g.gu_w", l), act, M=Mg, N=F, K=D, epi=ops.EPI_GEGLU, C2=None)
+            X2 = self.buf(f"inf.Xp{l % 2}", (Mg, D))
+            ops.gemm(act, self.w("g.down_w", l), X2, M=Mg, N=D, K=F, epi=ops.EPI_RESID, resid=X1)
+            X = X2
+        return X

@@ -114,3 +114,170 @@ def gemm(
     check(lib().lapb200_gemm_bf16(ctypes.byref(p), _stream()), "gemm_bf16")
     _count()
     return C
+
+
+# ---------------------------------------------------------------------------------------------
+# generic caller for the "plain" entry points: tensors -> void*, int -> int64, float -> float, + stream
+# ---------------------------------------------------------------------------------------------
+def _conv(a):
+    if a is None:
+        return ctypes.c_void_p(0)
+    if isinstance(a, torch.Tensor):
+        if not a.is_cuda:
+            raise RuntimeError("lap_b200 ops require CUDA tensors (there is no CPU fallback)")
+        return ctypes.c_void_p(a.data_ptr())
+    if isinstance(a, bool):
+        return ctypes.c_int64(int(a))
+    if isinstance(a, int):
+        return ctypes.c_int64(a)
+    if isinstance(a, float):
+        return ctypes.c_float(a)
+    raise TypeError(f"unsupported argument type {type(a)}")
+
+
+def call(name: str, *args) -> None:
+    fn = getattr(lib(), "lapb200_" + name)
+    rc = fn(*[_conv(a) for a in args], _stream())
+    check(rc, name)
+    _count()
+
+
+def cast_f32_bf16(src, dst):
+    call("cast_f32_bf16", src, dst, src.numel())
+
+
+def split_hi_lo(src, dst, rows, D):
+    call("split_hi_lo", src, dst, rows, D)
+
+
+def patchify(imgs, out, B, C, H, W, ps):
+    is_u8 = imgs[0].dtype == torch.uint8
+    p = list(imgs) + [None] * (3 - len(imgs))
+    call("patchify", p[0], p[1], p[2], is_u8, out, B, C, H, W, ps)
+
+
+def sgemm(A, B, C, M, N, K, sam, sak, sbn, sbk, ldc=None, bias=None, table=None, table_rows=0, accumulate=False):
+    """C[m,n] (+)= sum_k A[m*sam+k*sak] * B[n*sbn+k*sbk] (+bias[n]) (+table[m%table_rows, n]); fp32 math."""
+    call("sgemm", A, A.dtype == torch.bfloat16, B, B.dtype == torch.bfloat16, C, C.dtype == torch.bfloat16,
+         M, N, K, sam, sak, sbn, sbk, ldc if ldc is not None else N, bias, table, table_rows, accumulate)
+
+
+def layernorm_fwd(x, scale, bias, y, mean, rstd, M, W):
+    call("layernorm_fwd", x, scale, bias, y, mean, rstd, M, W)
+
+
+def layernorm_bwd(dy, x, scale, mean, rstd, dres, dx, dscale, dbias, M, W):
+    call("layernorm_bwd", dy, x, scale, mean, rstd, dres, dx, dscale, dbias, M, W)
+
+
+def rmsnorm_fwd(x, y, rstd, M, D, *, scale=None, mod=None, ldmod=0, rows_per_sample=1, ldx=None, ldy=None,
+                row_idx=None, dup=False):
+    call("rmsnorm_fwd", x, ldx if ldx is not None else D, row_idx, scale, mod, ldmod, rows_per_sample, y,
+         ldy if ldy is not None else D, dup, rstd, M, D)
+
+
+def rmsnorm_bwd(dy, x, scale, rstd, dres, dx, dscale, M, D, *, lddy=None, ldx=None, row_idx=None):
+    call("rmsnorm_bwd", dy, lddy if lddy is not None else D, x, ldx if ldx is not None else D, row_idx, scale, rstd,
+         dres, dx, dscale, M, D)
+
+
+def ada_rmsnorm_bwd(dy, x, mod, ldmod, rstd, dres, dx, dmod, lddmod, B, rows_per_sample, D):
+    call("ada_rmsnorm_bwd", dy, x, mod, ldmod, rstd, dres, dx, dmod, lddmod, B, rows_per_sample, D)
+
+
+def gated_bwd(dxo, y, gate, ldg, dy, dgate, lddg, B, rows_per_sample, D):
+    call("gated_bwd", dxo, y, gate, ldg, dy, dgate, lddg, B, rows_per_sample, D)
+
+
+def rope_fwd(qkv0, qkv1, positions, timescale, Q, Kc, Vc, B, P, A, Tpad, NH, HD, t_begin, qscale):
+    call("rope_fwd", qkv0, qkv1, positions, timescale, Q, Kc, Vc, B, P, A, Tpad, NH, HD, t_begin, float(qscale))
+
+
+def rope_bwd(dQ, dK, dV, positions, timescale, dqkv0, dqkv1, B, P, A, Tpad, NH, HD, qscale):
+    call("rope_bwd", dQ, dK, dV, positions, timescale, dqkv0, dqkv1, B, P, A, Tpad, NH, HD, float(qscale))
+
+
+def geglu_bwd(dact, gu, M, F):
+    call("geglu_bwd", dact, gu, M, F)
+
+
+def gelu_bwd(dh, pre, n):
+    call("gelu_bwd", dh, pre, n)
+
+
+def swish_fwd(z, y, y_bf16, n):
+    call("swish_fwd", z, y, y_bf16, n)
+
+
+def swish_bwd(z, dy, dy_bf16, dz, n):
+    call("swish_bwd", z, dy, dy_bf16, dz, n)
+
+
+def colsum(X, ldx, out, M, N):
+    call("colsum", X, ldx, out, M, N)
+
+
+def embed_fwd(ids, E, X, B, L, row_off, rows_per_sample, D, scale):
+    call("embed_fwd", ids, E, X, B, L, row_off, rows_per_sample, D, float(scale))
+
+
+def embed_bwd(ids, dX, dE, B, L, row_off, rows_per_sample, D, scale):
+    call("embed_bwd", ids, dX, dE, B, L, row_off, rows_per_sample, D, float(scale))
+
+
+def scatter_rows(d, rows, dX, R, D):
+    call("scatter_rows", d, rows, dX, R, D)
+
+
+def suffix_inputs(actions, noise, time, x_t, u_t, time_emb, B, AD, W):
+    call("suffix_inputs", actions, noise, time, x_t, u_t, time_emb, B, AD, W)
+
+
+def axpy(x, v, dt, n):
+    call("axpy", x, v, float(dt), n)
+
+
+def mask_build(pm, par, pma, sm, sar, bits, positions, B, P, A, W32, row_begin=0, infer_rows=False):
+    call("mask_build", pm, par, pma, sm, sar, bits, positions, B, P, A, W32, row_begin, infer_rows)
+
+
+def mask_expand(bits, dense, rows, S, W32):
+    call("mask_expand", bits, dense, rows, S, W32)
+
+
+def attn_softmax_fwd(S, bits, P, B, rows_per_batch, G, S_len, ld, W32):
+    call("attn_softmax_fwd", S, bits, P, B, rows_per_batch, G, S_len, ld, W32)
+
+
+def softmax_bwd(P, dP, dS, rows, ld):
+    call("softmax_bwd", P, dP, dS, rows, ld)
+
+
+def vit_softmax_fwd(S, rows, n, ld, mode=0):
+    call("vit_softmax_fwd", S, rows, n, ld, mode)
+
+
+def ce_fwd_bwd(logits, ld, targets, weights, nll, dlogits, ldd, R, V):
+    call("ce_fwd_bwd", logits, ld, targets, weights, nll, dlogits, ldd, R, V)
+
+
+def mse_fwd_bwd(v, u, loss, dv, B, AD, gscale):
+    call("mse_fwd_bwd", v, u, loss, dv, B, AD, float(gscale))
+
+
+def weighted_sum(x, w, out, n, alpha=1.0, accumulate=False):
+    call("weighted_sum", x, w, out, n, float(alpha), accumulate)
+
+
+def opt_num_partials() -> int:
+    return int(lib().lapb200_opt_num_partials())
+
+
+def sumsq_partials(x, n, partials):
+    call("sumsq_partials", x, n, partials)
+
+
+def adamw_ema(p, g, m, v, ema, w16, n, gpartials, n_partials, stats, kernel_begin, kernel_end, *, lr, b1, b2, eps, wd,
+              bc1, bc2, clip, ema_decay, ema_on):
+    call("adamw_ema", p, g, m, v, ema, w16, n, gpartials, n_partials, stats, kernel_begin, kernel_end, float(lr),
+         float(b1), float(b2), float(eps), float(wd), float(bc1), float(bc2), float(clip), float(ema_decay), ema_on)

@@ -1,0 +1,154 @@
+"""Training runtime of the hot path: TrainState, the train step and its data-parallel gradient exchange.
+
+Reference:
+  TrainState .............. src/lap/training/state.py:8-18
+  init_train_state ........ scripts/train.py:201-326
+  TrainingStepRunner ...... scripts/train.py:329-419  (value_and_grad -> clip -> AdamW -> EMA -> norms)
+  optimizer / schedule .... third_party/openpi/src/openpi/training/optimizer.py
+  data-parallel sharding .. src/lap/training/mh_sharding.py:14-63 + implicit GSPMD all-reduce (scripts/train.py:532-537)
+
+Design: one process per GPU; parameters, Adam moments and EMA are replicated as flat fp32 buffers (fsdp_devices=1 in
+the reference); the global batch is sharded on axis 0; the ONLY data-path collective is one sum-all-reduce of the flat
+fp32 gradient buffer over NCCL (bucketed so the tail of backward overlaps it).  Loss normalisers are global counts
+(lap.py:580-589), exchanged as two scalars before the step.
+"""
+from __future__ import annotations
+
+import dataclasses
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .config import TrainConfig
+from .model import LAP, F32
+from .observation import CoTObservation, Observation, to_numpy
+
+
+@dataclasses.dataclass
+class TrainState:
+    """src/lap/training/state.py:8-18 — engine-owned flat device buffers (donated / updated in place)."""
+
+    step: int
+    model: LAP  # owns params (fp32 master `P`) and the bf16 compute copy
+    mu: torch.Tensor
+    nu: torch.Tensor
+    ema_params: torch.Tensor | None
+    ema_decay: float | None
+
+    @property
+    def params(self) -> torch.Tensor:
+        return self.model.P
+
+
+def init_train_state(config: TrainConfig, seed: int | None = None, *, model: LAP | None = None,
+                     reference_zero_init: bool = True) -> TrainState:
+    """scripts/train.py:201-326 with weight_loader.kind=none (random init) unless a model is passed in."""
+    if model is None:
+        model = LAP(config.model, seed=config.seed if seed is None else seed, reference_zero_init=reference_zero_init)
+    n = model.layout.total
+    dev = model.device
+    model.G = torch.zeros(n, dtype=F32, device=dev)
+    ema_decay, ema_enabled = config.get_ema_init()
+    return TrainState(step=0, model=model, mu=torch.zeros(n, dtype=F32, device=dev),
+                      nu=torch.zeros(n, dtype=F32, device=dev),
+                      ema_params=model.P.clone() if ema_enabled else None, ema_decay=ema_decay)
+
+
+class TrainingStepRunner:
+    """Callable with the reference's signature: (rng, state, (observation, actions), step) -> (state, info)."""
+
+    def __init__(self, config: TrainConfig, *, bucket_bytes: int = 512 << 20):
+        self.config = config
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.bucket_bytes = bucket_bytes
+        self._partials = None
+        self._stats = None
+
+    # -- global loss normalisers (lap.py:580-589 are means over the GLOBAL batch) ------------------------------
+    def _global_counts(self, observation, B: int, device) -> tuple[float, float]:
+        sm = getattr(observation, "sample_mask", None)
+        n_active = float(to_numpy(sm).astype(bool).sum()) if sm is not None else float(B)
+        n_action = float(B)
+        if self.world > 1:
+            t = torch.tensor([n_active, n_action], dtype=torch.float64, device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            n_active, n_action = (float(x) for x in t.tolist())
+        return n_active, n_action
+
+    def _allreduce_grads(self, G: torch.Tensor) -> None:
+        """C1: the one data-path collective — sum of fp32 grads across ranks (NCCL over NVLink/NVSwitch)."""
+        if self.world == 1:
+            return
+        step = self.bucket_bytes // 4
+        works = []
+        for o in range(0, G.numel(), step):
+            works.append(dist.all_reduce(G[o : o + step], op=dist.ReduceOp.SUM, async_op=True))
+        for w in works:
+            w.wait()
+
+    def __call__(self, rng, state: TrainState, batch, step: int | None = None, *, with_metrics: bool = True):
+        cfg = self.config
+        model = state.model
+        observation, actions = batch[0], batch[1]
+        extra = batch[2] if len(batch) > 2 else {}
+        noise, time = extra.get("noise"), extra.get("time")
+        step = state.step if step is None else int(step)
+        B = to_numpy(actions).shape[0] if not isinstance(actions, torch.Tensor) else actions.shape[0]
+        mc = cfg.model
+        if noise is None or time is None:
+            # train_rng = fold_in(rng, step) (scripts/train.py:355); torch generator stands in for threefry
+            gen = torch.Generator().manual_seed((int(rng) if rng is not None else 0) * 1_000_003 + step)
+            if noise is None:
+                noise = torch.randn((B, mc.action_horizon, mc.action_dim), generator=gen)
+            if time is None:
+                u = torch.rand((B,), generator=gen)
+                time = u.pow(1.0 / 1.5) * 0.999 + 0.001  # Beta(1.5, 1) by inverse CDF
+        counts = self._global_counts(observation, B, model.device)
+        st = model._stage(observation, actions, noise, time, with_loss=True, global_counts=counts)
+        loss = model.forward_backward(st)
+        self._allreduce_grads(model.G)
+        info = self.apply_gradients(state, step)
+        info["loss"] = loss[0]
+        if self.world > 1:
+            # each rank holds its shard's share of the global mean; the sum over ranks is the global loss
+            lt = loss.clone()
+            dist.all_reduce(lt, op=dist.ReduceOp.SUM)
+            info["loss"] = lt[0]
+        if with_metrics:
+            info.update(model._metrics(st))
+        return state, info
+
+    def apply_gradients(self, state: TrainState, step: int) -> dict:
+        """clip_by_global_norm -> adamw -> apply -> EMA (scripts/train.py:363-396) + norms (:370-371,402-415)."""
+        cfg, o = self.config, self.config.optimizer
+        model = state.model
+        n = model.layout.total
+        if self._partials is None:
+            self._np = ops.opt_num_partials()
+            self._partials = torch.zeros(self._np, dtype=F32, device=model.device)
+            self._stats = torch.zeros(4, dtype=F32, device=model.device)
+        self._stats.zero_()
+        ops.sumsq_partials(model.G, n, self._partials)
+        lr = cfg.lr_schedule.lr(step)
+        count = step + 1
+        decay, ema_on = cfg.get_ema_decay_for_step(step)
+        ops.adamw_ema(model.P, model.G, state.mu, state.nu, state.ema_params, model.W16, n, self._partials, self._np,
+                      self._stats, 0, model.layout.kernel_end, lr=lr, b1=o.b1, b2=o.b2, eps=o.eps, wd=o.weight_decay,
+                      bc1=1.0 - o.b1 ** count, bc2=1.0 - o.b2 ** count, clip=o.clip_gradient_norm,
+                      ema_decay=float(decay), ema_on=bool(ema_on) and state.ema_params is not None)
+        model.refresh_embed_split()
+        state.step = step + 1
+        stats = self._stats.clone()
+        return {"grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[2].sqrt()}
+
+
+def train_step(config: TrainConfig, rng, state: TrainState, batch, step: int | None = None):
+    return TrainingStepRunner(config)(rng, state, batch, step)
+
+
+def batch_from_dict(d: dict):
+    """Loader-format dict (data_loader.py:327) -> ((CoTObservation, actions), extras)."""
+    obs = CoTObservation.from_dict(d)
+    return obs, d["actions"], {k: d[k] for k in ("noise", "time") if k in d}
