@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py — LAP-3B training throughput on B200 (the BASELINE.json metric), one JSON line on stdout.
+
+  python bench.py --gpus N --steps K --warmup W            # our arm (N>1: launched by torchrun, one rank per GPU)
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle port) on the host cores
+  python bench.py --mode infer                             # action-chunk inference latency (second headline metric)
+
+A "step" = one optimisation step (forward + backward + grad all-reduce + clip/AdamW/EMA) of the lap_libero
+configuration (LAP-3B: SigLIP-So400m + Gemma-2B + Gemma-300M expert; 2x224x224x3 images, 180 text tokens, 10-step
+action chunk) on a synthetic RLDS-shaped batch of 32 samples per GPU with random-init weights.
+  value : samples/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
+  e2e   : samples/s through the public API `TrainingStepRunner(rng, state, (obs, actions))` with HOST numpy
+          buffers: pinned H2D copy of the batch and D2H read of the loss inside the timed region
+  roofline : all tcgen05 GEMM launches of the timed region (the dominant kernel, >90 % of step FLOPs): algorithmic
+          FLOPs / CUDA-event time of those launches, against the measured sustained bf16 peak
+  cpu_baseline : the oracle (CPU restatement of the reference, torch fp32 eager) timed on this box's host cores on a
+          bounded sample (batch 1, forward+backward) — a reported baseline, not the target
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "LAP-3B train samples/sec"
+UNIT = "samples/s"
+PER_GPU_BATCH = 32
+
+
+def _peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int = 0):
+        self.proc = None
+        self.lines: list[str] = []
+        self.gpu_index = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu_index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference(steps: int, warmup: int, *, budget_s: float = 150.0) -> dict:
+    import numpy as np
+    import torch
+
+    from lap_b200 import params as P
+    from lap_b200.config import get_config
+    from lap_b200.data import synthetic_batch
+    from oracle import lap_oracle as O
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    tc = get_config("lap_libero")
+    cfg = tc.model
+    t0 = time.time()
+    shapes = P.reference_shapes(cfg)
+    gen = torch.Generator().manual_seed(0)
+    params = {}
+    for k, s in shapes.items():
+        t = torch.empty(s, dtype=torch.float32)
+        leaf = k.rsplit("/", 1)[-1]
+        if leaf == "scale" and "/img/" in k:
+            t.fill_(1.0)
+        elif leaf in ("bias", "scale"):
+            t.zero_()
+        else:
+            fan_in = s[-2] if len(s) >= 2 else s[-1]
+            t.normal_(0.0, 0.01 if k.endswith("input_embedding") else 1.0 / (fan_in ** 0.5), generator=gen)
+        params[k] = t
+    init_s = time.time() - t0
+    tt = lambda x: torch.from_numpy(np.asarray(x))
+
+    def one_step(i: int) -> float:
+        b = synthetic_batch(cfg, 1, step=i)
+        b["sample_mask"][:] = True
+        obs = dict(images={k: tt(v) for k, v in b["image"].items()}, image_masks={k: tt(v) for k, v in b["image_mask"].items()},
+                   tokenized_prompt=tt(b["tokenized_prompt"]), tokenized_prompt_mask=tt(b["tokenized_prompt_mask"]),
+                   tokenized_langact_mask=tt(b["tokenized_langact_mask"]), token_loss_mask=tt(b["token_loss_mask"]),
+                   sample_mask=tt(b["sample_mask"]))
+        ps = {k: v.requires_grad_(True) for k, v in params.items()}
+        t1 = time.time()
+        loss, _ = O.compute_loss(ps, cfg, obs, tt(b["actions"]), tt(b["noise"]), tt(b["time"]), bf16=False)
+        loss.backward()
+        for v in ps.values():
+            v.grad = None
+        return time.time() - t1
+
+    times = []
+    spent = 0.0
+    for i in range(warmup + steps):
+        dt = one_step(i)
+        spent += dt
+        if i >= warmup:
+            times.append(dt)
+        if spent > budget_s and len(times) >= 1:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    return {"value": 1e3 / ms, "ms_per_step": ms, "cores": cores, "steps_timed": len(times), "init_s": init_s,
+            "sample": "batch 1 of the lap_libero workload, full LAP-3B (fp32 eager torch restatement of the JAX "
+                      "reference, forward+backward, no optimizer), %d timed steps" % len(times)}
+
+
+def run_reference(args) -> None:
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference(args.steps, args.warmup)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": r["steps_timed"], "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "lap_libero LAP-3B train step, per-GPU batch 32 (reference arm: CPU, batch 1 sample)",
+                   "per_gpu_batch": PER_GPU_BATCH, "images": "2x224x224x3", "text_tokens": 180, "action_horizon": 10},
+        "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port", "sample": r["sample"]},
+        "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "JAX/Flax are not installable here (no wheels, no network): this is the oracle port of the reference "
+                "arithmetic on the host cores, not the JAX program",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------
+def run_train(args) -> None:
+    import torch
+    import torch.distributed as dist
+
+    from lap_b200 import ops
+    from lap_b200.config import get_config
+    from lap_b200.data import synthetic_batch
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+    tc = get_config("lap_libero")
+    B = PER_GPU_BATCH
+    state = init_train_state(tc, seed=0)
+    runner = TrainingStepRunner(tc)
+    model = state.model
+
+    def host_batch(i):
+        return batch_from_dict(synthetic_batch(tc.model, B, step=i, rank=rank))
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---------------- device-resident timing (`value`) ----------------
+    batches = [host_batch(i) for i in range(2)]
+    staged = []
+    for obs, actions, extra in batches:
+        counts = runner._global_counts(obs, B, dev)
+        staged.append(model._stage(obs, actions, extra["noise"], extra["time"], with_loss=True, global_counts=counts))
+    for i in range(args.warmup):
+        runner.step_staged(state, staged[i % 2])
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ops.gemm_profile_begin()
+    n0 = ops.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        runner.step_staged(state, staged[i % 2])
+    e1.record()
+    sync()
+    launches = ops.launch_count - n0
+    gemm_flops, gemm_ms, gemm_launches = ops.gemm_profile_end()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    # ---------------- end-to-end timing through the public API with host buffers (`e2e`) ----------------
+    hb = [host_batch(100 + i) for i in range(2)]
+    for i in range(max(1, min(args.warmup, 2))):
+        obs, actions, extra = hb[i % 2]
+        _, info = runner(0, state, (obs, actions, extra), with_metrics=False)
+        float(info["loss"])
+    sync()
+    t0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        obs, actions, extra = hb[i % 2]
+        _, info = runner(0, state, (obs, actions, extra), with_metrics=False)
+        loss_host = float(info["loss"])  # D2H read of the step's result
+    e1.record()
+    sync()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t0)) / args.steps)
+    h2d = model.last_h2d_bytes
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks, peak_kind = _peaks()
+    peak_tf = float(peaks.get("bf16_tflops_sustained", peaks.get("bf16_tflops", 1400.0)))
+    achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    value = world * B / (ms_dev * 1e-3)
+    e2e = world * B / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": "lap_libero LAP-3B train step (SigLIP-So400m x2 cams + Gemma-2B + Gemma-300M expert), "
+                               "per-GPU batch 32, random-init weights",
+                   "per_gpu_batch": B, "global_batch": world * B, "images": "2x224x224x3", "text_tokens": 180,
+                   "action_horizon": 10, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB)",
+                   "flops_per_sample_train": 10.35e12},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": 4},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "tensor", "kernel": "gemm_bf16_tcgen05 (all launches of the timed region)",
+                     "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                     "peak_kind": f"{peak_kind} sustained bf16", "traffic": None,
+                     "launches_per_step": gemm_launches / max(args.steps, 1), "gemm_ms_per_step": gemm_ms / args.steps,
+                     "step_model_flops_frac": (world * B * 10.35e12 / (ms_dev * 1e-3)) / (world * peak_tf * 1e12)},
+        "loss": loss_host,
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            r = cpu_reference(1, 0, budget_s=30.0)
+            line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        except Exception as ex:  # pragma: no cover
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                    "sample": f"failed: {ex}"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_infer(args) -> None:
+    import numpy as np
+    import torch
+
+    from lap_b200 import ops
+    from lap_b200.config import get_config
+    from lap_b200.data import synthetic_batch
+    from lap_b200.model import LAP
+    from lap_b200.observation import Observation
+
+    tc = get_config("lap_libero")
+    model = LAP(tc.model, seed=0)
+    b = synthetic_batch(tc.model, 1, step=0, with_langact=False)
+    obs = Observation.from_dict(b)
+    times = []
+    for i in range(args.warmup + args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        a = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+        a_host = a.cpu()
+        dt = time.perf_counter() - t0
+        if i >= args.warmup:
+            times.append(dt * 1e3)
+    times.sort()
+    line = {"metric": "action-chunk infer p50 ms", "value": times[len(times) // 2], "unit": "ms",
+            "p90": times[int(len(times) * 0.9)], "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "higher_is_better": False, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "lap_libero sample_actions, batch 1, 2x224px cameras, 180-token prompt, 10 Euler steps"}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="train", choices=["train", "infer"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    elif args.mode == "infer":
+        run_infer(args)
+    else:
+        run_train(args)
+
+
+if __name__ == "__main__":
+    main()

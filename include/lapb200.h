@@ -73,9 +73,111 @@ typedef struct {
   float q_div;
   int32_t block_n; /* 0 = auto, else 128 or 256 */
   int32_t max_ctas; /* 0 = number of SMs */
+  int32_t cta_group; /* 0 = auto, 1 = one CTA per tile, 2 = cta_group::2 pairs (256-row tiles) */
+  int32_t k_splits;  /* 0 = auto (fp32-out, EPI_NONE only), 1 = off, n = force n K-splits (atomic fp32 adds) */
 } lapb_gemm_t;
 
 int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream);
+
+/* ------------------------------------------------------------------------- */
+/* HBM-bound kernels. Convention: every integer is int64_t, every scalar is  */
+/* float, bf16 tensors are void*, last argument is the stream.               */
+/* ------------------------------------------------------------------------- */
+
+/* fp32 -> bf16 compute copy of parameters (lora.py:57 `w.astype(dtype)` hoisted out of the step). */
+int lapb200_cast_f32_bf16(const float* src, void* dst, int64_t n, lapb_stream_t s);
+/* dst[v,0:D]=bf16(E[v]), dst[v,D:2D]=bf16(E[v]-hi): the fp32 table of Embedder.decode (gemma.py:153-154) as a hi/lo pair. */
+int lapb200_split_hi_lo(const float* src, void* dst, int64_t rows, int64_t D, lapb_stream_t s);
+/* images -> fp32 patch rows (siglip.py:216-223 conv as im2col); is_u8 fuses Observation.from_dict's u8/255*2-1 (OP/models/model.py:116-118). */
+int lapb200_patchify(const void* img0, const void* img1, const void* img2, int64_t is_u8, float* out, int64_t B,
+                     int64_t C, int64_t H, int64_t W, int64_t ps, lapb_stream_t s);
+/* fp32 CUDA-core GEMM with generic strides for the layers the reference keeps in fp32:
+ * patch conv (siglip.py:216-229, +bias +pos_embedding table), action_in/out_proj, time MLP (pi0.py:159-169, lap.py:298). */
+int lapb200_sgemm(const void* A, int64_t a_bf16, const void* B, int64_t b_bf16, void* C, int64_t c_bf16, int64_t M,
+                  int64_t N, int64_t K, int64_t sam, int64_t sak, int64_t sbn, int64_t sbk, int64_t ldc,
+                  const float* bias, const float* table, int64_t table_rows, int64_t accumulate, lapb_stream_t s);
+
+/* flax nn.LayerNorm(dtype=bf16), eps 1e-6, fp32 fast-variance stats (siglip.py:87,98,161) and its backward
+ * (dx = dres + LN'(dy); dscale/dbias accumulated with atomics). */
+int lapb200_layernorm_fwd(const void* x, const float* scale, const float* bias, void* y, float* mean, float* rstd,
+                          int64_t M, int64_t W, lapb_stream_t s);
+int lapb200_layernorm_bwd(const void* dy, const void* x, const float* scale, const float* mean, const float* rstd,
+                          const void* dres, void* dx, float* dscale, float* dbias, int64_t M, int64_t W,
+                          lapb_stream_t s);
+
+/* gemma.RMSNorm (gemma.py:112-131): plain (scale) or adaptive (mod = [scale|shift|gate] per sample);
+ * row_idx gathers source rows, dup writes [y|y] (split-table LM head). */
+int lapb200_rmsnorm_fwd(const void* x, int64_t ldx, const int64_t* row_idx, const float* scale, const void* mod,
+                        int64_t ldmod, int64_t rows_per_sample, void* y, int64_t ldy, int64_t dup, float* rstd,
+                        int64_t M, int64_t D, lapb_stream_t s);
+int lapb200_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx, const int64_t* row_idx,
+                        const float* scale, const float* rstd, const void* dres, void* dx, float* dscale, int64_t M,
+                        int64_t D, lapb_stream_t s);
+int lapb200_ada_rmsnorm_bwd(const void* dy, const void* x, const void* mod, int64_t ldmod, const float* rstd,
+                            const void* dres, void* dx, void* dmod, int64_t lddmod, int64_t B,
+                            int64_t rows_per_sample, int64_t D, lapb_stream_t s);
+/* backward of the gated residual x + y*gate (gemma.py:577-583): dy = dxo*gate, dgate = sum_rows dxo*y. */
+int lapb200_gated_bwd(const void* dxo, const void* y, const void* gate, int64_t ldg, void* dy, void* dgate,
+                      int64_t lddg, int64_t B, int64_t rows_per_sample, int64_t D, lapb_stream_t s);
+
+/* RoPE + q*hd^-0.5 + gather of both experts' fused QKV into attention layout (gemma.py:204,215-218,548-564),
+ * also the KV-cache append of the suffix-only pass (gemma.py:227-230); and its backward. */
+int lapb200_rope_fwd(const void* qkv0, const void* qkv1, const int32_t* positions, const float* timescale, void* Q,
+                     void* Kc, void* Vc, int64_t B, int64_t P, int64_t A, int64_t Tpad, int64_t NH, int64_t HD,
+                     int64_t t_begin, float qscale, lapb_stream_t s);
+int lapb200_rope_bwd(const void* dQ, const void* dK, const void* dV, const int32_t* positions,
+                     const float* timescale, void* dqkv0, void* dqkv1, int64_t B, int64_t P, int64_t A, int64_t Tpad,
+                     int64_t NH, int64_t HD, float qscale, lapb_stream_t s);
+
+/* GeGLU backward in place (lora.py:124-142); GELU backward (siglip.py:71); swish (pi0.py:165-167). */
+int lapb200_geglu_bwd(void* dact, void* gu, int64_t M, int64_t F, lapb_stream_t s);
+int lapb200_gelu_bwd(void* dh, const void* pre, int64_t n, lapb_stream_t s);
+int lapb200_swish_fwd(const float* z, float* y, void* y_bf16, int64_t n, lapb_stream_t s);
+int lapb200_swish_bwd(const float* z, const float* dy, const void* dy_bf16, float* dz, int64_t n, lapb_stream_t s);
+/* out[n] += sum_m X[m,n] (bias / pos_embedding gradients). */
+int lapb200_colsum(const void* X, int64_t ldx, float* out, int64_t M, int64_t N, lapb_stream_t s);
+
+/* Embedder.encode (gemma.py:148-151,446-448) and its scatter-add backward. */
+int lapb200_embed_fwd(const int32_t* ids, const float* E, void* X, int64_t B, int64_t L, int64_t row_off,
+                      int64_t rows_per_sample, int64_t D, float scale, lapb_stream_t s);
+int lapb200_embed_bwd(const int32_t* ids, const void* dX, float* dE, int64_t B, int64_t L, int64_t row_off,
+                      int64_t rows_per_sample, int64_t D, float scale, lapb_stream_t s);
+int lapb200_scatter_rows(const void* d, const int64_t* rows, void* dX, int64_t R, int64_t D, lapb_stream_t s);
+
+/* flow-matching inputs x_t, u_t (lap.py:193-197) and posemb_sincos(t) (pi0.py:47-63); Euler step (lap.py:667). */
+int lapb200_suffix_inputs(const float* actions, const float* noise, const float* time, float* x_t, float* u_t,
+                          float* time_emb, int64_t B, int64_t AD, int64_t W, lapb_stream_t s);
+int lapb200_axpy(float* x, const float* v, float dt, int64_t n, lapb_stream_t s);
+
+/* K11: make_attn_mask / combined mask / positions (pi0.py:19-44, lap.py:303-377, :641-654) -> packed bits. */
+int lapb200_mask_build(const uint8_t* pm, const uint8_t* par, const uint8_t* pma, const uint8_t* sm,
+                       const uint8_t* sar, uint32_t* bits, int32_t* positions, int64_t B, int64_t P, int64_t A,
+                       int64_t W32, int64_t row_begin, int64_t infer_rows, lapb_stream_t s);
+int lapb200_mask_expand(const uint32_t* bits, uint8_t* dense, int64_t rows, int64_t S, int64_t W32, lapb_stream_t s);
+/* masked softmax between the attention GEMMs (gemma.py:258-261) and generic softmax backward. */
+int lapb200_attn_softmax_fwd(const float* S, const uint32_t* bits, void* P, int64_t B, int64_t rows_per_batch,
+                             int64_t G, int64_t S_len, int64_t ld, int64_t W32, lapb_stream_t s);
+int lapb200_softmax_bwd(const void* P, const void* dP, void* dS, int64_t rows, int64_t ld, lapb_stream_t s);
+/* SigLIP softmax evaluated in bf16 (flax MultiHeadDotProductAttention, siglip.py:88-93); mode 1 = fp32 softmax. */
+int lapb200_vit_softmax_fwd(void* S, int64_t rows, int64_t n, int64_t ld, int64_t mode, lapb_stream_t s);
+
+/* K9: log-softmax cross-entropy over fp32 LM-head logits + weighted bf16 gradient (lap.py:221-260). */
+int lapb200_ce_fwd_bwd(const float* logits, int64_t ld, const int32_t* targets, const float* weights, float* nll,
+                       void* dlogits, int64_t ldd, int64_t R, int64_t V, lapb_stream_t s);
+/* action MSE + gradient (lap.py:291-301); weighted scalar reduction for the final loss (lap.py:573-596). */
+int lapb200_mse_fwd_bwd(const float* v, const float* u, float* loss, float* dv, int64_t B, int64_t AD, float gscale,
+                        lapb_stream_t s);
+int lapb200_weighted_sum(const float* x, const float* w, float* out, int64_t n, float alpha, int64_t accumulate,
+                         lapb_stream_t s);
+
+/* K12: global-norm clip + AdamW + EMA + bf16 copy + norms over the flat state
+ * (scripts/train.py:363-415; OP/training/optimizer.py:76-85). */
+int lapb200_opt_num_partials(void);
+int lapb200_sumsq_partials(const float* x, int64_t n, float* partials, lapb_stream_t s);
+int lapb200_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* w16, int64_t n,
+                      const float* gpartials, int64_t n_partials, float* stats, int64_t kernel_begin,
+                      int64_t kernel_end, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
+                      float clip, float ema_decay, int64_t ema_on, lapb_stream_t s);
 
 #ifdef __cplusplus
 }

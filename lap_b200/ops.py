@@ -77,6 +77,8 @@ def gemm(
     q_div: float = 1.0,
     block_n: int = 0,
     max_ctas: int = 0,
+    cta_group: int = 0,
+    k_splits: int = 0,
 ) -> torch.Tensor:
     """C[b] = epi(A[b] @ B[b]^T). Strides are in elements; pointers are taken at the tensors' data_ptr()."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -111,9 +113,38 @@ def gemm(
     p.q_div = q_div
     p.block_n = block_n
     p.max_ctas = max_ctas
+    p.cta_group = cta_group
+    p.k_splits = k_splits
+    prof = _gemm_prof
+    if prof is not None:
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
     check(lib().lapb200_gemm_bf16(ctypes.byref(p), _stream()), "gemm_bf16")
+    if prof is not None:
+        e1.record()
+        prof.append((e0, e1, 2.0 * M * N * K * batch_i * batch_o * (2 if epi == EPI_GEGLU else 1)))
     _count()
     return C
+
+
+# optional per-launch CUDA-event timing of every GEMM (bench.py roofline)
+_gemm_prof: list | None = None
+
+
+def gemm_profile_begin() -> None:
+    global _gemm_prof
+    _gemm_prof = []
+
+
+def gemm_profile_end() -> tuple[float, float, int]:
+    """Returns (algorithmic FLOPs, summed kernel ms, launches) since gemm_profile_begin(); syncs the device."""
+    global _gemm_prof
+    prof, _gemm_prof = _gemm_prof or [], None
+    torch.cuda.synchronize()
+    flops = sum(f for _, _, f in prof)
+    ms = sum(a.elapsed_time(b) for a, b, _ in prof)
+    return flops, ms, len(prof)
 
 
 # ---------------------------------------------------------------------------------------------

@@ -120,6 +120,15 @@ class TrainingStepRunner:
             info.update(model._metrics(st))
         return state, info
 
+    def step_staged(self, state: TrainState, st) -> dict:
+        """One optimisation step on inputs already staged in HBM (model._stage) — no host<->device traffic."""
+        model = state.model
+        loss = model.forward_backward(st)
+        self._allreduce_grads(model.G)
+        info = self.apply_gradients(state, state.step)
+        info["loss"] = loss[0]
+        return info
+
     def apply_gradients(self, state: TrainState, step: int) -> dict:
         """clip_by_global_norm -> adamw -> apply -> EMA (scripts/train.py:363-396) + norms (:370-371,402-415)."""
         cfg, o = self.config, self.config.optimizer

@@ -1,0 +1,336 @@
+"""GPU tests of individual kernels through the C ABI, each against a plain PyTorch fp32 reference of the same op."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from lap_b200 import ops  # noqa: E402
+from tests.helpers import rel_err  # noqa: E402
+
+DEV = "cuda"
+
+
+def _gemm_ref(A, B):
+    return A.float() @ B.float().T
+
+
+@pytest.mark.parametrize("maj", [(0, 0), (0, 1), (1, 1), (1, 0)])
+@pytest.mark.parametrize("shape", [(128, 128, 64), (320, 1024, 1024), (200, 72, 256), (384, 1152, 4304), (1000, 2560, 2048)])
+def test_gemm_layouts(maj, shape):
+    M, N, K = shape
+    torch.manual_seed(M + N + K)
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = torch.randn(N, K, device=DEV).bfloat16()
+    Ain = A if maj[0] == 0 else A.T.contiguous()
+    Bin = B if maj[1] == 0 else B.T.contiguous()
+    C = torch.zeros(M, N, device=DEV, dtype=torch.float32)
+    ops.gemm(Ain, Bin, C, M=M, N=N, K=K, a_major=maj[0], b_major=maj[1])
+    # fp32 output of a bf16 x bf16 GEMM with fp32 accumulation: exact up to summation order
+    assert rel_err(C, _gemm_ref(A, B)) < 1e-5
+
+
+def test_gemm_bf16_output_is_correctly_rounded():
+    M, N, K = 256, 512, 512
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = torch.randn(N, K, device=DEV).bfloat16()
+    C = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, C, M=M, N=N, K=K)
+    ref = _gemm_ref(A, B)
+    ulp = (C.float() - ref).abs() / ref.abs().clamp_min(1e-3)
+    assert ulp.max() < 2 ** -7  # within one bf16 ulp everywhere
+    assert (C == ref.bfloat16()).float().mean() > 0.99
+
+
+def test_gemm_epilogues():
+    M, N, K = 320, 1024, 512
+    A = torch.randn(M, K, device=DEV).bfloat16()
+    B = (torch.randn(N, K, device=DEV) * 0.1).bfloat16()
+    bias = torch.randn(N, device=DEV)
+    R = torch.randn(M, N, device=DEV).bfloat16()
+    G = torch.randn(32, N, device=DEV).bfloat16()
+    y = _gemm_ref(A, B)
+    yb = y.bfloat16().float()
+    C = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, B, C, M=M, N=N, K=K, bias=bias)
+    assert rel_err(C, (yb + bias.bfloat16().float()).bfloat16()) < 1e-3
+    ops.gemm(A, B, C, M=M, N=N, K=K, epi=ops.EPI_RESID, resid=R)
+    assert rel_err(C, (R.float() + yb).bfloat16()) < 1e-3
+    Y2 = torch.zeros_like(C)
+    ops.gemm(A, B, C, M=M, N=N, K=K, epi=ops.EPI_GATED_RESID, resid=R, gate=G, ldg=N, gate_rows=10, C2=Y2, ldc2=N)
+    gate = G.float().repeat_interleave(10, 0)
+    assert rel_err(C, (R.float() + (yb * gate).bfloat16().float()).bfloat16()) < 1e-3
+    assert rel_err(Y2, yb) < 1e-3
+    C2 = torch.zeros_like(C)
+    ops.gemm(A, B, C, M=M, N=N, K=K, epi=ops.EPI_BIAS_GELU, bias=bias, C2=C2, ldc2=N)
+    pre = (yb + bias.bfloat16().float()).bfloat16().float()
+    assert rel_err(C2, pre) < 1e-3
+    assert rel_err(C, torch.nn.functional.gelu(pre, approximate="tanh")) < 3e-3
+    ops.gemm(A, B, C, M=M, N=N, K=K, epi=ops.EPI_QSCALE, q_cols=512, q_div=8.5)
+    exp = yb.clone()
+    exp[:, :512] /= 8.5
+    assert rel_err(C, exp) < 3e-3
+    # fp32 accumulate into C
+    Cf = torch.ones(M, N, device=DEV)
+    ops.gemm(A, B, Cf, M=M, N=N, K=K, accumulate=True)
+    assert rel_err(Cf, y + 1) < 1e-5
+
+
+def test_gemm_geglu_dual():
+    M, F, K = 300, 512, 256
+    X = torch.randn(M, K, device=DEV).bfloat16()
+    W = (torch.randn(2 * F, K, device=DEV) * 0.1).bfloat16()
+    act = torch.zeros(M, F, device=DEV, dtype=torch.bfloat16)
+    gu = torch.zeros(M, 2 * F, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, C2=gu, ldc2=2 * F)
+    g = _gemm_ref(X, W[:F]).bfloat16().float()
+    u = _gemm_ref(X, W[F:]).bfloat16().float()
+    assert rel_err(gu[:, :F], g) < 1e-3 and rel_err(gu[:, F:], u) < 1e-3
+    assert rel_err(act, torch.nn.functional.gelu(g, approximate="tanh").bfloat16().float() * u) < 3e-3
+
+
+def test_gemm_batched_broadcast_and_strided():
+    Bt, T, S, H = 3, 264, 200, 256
+    Q = torch.randn(Bt, T, H, device=DEV).bfloat16()
+    Kk = torch.randn(Bt, S, H, device=DEV).bfloat16()
+    Sc = torch.zeros(Bt, T, 208, device=DEV)
+    ops.gemm(Q, Kk, Sc, M=T, N=S, K=H, batch_i=Bt, a_bs=(T * H, 0), b_bs=(S * H, 0), c_bs=(T * 208, 0), ldc=208)
+    assert rel_err(Sc[:, :, :S], torch.einsum("bth,bsh->bts", Q.float(), Kk.float())) < 2e-6
+    # shared (broadcast) B across the batch
+    W = torch.randn(128, H, device=DEV).bfloat16()
+    O = torch.zeros(Bt, T, 128, device=DEV)
+    ops.gemm(Q, W, O, M=T, N=128, K=H, batch_i=Bt, a_bs=(T * H, 0), b_bs=(0, 0), c_bs=(T * 128, 0))
+    assert rel_err(O, Q.float() @ W.float().T) < 2e-6
+
+
+def test_gemm_rejects_bad_arguments():
+    A = torch.zeros(128, 64, device=DEV, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, A, torch.zeros(128, 12, device=DEV), M=128, N=12, K=64)  # N % 8
+    with pytest.raises(RuntimeError):
+        ops.gemm(A, A, torch.zeros(128, 128, device=DEV, dtype=torch.bfloat16), M=128, N=128, K=64, accumulate=True)
+
+
+def test_layernorm_fwd_bwd():
+    M, W = 300, 1152
+    x = (torch.randn(M, W, device=DEV) * 2 + 0.5).bfloat16()
+    sc, bi = torch.randn(W, device=DEV), torch.randn(W, device=DEV)
+    y = torch.empty_like(x)
+    mean, rstd = torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.layernorm_fwd(x, sc, bi, y, mean, rstd, M, W)
+    xr = x.float().requires_grad_(True)
+    scr, bir = sc.clone().requires_grad_(True), bi.clone().requires_grad_(True)
+    yr = torch.nn.functional.layer_norm(xr, (W,), scr, bir, eps=1e-6)
+    assert rel_err(y, yr) < 3e-3
+    dy = torch.randn(M, W, device=DEV).bfloat16()
+    dres = torch.randn(M, W, device=DEV).bfloat16()
+    dx = torch.empty_like(x)
+    dsc, dbi = torch.zeros(W, device=DEV), torch.zeros(W, device=DEV)
+    ops.layernorm_bwd(dy, x, sc, mean, rstd, dres, dx, dsc, dbi, M, W)
+    yr.backward(dy.float())
+    assert rel_err(dx, xr.grad + dres.float()) < 4e-3
+    assert rel_err(dsc, scr.grad) < 1e-3 and rel_err(dbi, bir.grad) < 1e-3
+
+
+def test_rmsnorm_plain_and_adaptive():
+    B, A, D = 4, 10, 1024
+    M = B * A
+    x = torch.randn(M, D, device=DEV).bfloat16()
+    sc = torch.randn(D, device=DEV) * 0.1
+    y, rstd = torch.empty_like(x), torch.empty(M, device=DEV)
+    ops.rmsnorm_fwd(x, y, rstd, M, D, scale=sc)
+    xr = x.float().requires_grad_(True)
+    scr = sc.clone().requires_grad_(True)
+    yr = xr * torch.rsqrt((xr * xr).mean(-1, keepdim=True) + 1e-6) * (1 + scr)
+    assert rel_err(y, yr) < 3e-3
+    dy, dres = torch.randn(M, D, device=DEV).bfloat16(), torch.randn(M, D, device=DEV).bfloat16()
+    dx, dsc = torch.empty_like(x), torch.zeros(D, device=DEV)
+    ops.rmsnorm_bwd(dy, x, sc, rstd, dres, dx, dsc, M, D)
+    yr.backward(dy.float())
+    assert rel_err(dx, xr.grad + dres.float()) < 4e-3 and rel_err(dsc, scr.grad) < 1e-3
+    # adaptive
+    mod = (torch.randn(B, 3 * D, device=DEV) * 0.2).bfloat16()
+    ops.rmsnorm_fwd(x, y, rstd, M, D, mod=mod, ldmod=3 * D, rows_per_sample=A)
+    xr = x.float().requires_grad_(True)
+    mr = mod.float().requires_grad_(True)
+    s_, sh_, _ = mr[:, None, :].chunk(3, -1)
+    n = (xr * torch.rsqrt((xr * xr).mean(-1, keepdim=True) + 1e-6)).view(B, A, D)
+    yr = (n * (1 + s_) + sh_).view(M, D)
+    assert rel_err(y, yr) < 4e-3
+    dmod = torch.zeros(B, 3 * D, device=DEV, dtype=torch.bfloat16)
+    ops.ada_rmsnorm_bwd(dy, x, mod, 3 * D, rstd, None, dx, dmod, 3 * D, B, A, D)
+    yr.backward(dy.float())
+    assert rel_err(dx, xr.grad) < 6e-3
+    assert rel_err(dmod[:, : 2 * D], mr.grad[:, : 2 * D]) < 6e-3
+
+
+def test_rope_roundtrip_and_reference():
+    from oracle.lap_oracle import apply_rope
+
+    B, P, A, NH, HD = 2, 20, 4, 8, 256
+    T = P + A
+    Tpad = 32
+    ld = (NH + 2) * HD
+    qkv0 = torch.randn(B * P, ld, device=DEV).bfloat16()
+    qkv1 = torch.randn(B * A, ld, device=DEV).bfloat16()
+    pos = torch.randint(0, 700, (B, T), device=DEV, dtype=torch.int32)
+    ts = (10_000.0 ** ((2.0 / HD) * torch.arange(HD // 2, dtype=torch.float32))).to(DEV)
+    Q = torch.zeros(B, T, NH, HD, device=DEV, dtype=torch.bfloat16)
+    Kc = torch.zeros(B, Tpad, HD, device=DEV, dtype=torch.bfloat16)
+    Vc = torch.zeros_like(Kc)
+    ops.rope_fwd(qkv0, qkv1, pos, ts, Q, Kc, Vc, B, P, A, Tpad, NH, HD, 0, HD ** -0.5)
+    allq = torch.cat([qkv0.view(B, P, ld), qkv1.view(B, A, ld)], 1).float().cpu()
+    q_ref = apply_rope(allq[..., : NH * HD].reshape(B, T, NH, HD), pos.cpu(), True) * HD ** -0.5
+    k_ref = apply_rope(allq[..., NH * HD:(NH + 1) * HD].reshape(B, T, 1, HD), pos.cpu(), True)[:, :, 0]
+    assert rel_err(Q, q_ref) < 2e-3
+    assert rel_err(Kc[:, :T], k_ref) < 2e-3
+    assert torch.equal(Vc[:, :T].cpu().float(), allq[..., (NH + 1) * HD:])
+    assert Kc[:, T:].abs().max() == 0
+    # backward of a rotation is the inverse rotation: rope_bwd(rope_fwd(x)) == x * qscale^2 for q, x for k
+    d0, d1 = torch.zeros_like(qkv0), torch.zeros_like(qkv1)
+    ops.rope_bwd(Q, Kc, Vc, pos, ts, d0, d1, B, P, A, Tpad, NH, HD, HD ** -0.5)
+    assert rel_err(d0[:, : NH * HD], qkv0[:, : NH * HD].float() / HD) < 8e-3
+    assert rel_err(d0[:, NH * HD:(NH + 1) * HD], qkv0[:, NH * HD:(NH + 1) * HD]) < 8e-3
+
+
+def test_attn_softmax_and_fully_masked_rows():
+    B, Tq, G, T, Tpad = 2, 5, 8, 70, 96
+    R = Tq * G
+    S = torch.randn(B, R, Tpad, device=DEV)
+    dense = torch.rand(B, Tq, T, device=DEV) < 0.6
+    dense[0, 0] = False  # fully masked query row -> uniform probabilities (gemma.py:258 finite big_neg)
+    W32 = Tpad // 32
+    bits = torch.zeros(B, Tq, W32, dtype=torch.int64, device=DEV)
+    for j in range(T):
+        bits[:, :, j // 32] |= dense[:, :, j].long() << (j % 32)
+    bits32 = (bits & 0xFFFFFFFF).to(torch.int64)
+    bits32 = torch.where(bits32 >= 2 ** 31, bits32 - 2 ** 32, bits32).to(torch.int32)
+    Pm = torch.empty(B, R, Tpad, device=DEV, dtype=torch.bfloat16)
+    ops.attn_softmax_fwd(S, bits32, Pm, B, R, G, T, Tpad, W32)
+    m = dense.repeat_interleave(G, 1)
+    ref = torch.softmax(torch.where(m, S[:, :, :T], torch.tensor(-2.3819763e38, device=DEV)), -1)
+    assert rel_err(Pm[:, :, :T], ref) < 3e-3
+    assert Pm[:, :, T:].abs().max() == 0
+    assert torch.allclose(Pm[0, 0, :T].float(), torch.full((T,), 1.0 / T, device=DEV), rtol=1e-2)
+    dP = torch.randn(B, R, Tpad, device=DEV).bfloat16()
+    dS = torch.empty_like(dP)
+    ops.softmax_bwd(Pm, dP, dS, B * R, Tpad)
+    p, d = Pm.float(), dP.float()
+    assert rel_err(dS, p * (d - (p * d).sum(-1, keepdim=True))) < 4e-3
+
+
+def test_mask_build_bit_exact_random():
+    from oracle import lap_oracle as O
+
+    rng = np.random.default_rng(0)
+    B, n_img, L, A = 6, 32, 24, 10
+    P_ = n_img + L
+    T = P_ + A
+    Tpad = (T + 31) // 32 * 32
+    pm = np.concatenate([np.repeat(rng.random((B, 1)) < 0.8, n_img, 1), np.arange(L)[None] < rng.integers(0, L + 1, (B, 1))], 1)
+    la_text = np.zeros((B, L), bool)
+    for b in range(B):
+        s = rng.integers(1, L - 2)
+        la_text[b, s:s + rng.integers(0, 8)] = True
+    la_text &= pm[:, n_img:]
+    par = np.concatenate([np.zeros((B, n_img), bool), la_text], 1)
+    pma = pm & ~par
+    sm = np.ones((B, A), bool)
+    sar = np.tile(np.array([1] + [0] * (A - 1), bool), (B, 1))
+    up = lambda x: torch.from_numpy(x.astype(np.uint8)).to(DEV)
+    bits = torch.zeros(B, T, Tpad // 32, dtype=torch.int32, device=DEV)
+    pos = torch.zeros(B, T, dtype=torch.int32, device=DEV)
+    ops.mask_build(up(pm), up(par), up(pma), up(sm), up(sar), bits, pos, B, P_, A, Tpad // 32)
+    dense = torch.zeros(B, T, T, dtype=torch.uint8, device=DEV)
+    ops.mask_expand(bits, dense, B * T, T, Tpad // 32)
+    t = torch.from_numpy
+    ref = O.build_combined_attention_mask(t(pm), t(par), t(pma), t(sm), t(sar))
+    refpos = O.build_combined_positions(t(pm), t(pma), t(sm))
+    assert torch.equal(dense.cpu().bool(), ref)
+    assert torch.equal(pos.cpu(), refpos)
+
+
+def test_ce_loss_and_gradient():
+    R, V = 64, 4096
+    logits = torch.randn(R, V, device=DEV) * 3
+    tgt = torch.randint(0, V, (R,), device=DEV, dtype=torch.int32)
+    w = torch.rand(R, device=DEV)
+    w[-5:] = 0
+    nll = torch.empty(R, device=DEV)
+    dl = torch.empty(R, V, device=DEV, dtype=torch.bfloat16)
+    ops.ce_fwd_bwd(logits, V, tgt, w, nll, dl, V, R, V)
+    lr = logits.clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(lr, tgt.long(), reduction="none")
+    assert rel_err(nll, ref) < 1e-5
+    (ref * w).sum().backward()
+    assert rel_err(dl, lr.grad) < 3e-3
+    assert dl[-5:].abs().max() == 0
+
+
+def test_adamw_ema_matches_closed_form():
+    n = 4096 * 3
+    p = torch.randn(n, device=DEV)
+    g = torch.randn(n, device=DEV) * 3
+    m, v = torch.rand(n, device=DEV) * 0.1, torch.rand(n, device=DEV) * 0.1
+    ema = p.clone()
+    p0, m0, v0 = p.clone(), m.clone(), v.clone()
+    w16 = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    npart = ops.opt_num_partials()
+    part = torch.zeros(npart, device=DEV)
+    stats = torch.zeros(4, device=DEV)
+    ops.sumsq_partials(g, n, part)
+    hp = dict(lr=1e-2, b1=0.9, b2=0.95, eps=1e-8, wd=1e-4, bc1=1 - 0.9 ** 3, bc2=1 - 0.95 ** 3, clip=1.0, ema_decay=0.99, ema_on=True)
+    ops.adamw_ema(p, g, m, v, ema, w16, n, part, npart, stats, 0, 4096, **hp)
+    gn = g.double().norm().float()
+    gs = g * (1.0 / gn)
+    mr = 0.9 * m0 + 0.1 * gs
+    vr = 0.95 * v0 + 0.05 * gs * gs
+    pr = p0 - 1e-2 * ((mr / hp["bc1"]) / ((vr / hp["bc2"]).sqrt() + 1e-8) + 1e-4 * p0)
+    assert abs(stats[0].item() - gn.item()) < 1e-3 * gn.item()
+    assert torch.allclose(p, pr, rtol=1e-5, atol=1e-7) and torch.allclose(m, mr, rtol=1e-5, atol=1e-8)
+    assert torch.allclose(ema, 0.99 * p0 + 0.01 * pr, rtol=1e-5, atol=1e-7)
+    assert torch.equal(w16, pr.bfloat16()) or rel_err(w16, pr) < 3e-3
+    assert abs(stats[2].sqrt().item() - pr[:4096].norm().item()) < 1e-3 * pr[:4096].norm().item()
+
+
+def test_split_hi_lo_recovers_fp32_table():
+    E = torch.randn(1000, 64, device=DEV) * 0.02
+    out = torch.empty(1000, 128, device=DEV, dtype=torch.bfloat16)
+    ops.split_hi_lo(E, out, 1000, 64)
+    rec = out[:, :64].float() + out[:, 64:].float()
+    assert ((rec - E).abs() / E.abs().clamp_min(1e-6)).max() < 2 ** -15
+
+
+def test_sgemm_patchify_colsum_embed():
+    B, C, H, ps, W = 2, 2, 56, 14, 32
+    imgs = [torch.rand(B, H, H, 3, device=DEV) * 2 - 1 for _ in range(C)]
+    np_ = (H // ps) ** 2
+    pk = ps * ps * 3
+    patches = torch.empty(B * C * np_, pk, device=DEV)
+    ops.patchify(imgs, patches, B, C, H, H, ps)
+    ref = torch.stack(imgs, 1).reshape(B * C, H // ps, ps, H // ps, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(-1, pk)
+    assert torch.equal(patches, ref)
+    u8 = [(torch.rand(B, H, H, 3, device=DEV) * 255).to(torch.uint8) for _ in range(C)]
+    ops.patchify(u8, patches, B, C, H, H, ps)
+    refu = (torch.stack(u8, 1).float() / 255.0 * 2.0 - 1.0).reshape(B * C, H // ps, ps, H // ps, ps, 3).permute(0, 1, 3, 2, 4, 5).reshape(-1, pk)
+    assert torch.allclose(patches, refu, atol=1e-6)
+    Wk, bias, pos = torch.randn(W, pk, device=DEV), torch.randn(W, device=DEV), torch.randn(np_, W, device=DEV)
+    out = torch.empty(B * C * np_, W, device=DEV)
+    ops.sgemm(ref, Wk, out, B * C * np_, W, pk, pk, 1, pk, 1, ldc=W, bias=bias, table=pos, table_rows=np_)
+    exp = ref @ Wk.T + bias + pos.repeat(B * C, 1)
+    assert rel_err(out, exp) < 1e-5
+    X = torch.randn(500, 96, device=DEV).bfloat16()
+    cs = torch.zeros(96, device=DEV)
+    ops.colsum(X, 96, cs, 500, 96)
+    assert rel_err(cs, X.float().sum(0)) < 1e-4
+    ids = torch.randint(0, 100, (2, 7), device=DEV, dtype=torch.int32)
+    E = torch.randn(100, 64, device=DEV)
+    Xo = torch.zeros(2 * 12, 64, device=DEV, dtype=torch.bfloat16)
+    ops.embed_fwd(ids, E, Xo, 2, 7, 5, 12, 64, 8.0)
+    assert rel_err(Xo.view(2, 12, 64)[:, 5:], (E[ids.long()] * 8.0).bfloat16()) == 0
+    dE = torch.zeros_like(E)
+    ops.embed_bwd(ids, Xo, dE, 2, 7, 5, 12, 64, 8.0)
+    ref_dE = torch.zeros_like(E).index_add_(0, ids.view(-1).long(), Xo.view(2, 12, 64)[:, 5:].reshape(-1, 64).float() * 8.0)
+    assert rel_err(dE, ref_dE) < 1e-5

@@ -1,0 +1,121 @@
+"""CPU tests of the host side: parameter tree mapping, layout, C-ABI library loading and symbol export, error paths."""
+import ctypes
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from lap_b200 import _lib
+from lap_b200 import params as P
+from lap_b200.config import LAPConfig, get_config
+from lap_b200.data import synthetic_batch
+from lap_b200.observation import CoTObservation, Observation
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    syms = _lib.exported_symbols()
+    assert len(syms) >= 30
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert lib.lapb200_version() >= 100
+    assert isinstance(_lib.last_error(), str)
+
+
+def test_gemm_struct_matches_header_size():
+    # 64-bit fields are 8-aligned; a mismatch with include/lapb200.h would shift every later field
+    assert ctypes.sizeof(_lib.GemmParams) % 8 == 0
+    names = [f[0] for f in _lib.GemmParams._fields_]
+    import re
+    hdr = (_lib.INCLUDE / "lapb200.h").read_text()
+    body = hdr[hdr.index("typedef struct {"):hdr.index("} lapb_gemm_t;")]
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    decl = []
+    for stmt in body.split(";"):
+        stmt = stmt.replace("typedef struct {", "").strip()
+        if not stmt:
+            continue
+        parts = stmt.split(",")
+        for i, p_ in enumerate(parts):
+            decl.append(re.findall(r"[A-Za-z_0-9]+", p_)[-1])
+    assert decl == names
+
+
+def test_ops_reject_cpu_tensors():
+    from lap_b200 import ops
+    x = torch.zeros(16, dtype=torch.float32)
+    with pytest.raises(RuntimeError):
+        ops.cast_f32_bf16(x, torch.zeros(16, dtype=torch.bfloat16))
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_model_fails_loudly_without_gpu():
+    from lap_b200.model import LAP
+    with pytest.raises(RuntimeError):
+        LAP(get_config("debug_tiny").model)
+
+
+def test_reference_engine_roundtrip_is_exact():
+    for name in ("debug_tiny", "debug_small"):
+        cfg = get_config(name).model
+        ref = P.init_reference_params(cfg, 3, reference_zero_init=False)
+        eng = P.reference_to_engine(cfg, ref)
+        lay = P.FlatLayout(cfg)
+        for k, s in lay.shapes.items():
+            assert tuple(eng[k].shape) == tuple(s), k
+        flat = P.flat_from_engine(lay, eng)
+        back = P.engine_to_reference(cfg, P.engine_from_flat(lay, flat))
+        assert set(back) == set(ref)
+        for k in ref:
+            assert torch.equal(back[k], ref[k]), k
+        for k, o in lay.offsets.items():
+            assert o % P.ALIGN == 0
+        assert lay.kernel_end <= lay.offsets["g.embed"] and lay.total % 4 == 0
+
+
+def test_lap3b_parameter_count_and_names():
+    """3.353 B parameters; names/shapes of the checkpoint contract."""
+    cfg = get_config("lap_libero").model
+    shapes = P.reference_shapes(cfg)
+    n = sum(math.prod(s) for s in shapes.values())
+    assert abs(n / 1e9 - 3.353) < 0.002
+    assert shapes["PaliGemma/llm/layers/attn/q_einsum/w"] == (18, 8, 2048, 256)
+    assert shapes["PaliGemma/llm/layers/attn/kv_einsum_1/w"] == (18, 2, 1, 1024, 256)
+    assert shapes["PaliGemma/llm/layers/mlp/gating_einsum"] == (18, 2, 2048, 16384)
+    assert shapes["PaliGemma/img/Transformer/encoderblock/MlpBlock_0/Dense_0/kernel"] == (27, 1152, 4304)
+    assert shapes["PaliGemma/llm/layers/pre_ffw_norm_1/Dense_0/kernel"] == (18, 1024, 3072)
+    assert "PaliGemma/llm/layers/pre_ffw_norm_1/scale" not in shapes
+    assert shapes["PaliGemma/llm/embedder/input_embedding"] == (257152, 2048)
+    assert cfg.prefix_len == 692 and cfg.num_patches == 256
+
+
+def test_nested_tree_helpers():
+    flat = {"a/b/c": torch.ones(1), "a/d": torch.zeros(2)}
+    nested = P.to_nested(flat)
+    assert set(nested["a"].keys()) == {"b", "d"}
+    nested["a"]["d"] = {"value": nested["a"]["d"]}  # orbax-style `value` leaf
+    back = P.from_nested(nested)
+    assert set(back) == set(flat)
+
+
+def test_observation_from_dict_and_synthetic_batch():
+    cfg = get_config("debug_tiny").model
+    b = synthetic_batch(cfg, 4, step=2)
+    obs = CoTObservation.from_dict(b)
+    assert obs.tokenized_prompt.shape == (4, cfg.max_token_len)
+    assert set(obs.images) == set(cfg.image_keys)
+    la, pm = b["tokenized_langact_mask"], b["tokenized_prompt_mask"]
+    assert (la & ~pm).sum() == 0 and la.any(axis=1).all()
+    with pytest.raises(ValueError):
+        Observation.from_dict({"image": {}, "image_mask": {}, "state": None, "tokenized_prompt": 1})
+    b8 = synthetic_batch(cfg, 2, uint8_images=True)
+    assert b8["image"]["base_0_rgb"].dtype == np.uint8
+
+
+def test_config_registry():
+    c = get_config("lap_libero")
+    assert c.model.action_horizon == 10 and c.model.max_token_len == 180 and c.model.language_loss_weight == 0.4
+    assert c.optimizer.weight_decay == 1e-4 and c.ema_schedule_choice.kind == "constant"
+    with pytest.raises(ValueError):
+        get_config("nope")

@@ -31,13 +31,16 @@ def run(M, N, K, a_major=0, b_major=0, **kw):
     torch.cuda.synchronize()
     return report(f"gemm M={M} N={N} K={K} maj=({a_major},{b_major}) {kw}", C, ref)
 
+import os
+CGS = [int(x) for x in os.environ.get("CGS", "2").split(",")]
 for (M, N, K) in [(128, 128, 64), (128, 256, 64), (128, 128, 256), (256, 256, 512), (1024, 2048, 2048), (320, 1024, 1024), (200, 72, 256), (384, 1152, 4304), (500, 4304, 1152)]:
     for maj in [(0, 0), (0, 1), (1, 1), (1, 0)]:
         if maj[0] == 1 and M % 8: continue
-        try:
-            run(M, N, K, *maj)
-        except Exception as e:
-            print("EXC", M, N, K, maj, e)
+        for cg in CGS:
+            try:
+                run(M, N, K, *maj, cta_group=cg)
+            except Exception as e:
+                print("EXC", M, N, K, maj, e)
 run(512, 512, 512, block_n=128)
 run(512, 512, 512, block_n=256)
 
@@ -86,12 +89,14 @@ report("batched PV", O.reshape(-1, H), torch.einsum("bts,bsh->bth", P.float(), V
 # timing
 for (M, N, K, kw) in [(8192, 8192, 8192, {}), (22144, 2048, 2048, {}), (22144, 2048, 16384, {}), (16384, 4304, 1152, {}), (22144, 2560, 2048, {})]:
     A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(N, K, device=dev).bfloat16(); C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
-    for _ in range(3): ops.gemm(A, B, C, M=M, N=N, K=K, **kw)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(10): ops.gemm(A, B, C, M=M, N=N, K=K, **kw)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / 10
+    for cg in (1, 2):
+        for _ in range(3): ops.gemm(A, B, C, M=M, N=N, K=K, cta_group=cg, **kw)
+        e0.record()
+        for _ in range(10): ops.gemm(A, B, C, M=M, N=N, K=K, cta_group=cg, **kw)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 10
+        print(f"   cg={cg}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
     for _ in range(3): torch.matmul(A, B.T, out=C)
     e0.record()
     for _ in range(10): torch.matmul(A, B.T, out=C)
@@ -102,11 +107,78 @@ for (M, N, K, kw) in [(8192, 8192, 8192, {}), (22144, 2048, 2048, {}), (22144, 2
 M, F, K = 22144, 16384, 2048
 X = torch.randn(M, K, device=dev).bfloat16(); W = (torch.randn(2 * F, K, device=dev) * 0.02).bfloat16()
 act = torch.empty(M, F, device=dev, dtype=torch.bfloat16); gu = torch.empty(M, 2 * F, device=dev, dtype=torch.bfloat16)
-for _ in range(2): ops.gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, C2=gu, ldc2=2 * F)
 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+for cg in (1, 2):
+    for _ in range(2): ops.gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, C2=gu, ldc2=2 * F, cta_group=cg)
+    e0.record()
+    for _ in range(5): ops.gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, C2=gu, ldc2=2 * F, cta_group=cg)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"time GEGLU dual cg={cg} M={M} F={F} K={K}: {ms:.3f} ms = {2*M*2*F*K/ms/1e9:.1f} TFLOP/s")
+# wgrad / dgrad shapes of the Gemma MLP
+for (M, N, K, am, bm, f32) in [(22144, 16384, 2048, 0, 1, False), (32768, 2048, 22144, 1, 1, True), (2048, 16384, 22144, 1, 1, True), (22144, 2048, 32768, 0, 1, False)]:
+    A = torch.randn((M, K) if am == 0 else (K, M), device=dev).bfloat16(); B = torch.randn((N, K) if bm == 0 else (K, N), device=dev).bfloat16()
+    C = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.bfloat16)
+    for cg in (1, 2):
+        for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, a_major=am, b_major=bm, cta_group=cg)
+        e0.record()
+        for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, a_major=am, b_major=bm, cta_group=cg)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"time maj=({am},{bm}) f32out={f32} cg={cg} M={M} N={N} K={K}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+# split-K correctness + speed on under-filled wgrads
+for (M, N, K) in [(1152, 1152, 16384), (2560, 2048, 22144), (4304, 1152, 16384), (512, 384, 4000)]:
+    A = torch.randn(K, M, device=dev).bfloat16(); B = torch.randn(K, N, device=dev).bfloat16()
+    ref = A.float().T @ B.float()
+    for ks in (1, 0, 4):
+        C = torch.full((M, N), 7.0, device=dev)
+        ops.gemm(A, B, C, M=M, N=N, K=K, a_major=1, b_major=1, k_splits=ks)
+        report(f"wgrad split-K ks={ks} M={M} N={N} K={K}", C, ref)
+        for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, a_major=1, b_major=1, k_splits=ks)
+        e0.record()
+        for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, a_major=1, b_major=1, k_splits=ks)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        print(f"   ks={ks}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+    C = torch.ones(M, N, device=dev)
+    ops.gemm(A, B, C, M=M, N=N, K=K, a_major=1, b_major=1, k_splits=3, accumulate=True)
+    report("wgrad split-K accumulate", C, ref + 1)
+# SigLIP forward shapes with heavy epilogues
+M, N, K = 16384, 4304, 1152
+A = torch.randn(M, K, device=dev).bfloat16(); B = (torch.randn(N, K, device=dev) * 0.05).bfloat16(); bias = torch.randn(N, device=dev)
+C = torch.empty(M, N, device=dev, dtype=torch.bfloat16); C2 = torch.empty_like(C)
+for name, kw in [("bias_gelu", dict(epi=ops.EPI_BIAS_GELU, bias=bias, C2=C2, ldc2=N)), ("plain", {})]:
+    for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, **kw)
+    e0.record()
+    for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, **kw)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"siglip fc1 {name}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+M, N, K = 16384, 1152, 1152
+A = torch.randn(M, K, device=dev).bfloat16(); B = (torch.randn(N, K, device=dev) * 0.05).bfloat16(); bias = torch.randn(N, device=dev); R = torch.randn(M, N, device=dev).bfloat16()
+C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, bias=bias, epi=ops.EPI_RESID, resid=R)
 e0.record()
-for _ in range(5): ops.gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, C2=gu, ldc2=2 * F)
+for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, bias=bias, epi=ops.EPI_RESID, resid=R)
 e1.record(); torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 5
-print(f"time GEGLU dual M={M} F={F} K={K}: {ms:.3f} ms = {2*M*2*F*K/ms/1e9:.1f} TFLOP/s")
+print(f"siglip out-proj bias+resid: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+# leading-dimension experiment for the K=32768 dgrad shape
+M, N, K = 22144, 2048, 32768
+for pad in (0,):
+    A = torch.randn(M, K + pad, device=dev).bfloat16(); B = torch.randn(K, N, device=dev).bfloat16(); C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, b_major=1, lda=K + pad)
+    e0.record()
+    for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, b_major=1, lda=K + pad)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"dgrad K=32768 lda pad {pad}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
+for blk in ():
+    A = torch.randn(M, K, device=dev).bfloat16(); B = torch.randn(K, N, device=dev).bfloat16(); C = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+    for _ in range(2): ops.gemm(A, B, C, M=M, N=N, K=K, b_major=1, block_n=blk)
+    e0.record()
+    for _ in range(5): ops.gemm(A, B, C, M=M, N=N, K=K, b_major=1, block_n=blk)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"dgrad K=32768 block_n {blk}: {ms:.3f} ms = {2*M*N*K/ms/1e9:.1f} TFLOP/s", flush=True)
 print("DONE")
