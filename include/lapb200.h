@@ -42,7 +42,9 @@ enum {
   LAPB_EPI_RESID = 2,         /* C = bf16(resid + y), y = bf16(acc) (+bias)                 gemma.py:582     */
   LAPB_EPI_GATED_RESID = 3,   /* C = bf16(resid + bf16(y*gate[row/gate_rows]))              gemma.py:583     */
   LAPB_EPI_GEGLU = 4,         /* dual-B: C=bf16(gelu(g)*u), C2[:, n]=g, C2[:, n+N]=u        lora.py:124-142  */
-  LAPB_EPI_QSCALE = 5         /* as NONE(+bias); columns < q_cols are divided by q_div      flax MHA q/sqrt(d) */
+  LAPB_EPI_QSCALE = 5,        /* as NONE(+bias); columns < q_cols are divided by q_div      flax MHA q/sqrt(d) */
+  LAPB_EPI_GEGLU_BWD = 6,     /* acc = dAct; C2 = [g|u] in, [dg|du] out (in place); C = act (recomputed)   lora.py:124-142 bwd */
+  LAPB_EPI_GELU_BWD = 7       /* C = bf16(acc) * gelu'(C2)                                   siglip.py:71 bwd */
 };
 
 typedef struct {
@@ -89,8 +91,9 @@ int lapb200_cast_f32_bf16(const float* src, void* dst, int64_t n, lapb_stream_t 
 /* dst[v,0:D]=bf16(E[v]), dst[v,D:2D]=bf16(E[v]-hi): the fp32 table of Embedder.decode (gemma.py:153-154) as a hi/lo pair. */
 int lapb200_split_hi_lo(const float* src, void* dst, int64_t rows, int64_t D, lapb_stream_t s);
 /* images -> fp32 patch rows (siglip.py:216-223 conv as im2col); is_u8 fuses Observation.from_dict's u8/255*2-1 (OP/models/model.py:116-118). */
-int lapb200_patchify(const void* img0, const void* img1, const void* img2, int64_t is_u8, float* out, int64_t B,
-                     int64_t C, int64_t H, int64_t W, int64_t ps, lapb_stream_t s);
+int lapb200_patchify(const void* img0, const void* img1, const void* img2, int64_t is_u8, float* out, void* out_hi,
+                     void* out_lo, int64_t pk_pad, int64_t B, int64_t C, int64_t H, int64_t W, int64_t ps,
+                     lapb_stream_t s);
 /* fp32 CUDA-core GEMM with generic strides for the layers the reference keeps in fp32:
  * patch conv (siglip.py:216-229, +bias +pos_embedding table), action_in/out_proj, time MLP (pi0.py:159-169, lap.py:298). */
 int lapb200_sgemm(const void* A, int64_t a_bf16, const void* B, int64_t b_bf16, void* C, int64_t c_bf16, int64_t M,
@@ -170,6 +173,9 @@ int lapb200_mse_fwd_bwd(const float* v, const float* u, float* loss, float* dv, 
 int lapb200_weighted_sum(const float* x, const float* w, float* out, int64_t n, float alpha, int64_t accumulate,
                          lapb_stream_t s);
 
+/* buf[dst] = sqrt(buf[src]) on the device (param_norm = sqrt(sum p^2), scripts/train.py:411) */
+int lapb200_sqrt_scalar(float* buf, int64_t src, int64_t dst, lapb_stream_t s);
+
 /* K12: global-norm clip + AdamW + EMA + bf16 copy + norms over the flat state
  * (scripts/train.py:363-415; OP/training/optimizer.py:76-85). */
 int lapb200_opt_num_partials(void);
@@ -177,7 +183,7 @@ int lapb200_sumsq_partials(const float* x, int64_t n, float* partials, lapb_stre
 int lapb200_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* w16, int64_t n,
                       const float* gpartials, int64_t n_partials, float* stats, int64_t kernel_begin,
                       int64_t kernel_end, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
-                      float clip, float ema_decay, int64_t ema_on, lapb_stream_t s);
+                      float clip, float ema_decay, int64_t ema_on, const float* hyper, lapb_stream_t s);
 
 #ifdef __cplusplus
 }

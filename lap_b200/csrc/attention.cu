@@ -106,40 +106,57 @@ attn_softmax_fwd_kernel(const float* __restrict__ S, const uint32_t* __restrict_
   int lane = threadIdx.x & 31;
   long b = row / rows_per_batch, r = row % rows_per_batch;
   const uint32_t* mrow = bits + (b * (rows_per_batch / G) + r / G) * W32;
-  const float* s = S + row * ld;
-  int nw = ld / 32;
-  float v[32];
+  const float4* s4 = reinterpret_cast<const float4*>(S + row * ld);
+  const int ngroups = ld >> 2;  // float4 groups per row (ld % 32 == 0)
+  float4 v[8];
   float mx = -3.4e38f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < nw) {
-      int c = i * 32 + lane;
-      float x = BIG_NEG;
-      bool in = c < S_len;
-      if (in) {
-        uint32_t w = mrow[i];
-        x = ((w >> lane) & 1u) ? s[c] : BIG_NEG;
-        mx = fmaxf(mx, x);
-      }
+  for (int i = 0; i < 8; ++i) {
+    int g = lane + 32 * i;
+    if (g < ngroups) {
+      float4 x = s4[g];
+      int c = g * 4;
+      uint32_t m4 = (mrow[c >> 5] >> (c & 31)) & 0xFu;
+      x.x = (m4 & 1u) ? x.x : BIG_NEG;
+      x.y = (m4 & 2u) ? x.y : BIG_NEG;
+      x.z = (m4 & 4u) ? x.z : BIG_NEG;
+      x.w = (m4 & 8u) ? x.w : BIG_NEG;
+      // columns >= S_len are padding: excluded from max / sum, written as 0
+      if (c + 0 < S_len) mx = fmaxf(mx, x.x);
+      if (c + 1 < S_len) mx = fmaxf(mx, x.y);
+      if (c + 2 < S_len) mx = fmaxf(mx, x.z);
+      if (c + 3 < S_len) mx = fmaxf(mx, x.w);
       v[i] = x;
     }
   }
   mx = warp_max(mx);
   float sum = 0.f;
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < nw) {
-      int c = i * 32 + lane;
-      float e = (c < S_len) ? __expf(v[i] - mx) : 0.f;
+  for (int i = 0; i < 8; ++i) {
+    int g = lane + 32 * i;
+    if (g < ngroups) {
+      int c = g * 4;
+      float4 e;
+      e.x = (c + 0 < S_len) ? __expf(v[i].x - mx) : 0.f;
+      e.y = (c + 1 < S_len) ? __expf(v[i].y - mx) : 0.f;
+      e.z = (c + 2 < S_len) ? __expf(v[i].z - mx) : 0.f;
+      e.w = (c + 3 < S_len) ? __expf(v[i].w - mx) : 0.f;
+      sum += (e.x + e.y) + (e.z + e.w);
       v[i] = e;
-      sum += e;
     }
   }
   sum = warp_sum(sum);
   float inv = 1.0f / sum;
+  uint2* p2 = reinterpret_cast<uint2*>(Pout + row * ld);
 #pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    if (i < nw) Pout[row * ld + i * 32 + lane] = __float2bfloat16_rn(v[i] * inv);
+  for (int i = 0; i < 8; ++i) {
+    int g = lane + 32 * i;
+    if (g < ngroups) {
+      uint2 o;
+      o.x = pack_bf16x2(v[i].x * inv, v[i].y * inv);
+      o.y = pack_bf16x2(v[i].z * inv, v[i].w * inv);
+      p2[g] = o;
+    }
   }
 }
 
@@ -171,44 +188,57 @@ softmax_bwd_kernel(const bf16* __restrict__ P, const bf16* __restrict__ dP, bf16
 //   e = bf16(exp(bf16(x - max)));  p = bf16(e / bf16(sum e))          [mode 0: as written in jax.nn.softmax on bf16]
 //   p = bf16(softmax_fp32(x))                                          [mode 1]
 // ------------------------------------------------------------------------------------------------
+template <int NV>
 __global__ void __launch_bounds__(256)
 vit_softmax_fwd_kernel(bf16* __restrict__ S, int n, int ld, long total_rows, int mode) {
   long row = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
   if (row >= total_rows) return;
   int lane = threadIdx.x & 31;
   bf16* s = S + row * ld;
+  const int nvec = n >> 3;  // 8 bf16 per 16-byte vector (n % 8 == 0)
+  float x[NV][8];
   float mx = -3.4e38f;
-  for (int c = lane * 2; c < n; c += 64) {
-    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
-    mx = fmaxf(mx, fmaxf(x.x, x.y));
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int v = lane + 32 * i;
+    if (v < nvec) {
+      uint4 u = *reinterpret_cast<const uint4*>(s + v * 8);
+      float2 f;
+      f = unpack_bf16x2(u.x); x[i][0] = f.x; x[i][1] = f.y;
+      f = unpack_bf16x2(u.y); x[i][2] = f.x; x[i][3] = f.y;
+      f = unpack_bf16x2(u.z); x[i][4] = f.x; x[i][5] = f.y;
+      f = unpack_bf16x2(u.w); x[i][6] = f.x; x[i][7] = f.y;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) mx = fmaxf(mx, x[i][j]);
+    }
   }
   mx = warp_max(mx);
   float sum = 0.f;
-  for (int c = lane * 2; c < n; c += 64) {
-    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
-    float e0, e1;
-    if (mode == 0) {
-      e0 = bf16r(__expf(bf16r(x.x - mx)));
-      e1 = bf16r(__expf(bf16r(x.y - mx)));
-    } else {
-      e0 = __expf(x.x - mx);
-      e1 = __expf(x.y - mx);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int v = lane + 32 * i;
+    if (v < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float e = (mode == 0) ? bf16r(__expf(bf16r(x[i][j] - mx))) : __expf(x[i][j] - mx);
+        x[i][j] = e;
+        sum += e;
+      }
     }
-    sum += e0 + e1;
   }
   sum = warp_sum(sum);
   if (mode == 0) sum = bf16r(sum);
-  for (int c = lane * 2; c < n; c += 64) {
-    float2 x = unpack_bf16x2(*reinterpret_cast<const uint32_t*>(s + c));
-    float e0, e1;
-    if (mode == 0) {
-      e0 = bf16r(__expf(bf16r(x.x - mx)));
-      e1 = bf16r(__expf(bf16r(x.y - mx)));
-    } else {
-      e0 = __expf(x.x - mx);
-      e1 = __expf(x.y - mx);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    int v = lane + 32 * i;
+    if (v < nvec) {
+      uint4 u;
+      u.x = pack_bf16x2(x[i][0] / sum, x[i][1] / sum);
+      u.y = pack_bf16x2(x[i][2] / sum, x[i][3] / sum);
+      u.z = pack_bf16x2(x[i][4] / sum, x[i][5] / sum);
+      u.w = pack_bf16x2(x[i][6] / sum, x[i][7] / sum);
+      *reinterpret_cast<uint4*>(s + v * 8) = u;
     }
-    *reinterpret_cast<uint32_t*>(s + c) = pack_bf16x2(e0 / sum, e1 / sum);
   }
 }
 
@@ -257,8 +287,13 @@ int lapb200_softmax_bwd(const void* P, const void* dP, void* dS, int64_t rows, i
 }
 
 int lapb200_vit_softmax_fwd(void* S, int64_t rows, int64_t n, int64_t ld, int64_t mode, lapb_stream_t s) {
-  LAPB_REQUIRE(n % 2 == 0 && ld % 2 == 0, "vit_softmax: n, ld must be even");
-  vit_softmax_fwd_kernel<<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((bf16*)S, (int)n, (int)ld, rows, (int)mode);
+  LAPB_REQUIRE(n % 8 == 0 && ld % 8 == 0 && n <= 1024, "vit_softmax: n, ld must be multiples of 8 and n <= 1024");
+  if (n <= 256)
+    vit_softmax_fwd_kernel<1><<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((bf16*)S, (int)n, (int)ld, rows, (int)mode);
+  else if (n <= 512)
+    vit_softmax_fwd_kernel<2><<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((bf16*)S, (int)n, (int)ld, rows, (int)mode);
+  else
+    vit_softmax_fwd_kernel<4><<<cdiv(rows, 8), 256, 0, STREAM(s)>>>((bf16*)S, (int)n, (int)ld, rows, (int)mode);
   LAPB_LAUNCH_OK("vit_softmax_fwd");
   return 0;
 }

@@ -7,6 +7,7 @@
 #include "../../include/lapb200.h"
 #include "common.cuh"
 #include "host_util.h"
+#include <algorithm>
 
 namespace lapb {
 
@@ -75,7 +76,8 @@ struct ImgPtrs {
   const void* p[4];
 };
 template <bool U8>
-__global__ void patchify_kernel(ImgPtrs imgs, float* __restrict__ out, int B, int C, int H, int W, int ps) {
+__global__ void patchify_kernel(ImgPtrs imgs, float* __restrict__ out, bf16* __restrict__ out_hi,
+                                bf16* __restrict__ out_lo, int pk_pad, int B, int C, int H, int W, int ps) {
   int gh = H / ps, gw = W / ps, np = gh * gw, pk = ps * ps * 3;
   long total = (long)B * C * np * pk;
   for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
@@ -93,6 +95,11 @@ __global__ void patchify_kernel(ImgPtrs imgs, float* __restrict__ out, int B, in
     else
       v = reinterpret_cast<const float*>(imgs.p[cam])[off];
     out[idx] = v;
+    if (out_hi) {  // bf16 hi/lo split of the patch matrix (tensor-core weight gradient of the fp32 conv)
+      float hi = bf16r(v);
+      out_hi[row * pk_pad + col] = __float2bfloat16_rn(hi);
+      out_lo[row * pk_pad + col] = __float2bfloat16_rn(v - hi);
+    }
   }
 }
 
@@ -196,24 +203,32 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale
   }
 }
 
-// dx = dres + LN'(dy); dscale += sum dy*xhat; dbias += sum dy.  Each CTA handles `rows_per_cta` rows and issues one
-// atomicAdd per column at the end.
-__global__ void __launch_bounds__(128)
+// dx = dres + LN'(dy); dscale += sum dy*xhat; dbias += sum dy.
+// One WARP per row, shuffle reductions only.  Two passes over the row (the second read is served by L1/L2) keep
+// the register footprint small so many warps — and many bytes — are in flight per SM.  Each lane owns fixed columns
+// and keeps its dscale/dbias partial sums in registers across the rows of its warp; the warps of a CTA are combined
+// in shared memory and issue one atomicAdd per column per CTA.
+template <int NV>
+__global__ void __launch_bounds__(256)
 layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ scale,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
-                     bf16* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias, long M, int W,
-                     int rows_per_cta) {
-  __shared__ float red[32];
-  constexpr int MAXV = 2;  // W <= 128*8*MAXV = 2048
-  float ds[MAXV][8] = {}, db[MAXV][8] = {};
-  long r0 = (long)blockIdx.x * rows_per_cta;
-  for (long row = r0; row < r0 + rows_per_cta && row < M; ++row) {
-    float mu = mean[row], rs = rstd[row];
-    float g[MAXV][8], xh[MAXV][8];
+                     bf16* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias, long M, int W) {
+  extern __shared__ float sred[];  // [2][W]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ds[NV][8], db[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { ds[i][j] = 0.f; db[i][j] = 0.f; }
+  for (int c = threadIdx.x; c < 2 * W; c += 256) sred[c] = 0.f;
+  __syncthreads();
+  const long nwarps = (long)gridDim.x * 8;
+  for (long row = (long)blockIdx.x * 8 + warp; row < M; row += nwarps) {
+    const float mu = mean[row], rs = rstd[row];
     float sg = 0.f, sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int c = (threadIdx.x + i * 128) * 8;
+    for (int i = 0; i < NV; ++i) {
+      int c = (lane + 32 * i) * 8;
       if (c < W) {
         float d[8], xv[8], sc[8];
         ld8(dy + row * W + c, d);
@@ -221,26 +236,29 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
         ld8f(scale + c, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = (xv[j] - mu) * rs;
-          g[i][j] = d[j] * sc[j];
-          sg += g[i][j];
-          sgx += g[i][j] * xh[i][j];
-          ds[i][j] += d[j] * xh[i][j];
+          float xh = (xv[j] - mu) * rs, g = d[j] * sc[j];
+          sg += g;
+          sgx += g * xh;
+          ds[i][j] += d[j] * xh;
           db[i][j] += d[j];
         }
       }
     }
-    sg = block_sum(sg, red) / W;
-    sgx = block_sum(sgx, red) / W;
+    sg = warp_sum(sg) / W;
+    sgx = warp_sum(sgx) / W;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int c = (threadIdx.x + i * 128) * 8;
+    for (int i = 0; i < NV; ++i) {
+      int c = (lane + 32 * i) * 8;
       if (c < W) {
-        float o[8], rr[8];
+        float d[8], xv[8], sc[8], o[8], rr[8];
+        ld8(dy + row * W + c, d);
+        ld8(x + row * W + c, xv);
+        ld8f(scale + c, sc);
         if (dres) ld8(dres + row * W + c, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (g[i][j] - sg - xh[i][j] * sgx);
+          float xh = (xv[j] - mu) * rs;
+          o[j] = rs * (d[j] * sc[j] - sg - xh * sgx);
           if (dres) o[j] += rr[j];
         }
         st8(dx + row * W + c, o);
@@ -248,15 +266,20 @@ layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, co
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int c = (threadIdx.x + i * 128) * 8;
+  for (int i = 0; i < NV; ++i) {
+    int c = (lane + 32 * i) * 8;
     if (c < W) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(dscale + c + j, ds[i][j]);
-        atomicAdd(dbias + c + j, db[i][j]);
+        atomicAdd(&sred[c + j], ds[i][j]);
+        atomicAdd(&sred[W + c + j], db[i][j]);
       }
     }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < W; c += 256) {
+    atomicAdd(dscale + c, sred[c]);
+    atomicAdd(dbias + c, sred[W + c]);
   }
 }
 
@@ -306,23 +329,29 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, long ldx, const long* __restrict_
 }
 
 // plain RMSNorm backward: dx[dst] = (dres? dres:0) + rstd*(g - xhat*mean(g*xhat)), g = dy*(1+scale); dscale += dy*xhat
-__global__ void __launch_bounds__(128)
+// (warp per row, two passes, same structure as layernorm_bwd_kernel)
+template <int NV>
+__global__ void __launch_bounds__(256)
 rmsnorm_bwd_kernel(const bf16* __restrict__ dy, long lddy, const bf16* __restrict__ x, long ldx,
                    const long* __restrict__ row_idx, const float* __restrict__ scale, const float* __restrict__ rstd,
-                   const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dscale, long M, int D,
-                   int rows_per_cta) {
-  __shared__ float red[32];
-  constexpr int MAXV = 2;  // D <= 2048
-  float ds[MAXV][8] = {};
-  long r0 = (long)blockIdx.x * rows_per_cta;
-  for (long row = r0; row < r0 + rows_per_cta && row < M; ++row) {
-    long src = row_idx ? row_idx[row] : row;
-    float rs = rstd[row];
-    float g[MAXV][8], xh[MAXV][8];
+                   const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dscale, long M, int D) {
+  extern __shared__ float sred[];  // [D]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float ds[NV][8];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) ds[i][j] = 0.f;
+  for (int c = threadIdx.x; c < D; c += 256) sred[c] = 0.f;
+  __syncthreads();
+  const long nwarps = (long)gridDim.x * 8;
+  for (long row = (long)blockIdx.x * 8 + warp; row < M; row += nwarps) {
+    const long src = row_idx ? row_idx[row] : row;
+    const float rs = rstd[row];
     float sgx = 0.f;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int c = (threadIdx.x + i * 128) * 8;
+    for (int i = 0; i < NV; ++i) {
+      int c = (lane + 32 * i) * 8;
       if (c < D) {
         float d[8], xv[8], sc[8];
         ld8(dy + row * lddy + c, d);
@@ -330,23 +359,25 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, long lddy, const bf16* __restric
         ld8f(scale + c, sc);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          xh[i][j] = xv[j] * rs;
-          g[i][j] = d[j] * (1.0f + sc[j]);
-          sgx += g[i][j] * xh[i][j];
-          ds[i][j] += d[j] * xh[i][j];
+          float xh = xv[j] * rs;
+          sgx += d[j] * (1.0f + sc[j]) * xh;
+          ds[i][j] += d[j] * xh;
         }
       }
     }
-    sgx = block_sum(sgx, red) / D;
+    sgx = warp_sum(sgx) / D;
 #pragma unroll
-    for (int i = 0; i < MAXV; ++i) {
-      int c = (threadIdx.x + i * 128) * 8;
+    for (int i = 0; i < NV; ++i) {
+      int c = (lane + 32 * i) * 8;
       if (c < D) {
-        float o[8], rr[8];
+        float d[8], xv[8], sc[8], o[8], rr[8];
+        ld8(dy + row * lddy + c, d);
+        ld8(x + src * ldx + c, xv);
+        ld8f(scale + c, sc);
         if (dres) ld8(dres + src * ldx + c, rr);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (g[i][j] - xh[i][j] * sgx);
+          o[j] = rs * (d[j] * (1.0f + sc[j]) - xv[j] * rs * sgx);
           if (dres) o[j] += rr[j];
         }
         st8(dx + src * ldx + c, o);
@@ -354,13 +385,15 @@ rmsnorm_bwd_kernel(const bf16* __restrict__ dy, long lddy, const bf16* __restric
     }
   }
 #pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    int c = (threadIdx.x + i * 128) * 8;
+  for (int i = 0; i < NV; ++i) {
+    int c = (lane + 32 * i) * 8;
     if (c < D) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(dscale + c + j, ds[i][j]);
+      for (int j = 0; j < 8; ++j) atomicAdd(&sred[c + j], ds[i][j]);
     }
   }
+  __syncthreads();
+  for (int c = threadIdx.x; c < D; c += 256) atomicAdd(dscale + c, sred[c]);
 }
 
 // adaptive RMSNorm backward, one CTA per sample (rows_per_sample rows):
@@ -708,16 +741,17 @@ int lapb200_split_hi_lo(const float* src, void* dst, int64_t rows, int64_t D, la
   return 0;
 }
 
-int lapb200_patchify(const void* img0, const void* img1, const void* img2, int64_t is_u8, float* out, int64_t B,
-                     int64_t C, int64_t H, int64_t W, int64_t ps, lapb_stream_t s) {
+int lapb200_patchify(const void* img0, const void* img1, const void* img2, int64_t is_u8, float* out, void* out_hi,
+                     void* out_lo, int64_t pk_pad, int64_t B, int64_t C, int64_t H, int64_t W, int64_t ps,
+                     lapb_stream_t s) {
   LAPB_REQUIRE(C >= 1 && C <= 3, "patchify: 1..3 cameras");
   ImgPtrs p;
   p.p[0] = img0; p.p[1] = img1; p.p[2] = img2; p.p[3] = nullptr;
   long total = B * C * (H / ps) * (W / ps) * ps * ps * 3;
   if (is_u8)
-    patchify_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(s)>>>(p, out, B, C, H, W, ps);
+    patchify_kernel<true><<<grid_for(total, 256), 256, 0, STREAM(s)>>>(p, out, (bf16*)out_hi, (bf16*)out_lo, (int)pk_pad, B, C, H, W, ps);
   else
-    patchify_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(s)>>>(p, out, B, C, H, W, ps);
+    patchify_kernel<false><<<grid_for(total, 256), 256, 0, STREAM(s)>>>(p, out, (bf16*)out_hi, (bf16*)out_lo, (int)pk_pad, B, C, H, W, ps);
   LAPB_LAUNCH_OK("patchify");
   return 0;
 }
@@ -752,11 +786,16 @@ int lapb200_layernorm_bwd(const void* dy, const void* x, const float* scale, con
                           const void* dres, void* dx, float* dscale, float* dbias, int64_t M, int64_t W,
                           lapb_stream_t s) {
   LAPB_REQUIRE(W % 8 == 0 && W <= 2048, "layernorm_bwd: W must be a multiple of 8 and <= 2048");
-  int rpc = (int)((M + 148 * 8 - 1) / (148 * 8));
-  if (rpc < 1) rpc = 1;
-  layernorm_bwd_kernel<<<cdiv(M, rpc), 128, 0, STREAM(s)>>>((const bf16*)dy, (const bf16*)x, scale, mean, rstd,
-                                                            (const bf16*)dres, (bf16*)dx, dscale, dbias, M, (int)W,
-                                                            rpc);
+  int grid = (int)std::min<long>((M + 7) / 8, 148L * 8);
+  size_t smem = 2 * (size_t)W * sizeof(float);
+#define LN_BWD(NV)                                                                                                  \
+  layernorm_bwd_kernel<NV><<<grid, 256, smem, STREAM(s)>>>((const bf16*)dy, (const bf16*)x, scale, mean, rstd,      \
+                                                           (const bf16*)dres, (bf16*)dx, dscale, dbias, M, (int)W)
+  if (W <= 256) LN_BWD(1);
+  else if (W <= 1024) LN_BWD(4);
+  else if (W <= 1280) LN_BWD(5);
+  else LN_BWD(8);
+#undef LN_BWD
   LAPB_LAUNCH_OK("layernorm_bwd");
   return 0;
 }
@@ -779,11 +818,17 @@ int lapb200_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx
                         const float* scale, const float* rstd, const void* dres, void* dx, float* dscale, int64_t M,
                         int64_t D, lapb_stream_t s) {
   LAPB_REQUIRE(D % 8 == 0 && D <= 2048, "rmsnorm_bwd: D must be a multiple of 8 and <= 2048");
-  int rpc = (int)((M + 148 * 8 - 1) / (148 * 8));
-  if (rpc < 1) rpc = 1;
-  rmsnorm_bwd_kernel<<<cdiv(M, rpc), 128, 0, STREAM(s)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx,
-                                                          (const long*)row_idx, scale, rstd, (const bf16*)dres,
-                                                          (bf16*)dx, dscale, M, (int)D, rpc);
+  int grid = (int)std::min<long>((M + 7) / 8, 148L * 8);
+  size_t smem = (size_t)D * sizeof(float);
+#define RMS_BWD(NV)                                                                                              \
+  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, STREAM(s)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx,              \
+                                                         (const long*)row_idx, scale, rstd, (const bf16*)dres,    \
+                                                         (bf16*)dx, dscale, M, (int)D)
+  if (D <= 256) RMS_BWD(1);
+  else if (D <= 1024) RMS_BWD(4);
+  else if (D <= 1280) RMS_BWD(5);
+  else RMS_BWD(8);
+#undef RMS_BWD
   LAPB_LAUNCH_OK("rmsnorm_bwd");
   return 0;
 }

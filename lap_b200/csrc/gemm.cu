@@ -343,6 +343,33 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const GemmKArgs& a, uint8_t*
         if (col0 + j < a.q_cols) x[j] = bf16r(x[j]) * a.q_div;  // q_div holds 1/divisor
       break;
     }
+    case LAPB_EPI_GELU_BWD: {
+      float pre[32];
+      staged_load_bf16(stg, lane, a.C2 + c_boff + row0 * a.ldc2 + col0, a.ldc2, rows_valid, cols_valid, pre);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = bf16r(x[j]) * gelu_tanh_grad(pre[j]);
+      break;
+    }
+    case LAPB_EPI_GEGLU_BWD: {
+      // acc = dAct (rounded to bf16 like the stored cotangent); recompute act, emit dg/du over g/u in place
+      __nv_bfloat16* gu = a.C2 + row0 * a.ldc2 + col0;
+      float g[32], u[32];
+      staged_load_bf16(stg, lane, gu, a.ldc2, rows_valid, cols_valid, g);
+      staged_load_bf16(stg, lane, gu + a.N, a.ldc2, rows_valid, cols_valid, u);
+      uint32_t pdg[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        float d0 = bf16r(x[2 * j]), d1 = bf16r(x[2 * j + 1]);
+        float ge0 = bf16r(gelu_tanh(g[2 * j])), ge1 = bf16r(gelu_tanh(g[2 * j + 1]));
+        pdg[j] = pack_bf16x2(d0 * u[2 * j] * gelu_tanh_grad(g[2 * j]), d1 * u[2 * j + 1] * gelu_tanh_grad(g[2 * j + 1]));
+        pk[j] = pack_bf16x2(d0 * ge0, d1 * ge1);  // du
+        x[2 * j] = ge0 * u[2 * j];                 // act
+        x[2 * j + 1] = ge1 * u[2 * j + 1];
+      }
+      staged_store_bf16(stg, lane, pdg, gu, a.ldc2, rows_valid, cols_valid);
+      staged_store_bf16(stg, lane, pk, gu + a.N, a.ldc2, rows_valid, cols_valid);
+      break;
+    }
     default:
       break;
   }
@@ -662,6 +689,8 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
     LAPB_REQUIRE(p->resid != nullptr && p->ldr % 8 == 0, "gemm: residual epilogue needs resid with ldr%%8==0");
   if (p->epi == LAPB_EPI_GATED_RESID)
     LAPB_REQUIRE(p->gate != nullptr && p->gate_rows > 0 && p->ldg % 8 == 0, "gemm: gated epilogue needs gate");
+  if (p->epi == LAPB_EPI_GEGLU_BWD || p->epi == LAPB_EPI_GELU_BWD)
+    LAPB_REQUIRE(p->C2 != nullptr && p->ldc2 % 8 == 0 && !p->c_fp32, "gemm: activation-backward epilogue needs bf16 C and C2");
 
   int bi = p->batch_i > 0 ? p->batch_i : 1, bo = p->batch_o > 0 ? p->batch_o : 1;
   int BN;

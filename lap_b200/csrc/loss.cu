@@ -82,6 +82,8 @@ weighted_sum_kernel(const float* __restrict__ x, const float* __restrict__ w, fl
   if (threadIdx.x == 0) out[0] = (accumulate ? out[0] : 0.f) + alpha * acc;
 }
 
+__global__ void sqrt_scalar_kernel(float* buf, int src, int dst) { buf[dst] = sqrtf(buf[src]); }
+
 }  // namespace lapb
 
 using namespace lapb;
@@ -110,6 +112,12 @@ int lapb200_weighted_sum(const float* x, const float* w, float* out, int64_t n, 
                          lapb_stream_t s) {
   weighted_sum_kernel<<<1, 256, 0, STREAM(s)>>>(x, w, out, n, alpha, (int)accumulate);
   LAPB_LAUNCH_OK("weighted_sum");
+  return 0;
+}
+
+int lapb200_sqrt_scalar(float* buf, int64_t src, int64_t dst, lapb_stream_t s) {
+  sqrt_scalar_kernel<<<1, 1, 0, STREAM(s)>>>(buf, (int)src, (int)dst);
+  LAPB_LAUNCH_OK("sqrt_scalar");
   return 0;
 }
 

@@ -42,10 +42,15 @@ struct AdamArgs {
   long kernel_begin, kernel_end;  // element range counted in param_norm
   float lr, b1, b2, eps, wd, bc1, bc2, clip, ema_decay;
   int ema_on;
+  const float* hyper;  // optional device array [lr, bc1, bc2, ema_decay, ema_on]: overrides the by-value fields
 };
 
 __global__ void __launch_bounds__(OPT_THREADS) adamw_ema_kernel(AdamArgs a) {
   __shared__ float red[32];
+  if (a.hyper) {  // per-step scalars live in device memory so a captured CUDA graph can be replayed unchanged
+    a.lr = a.hyper[0]; a.bc1 = a.hyper[1]; a.bc2 = a.hyper[2]; a.ema_decay = a.hyper[3];
+    a.ema_on = a.hyper[4] != 0.f;
+  }
   __shared__ float s_scale;
   float acc = 0.f;
   for (int i = threadIdx.x; i < a.n_partials; i += OPT_THREADS) acc += a.gpartials[i];
@@ -122,7 +127,7 @@ int lapb200_sumsq_partials(const float* x, int64_t n, float* partials, lapb_stre
 int lapb200_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, void* w16, int64_t n,
                       const float* gpartials, int64_t n_partials, float* stats, int64_t kernel_begin,
                       int64_t kernel_end, float lr, float b1, float b2, float eps, float wd, float bc1, float bc2,
-                      float clip, float ema_decay, int64_t ema_on, lapb_stream_t s) {
+                      float clip, float ema_decay, int64_t ema_on, const float* hyper, lapb_stream_t s) {
   LAPB_REQUIRE(n % 4 == 0, "adamw: n must be a multiple of 4");
   LAPB_REQUIRE(kernel_begin % 4 == 0 && kernel_end % 4 == 0, "adamw: kernel range must be 4-aligned");
   AdamArgs a;
@@ -130,7 +135,7 @@ int lapb200_adamw_ema(float* p, const float* g, float* m, float* v, float* ema, 
   a.gpartials = gpartials; a.n_partials = (int)n_partials; a.stats = stats;
   a.kernel_begin = kernel_begin; a.kernel_end = kernel_end;
   a.lr = lr; a.b1 = b1; a.b2 = b2; a.eps = eps; a.wd = wd; a.bc1 = bc1; a.bc2 = bc2; a.clip = clip;
-  a.ema_decay = ema_decay; a.ema_on = (int)ema_on;
+  a.ema_decay = ema_decay; a.ema_on = (int)ema_on; a.hyper = hyper;
   adamw_ema_kernel<<<num_sms() * 8, OPT_THREADS, 0, STREAM(s)>>>(a);
   LAPB_LAUNCH_OK("adamw_ema");
   return 0;

@@ -87,6 +87,9 @@ class LAP:
         self.E_split = torch.zeros(cfg.vocab_size, 2 * D, dtype=BF16, device=self.device)
         self.G: torch.Tensor | None = None  # flat grads, allocated by the trainer
         self._bufs: dict[str, torch.Tensor] = {}
+        self._io: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}  # persistent (pinned host, device) input buffers
+        self._io_event = None
+        self.R_cap: int | None = None
         hd = cfg.gemma.head_dim
         ts = (10_000.0 ** ((2.0 / hd) * torch.arange(hd // 2, dtype=torch.float32))).to(self.device)
         self.timescale = ts
@@ -189,21 +192,29 @@ class LAP:
         cfg = self.cfg
         dev = self.device
         nbytes = 0
+        # Inputs land in PERSISTENT device buffers (fixed addresses -> the step can be replayed as a CUDA graph) through
+        # persistent pinned host buffers.  The previous step's H2D copies must have executed before the pinned
+        # buffers are overwritten.
+        if self._io_event is not None:
+            self._io_event.synchronize()
 
-        def up(x, dtype=None):
+        def up(x, dtype=None, name=None):
             nonlocal nbytes
-            if isinstance(x, torch.Tensor):
-                t = x
+            t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
+            dtype = dtype or t.dtype
+            ent = self._io.get(name)
+            if ent is None or tuple(ent[1].shape) != tuple(t.shape) or ent[1].dtype != dtype:
+                ent = (torch.empty(tuple(t.shape), dtype=dtype).pin_memory(),
+                       torch.empty(tuple(t.shape), dtype=dtype, device=dev))
+                self._io[name] = ent
+            host, devbuf = ent
+            if t.is_cuda:
+                devbuf.copy_(t)
             else:
-                t = torch.from_numpy(np.ascontiguousarray(x))
-            if dtype is not None and t.dtype != dtype:
-                t = t.to(dtype)
-            if t.device != dev:
-                nbytes += t.numel() * t.element_size()
-                if not t.is_cuda and not t.is_pinned():
-                    t = t.pin_memory()
-                t = t.to(dev, non_blocking=True)
-            return t.contiguous()
+                host.copy_(t)
+                devbuf.copy_(host, non_blocking=True)
+                nbytes += host.numel() * host.element_size()
+            return devbuf
 
         images = []
         for k in cfg.image_keys:
@@ -214,7 +225,7 @@ class LAP:
             if tuple(im_t.shape[1:3]) != (cfg.image_size, cfg.image_size):
                 raise ValueError(f"image {k} has resolution {tuple(im_t.shape[1:3])}; resize_with_pad is outside the "
                                  f"hot path (model_adapter.py:113-116) — provide {cfg.image_size}x{cfg.image_size}")
-            images.append(up(im_t))
+            images.append(up(im_t, name=f"img.{k}"))
         B = images[0].shape[0]
         Np, L, C = cfg.num_patches, cfg.max_token_len, len(cfg.image_keys)
         tokens = to_numpy(obs.tokenized_prompt).astype(np.int32)
@@ -233,15 +244,16 @@ class LAP:
         else:
             pma = pm
         A = cfg.action_horizon
-        st = Staged(B=B, images=images, tokens=up(tokens), pm=up(pm.astype(np.uint8)), par=up(par.astype(np.uint8)),
-                    pma=up(pma.astype(np.uint8)),
-                    sm=up(np.ones((B, A), np.uint8)), sar=up(np.tile(np.array([1] + [0] * (A - 1), np.uint8), (B, 1))))
+        st = Staged(B=B, images=images, tokens=up(tokens, name="tokens"), pm=up(pm.astype(np.uint8), name="pm"),
+                    par=up(par.astype(np.uint8), name="par"), pma=up(pma.astype(np.uint8), name="pma"),
+                    sm=up(np.ones((B, A), np.uint8), name="sm"),
+                    sar=up(np.tile(np.array([1] + [0] * (A - 1), np.uint8), (B, 1)), name="sar"))
         if actions is not None:
-            st.actions = up(to_numpy(actions).astype(np.float32))
+            st.actions = up(to_numpy(actions).astype(np.float32), name="actions")
         if noise is not None:
-            st.noise = up(to_numpy(noise).astype(np.float32))
+            st.noise = up(to_numpy(noise).astype(np.float32), name="noise")
         if time is not None:
-            st.time = up(to_numpy(time).astype(np.float32))
+            st.time = up(to_numpy(time).astype(np.float32), name="time")
         if with_loss:
             if la is None:
                 raise ValueError("compute_loss needs tokenized_langact_mask (lap.py:232)")
@@ -256,7 +268,10 @@ class LAP:
             n_active = max(n_active, 1.0)
             bb, jj = np.nonzero(lm)
             R = len(bb)
-            Rp = max(_round_up(R, 128), 128)
+            # fixed row capacity (padding rows weigh 0) so that the captured step keeps its shapes; grows if needed
+            if self.R_cap is None or R > self.R_cap:
+                self.R_cap = max(_round_up(int(R * 1.25) + 1, 128), 128)
+            Rp = self.R_cap
             rows = np.zeros(Rp, np.int64)
             tgt = np.zeros(Rp, np.int32)
             wts = np.zeros(Rp, np.float32)
@@ -267,11 +282,13 @@ class LAP:
             wts[:R] = cfg.language_loss_weight / (n_b[bb] * n_active)
             smp[:R] = bb
             inv[:R] = 1.0 / n_b[bb]
-            st.ce_rows, st.ce_targets, st.ce_weights = up(rows), up(tgt), up(wts)
-            st.ce_sample, st.ce_inv_count = up(smp), up(inv)
+            st.ce_rows, st.ce_targets, st.ce_weights = up(rows, name="ce_rows"), up(tgt, name="ce_tgt"), up(wts, name="ce_w")
+            st.ce_sample, st.ce_inv_count = up(smp, name="ce_smp"), up(inv, name="ce_inv")
             st.R = Rp
             st.n_active, st.n_action = n_active, max(n_action, 1.0)
-            st.sample_mask = up(smask.astype(np.float32))
+            st.sample_mask = up(smask.astype(np.float32), name="sample_mask")
+        self._io_event = torch.cuda.Event()
+        self._io_event.record()
         st.h2d_bytes = nbytes
         LAP.last_h2d_bytes = nbytes
         return st
@@ -300,7 +317,10 @@ class LAP:
         Ni, Ms = B * C, B * C * Np
         pk = s.patch_size * s.patch_size * 3
         patches = self.buf("img.patches", (Ms, pk), F32)
-        ops.patchify(st.images, patches, B, C, cfg.image_size, cfg.image_size, s.patch_size)
+        pk_pad = _round_up(pk, 8)
+        p_hi = self.buf("img.patches_hi", (Ms, pk_pad), zero=True)
+        p_lo = self.buf("img.patches_lo", (Ms, pk_pad), zero=True)
+        ops.patchify(st.images, patches, B, C, cfg.image_size, cfg.image_size, s.patch_size, p_hi, p_lo, pk_pad)
         x = self.buf("img.x.0", (Ms, W))
         ops.sgemm(patches, self.p("img.patch_w"), x, Ms, W, pk, pk, 1, pk, 1, ldc=W, bias=self.p("img.patch_b"),
                   table=self.p("img.pos"), table_rows=Np)
@@ -406,8 +426,15 @@ class LAP:
         # patch embedding: pos (sum over images), bias, kernel (fp32)
         ops.colsum(dx, Np * W, self.g("img.pos"), Ni, Np * W)
         ops.colsum(dx, W, self.g("img.patch_b"), Ms, W)
-        patches = self._bufs["img.patches"]
-        ops.sgemm(dx, patches, self.g("img.patch_w"), W, pk, Ms, 1, W, 1, pk, ldc=pk)
+        # fp32 conv kernel gradient on the tensor cores: dW = dx^T [patch_hi + patch_lo] (bf16 hi/lo split of the fp32
+        # patch matrix keeps ~16 mantissa bits; siglip.py:216-223 evaluates this conv in fp32)
+        pk_pad = _round_up(pk, 8)
+        dwp = self.buf("img.dpatch_w", (W, pk_pad), F32)
+        ops.gemm(dx, self._bufs["img.patches_hi"], dwp, M=W, N=pk_pad, K=Ms, a_major=1, b_major=1, lda=W, ldb=pk_pad,
+                 ldc=pk_pad)
+        ops.gemm(dx, self._bufs["img.patches_lo"], dwp, M=W, N=pk_pad, K=Ms, a_major=1, b_major=1, lda=W, ldb=pk_pad,
+                 ldc=pk_pad, accumulate=True)
+        self.g("img.patch_w").copy_(dwp[:, :pk])
 
     # ------------------------------------------------------------------------------------------
     # suffix (flow-matching) embedding — fp32 (OP/models/pi0.py:139-186, lap.py:185-207)
@@ -676,6 +703,8 @@ class LAP:
             sv = lambda n: bufs[f"g.{n}.{l}"]
             # ===== MLP, prefix expert =====
             GU, h2, X1 = sv("GU"), sv("h2"), sv("X1")
+            # (fusing geglu_bwd into this GEMM's epilogue — EPI_GEGLU_BWD — measured slower: the epilogue becomes the
+            #  bottleneck; the streaming kernel runs at the HBM roofline instead)
             self._dgrad(dX, self.w("g.down_w", l), dact, Mg, D, F)
             ops.geglu_bwd(dact, GU, Mg, F)  # dact <- act, GU <- [dg|du]
             self._wgrad(dX, dact, self.g("g.down_w", l), Mg, D, F)

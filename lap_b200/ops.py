@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmParams, check
 
-EPI_NONE, EPI_BIAS_GELU, EPI_RESID, EPI_GATED_RESID, EPI_GEGLU, EPI_QSCALE = range(6)
+EPI_NONE, EPI_BIAS_GELU, EPI_RESID, EPI_GATED_RESID, EPI_GEGLU, EPI_QSCALE, EPI_GEGLU_BWD, EPI_GELU_BWD = range(8)
 
 # launch counter: every C-ABI kernel entry increments this (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -181,10 +181,10 @@ def split_hi_lo(src, dst, rows, D):
     call("split_hi_lo", src, dst, rows, D)
 
 
-def patchify(imgs, out, B, C, H, W, ps):
+def patchify(imgs, out, B, C, H, W, ps, out_hi=None, out_lo=None, pk_pad=0):
     is_u8 = imgs[0].dtype == torch.uint8
     p = list(imgs) + [None] * (3 - len(imgs))
-    call("patchify", p[0], p[1], p[2], is_u8, out, B, C, H, W, ps)
+    call("patchify", p[0], p[1], p[2], is_u8, out, out_hi, out_lo, pk_pad, B, C, H, W, ps)
 
 
 def sgemm(A, B, C, M, N, K, sam, sak, sbn, sbk, ldc=None, bias=None, table=None, table_rows=0, accumulate=False):
@@ -309,6 +309,10 @@ def sumsq_partials(x, n, partials):
 
 
 def adamw_ema(p, g, m, v, ema, w16, n, gpartials, n_partials, stats, kernel_begin, kernel_end, *, lr, b1, b2, eps, wd,
-              bc1, bc2, clip, ema_decay, ema_on):
+              bc1, bc2, clip, ema_decay, ema_on, hyper=None):
     call("adamw_ema", p, g, m, v, ema, w16, n, gpartials, n_partials, stats, kernel_begin, kernel_end, float(lr),
-         float(b1), float(b2), float(eps), float(wd), float(bc1), float(bc2), float(clip), float(ema_decay), ema_on)
+         float(b1), float(b2), float(eps), float(wd), float(bc1), float(bc2), float(clip), float(ema_decay), ema_on, hyper)
+
+
+def sqrt_scalar(buf, src, dst):
+    call("sqrt_scalar", buf, src, dst)

@@ -59,12 +59,16 @@ def init_train_state(config: TrainConfig, seed: int | None = None, *, model: LAP
 class TrainingStepRunner:
     """Callable with the reference's signature: (rng, state, (observation, actions), step) -> (state, info)."""
 
-    def __init__(self, config: TrainConfig, *, bucket_bytes: int = 512 << 20):
+    def __init__(self, config: TrainConfig, *, bucket_bytes: int = 512 << 20, use_cuda_graph: bool = True):
         self.config = config
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
+        self.use_cuda_graph = use_cuda_graph
         self._partials = None
         self._stats = None
+        self._hyper_host = None
+        self._graphs: dict = {}  # (B, R_cap) -> (fwd/bwd graph, optimizer graph, loss buffer)
+        self._warm: dict = {}  # eager steps run per (B, R_cap): workspaces exist before capture
 
     # -- global loss normalisers (lap.py:580-589 are means over the GLOBAL batch) ------------------------------
     def _global_counts(self, observation, B: int, device) -> tuple[float, float]:
@@ -107,50 +111,98 @@ class TrainingStepRunner:
                 time = u.pow(1.0 / 1.5) * 0.999 + 0.001  # Beta(1.5, 1) by inverse CDF
         counts = self._global_counts(observation, B, model.device)
         st = model._stage(observation, actions, noise, time, with_loss=True, global_counts=counts)
-        loss = model.forward_backward(st)
-        self._allreduce_grads(model.G)
-        info = self.apply_gradients(state, step)
-        info["loss"] = loss[0]
+        info = self.step_staged(state, st, step)
         if self.world > 1:
             # each rank holds its shard's share of the global mean; the sum over ranks is the global loss
-            lt = loss.clone()
+            lt = info["loss"].clone()
             dist.all_reduce(lt, op=dist.ReduceOp.SUM)
-            info["loss"] = lt[0]
+            info["loss"] = lt
         if with_metrics:
             info.update(model._metrics(st))
         return state, info
 
-    def step_staged(self, state: TrainState, st) -> dict:
-        """One optimisation step on inputs already staged in HBM (model._stage) — no host<->device traffic."""
+    def step_staged(self, state: TrainState, st, step: int | None = None) -> dict:
+        """One optimisation step on inputs already staged in HBM (model._stage) — no host<->device traffic except
+        the 20-byte per-step hyper-parameter vector.  After two eager steps (which allocate every workspace) the
+        forward+backward and the optimizer are captured as CUDA graphs and replayed: ~1700 kernel launches become
+        two graph launches (plus the NCCL all-reduce between them when world > 1)."""
         model = state.model
-        loss = model.forward_backward(st)
-        self._allreduce_grads(model.G)
-        info = self.apply_gradients(state, state.step)
-        info["loss"] = loss[0]
-        return info
+        step = state.step if step is None else int(step)
+        self._set_hyper(state, step)
+        key = (st.B, st.R)
+        g = self._graphs.get(key)
+        if g is None and self.use_cuda_graph and self._warm.get(key, 0) >= 2:
+            g = self._capture(state, st)
+            self._graphs[key] = g
+        if g is None:
+            loss = model.forward_backward(st)
+            self._allreduce_grads(model.G)
+            self._apply_gradients_device(state)
+            self._warm[key] = self._warm.get(key, 0) + 1
+        else:
+            g[0].replay()
+            self._allreduce_grads(model.G)
+            g[1].replay()
+            loss = model._bufs["loss.total"]
+        state.step = step + 1
+        stats = self._stats
+        return {"loss": loss[0], "grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
-    def apply_gradients(self, state: TrainState, step: int) -> dict:
-        """clip_by_global_norm -> adamw -> apply -> EMA (scripts/train.py:363-396) + norms (:370-371,402-415)."""
+    def _capture(self, state: TrainState, st):
+        model = state.model
+        torch.cuda.synchronize()
+        pool = torch.cuda.graph_pool_handle()
+        g1 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g1, pool=pool):
+            model.forward_backward(st)
+        g2 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g2, pool=pool):
+            self._apply_gradients_device(state)
+        torch.cuda.synchronize()
+        # capture does not execute: run the captured step once so this call still performs its optimisation step
+        return (g1, g2)
+
+    def _set_hyper(self, state: TrainState, step: int) -> None:
+        """Per-step scalars (lr, Adam bias corrections, EMA decay) go to the device as one tiny pinned copy."""
         cfg, o = self.config, self.config.optimizer
         model = state.model
-        n = model.layout.total
         if self._partials is None:
             self._np = ops.opt_num_partials()
             self._partials = torch.zeros(self._np, dtype=F32, device=model.device)
             self._stats = torch.zeros(4, dtype=F32, device=model.device)
-        self._stats.zero_()
-        ops.sumsq_partials(model.G, n, self._partials)
-        lr = cfg.lr_schedule.lr(step)
+            self._hyper_host = torch.zeros(8, dtype=F32).pin_memory()
+            self._hyper = torch.zeros(8, dtype=F32, device=model.device)
         count = step + 1
         decay, ema_on = cfg.get_ema_decay_for_step(step)
+        h = self._hyper_host
+        h[0] = cfg.lr_schedule.lr(step)
+        h[1] = 1.0 - o.b1 ** count
+        h[2] = 1.0 - o.b2 ** count
+        h[3] = float(decay)
+        h[4] = 1.0 if (ema_on and state.ema_params is not None) else 0.0
+        self._hyper.copy_(h, non_blocking=True)
+
+    def _apply_gradients_device(self, state: TrainState) -> None:
+        """clip_by_global_norm -> adamw -> apply -> EMA (scripts/train.py:363-396) + norms (:370-371,402-415); all
+        step-dependent scalars are read from device memory (self._hyper)."""
+        o = self.config.optimizer
+        model = state.model
+        n = model.layout.total
+        self._stats[2:].zero_()
+        ops.sumsq_partials(model.G, n, self._partials)
         ops.adamw_ema(model.P, model.G, state.mu, state.nu, state.ema_params, model.W16, n, self._partials, self._np,
-                      self._stats, 0, model.layout.kernel_end, lr=lr, b1=o.b1, b2=o.b2, eps=o.eps, wd=o.weight_decay,
-                      bc1=1.0 - o.b1 ** count, bc2=1.0 - o.b2 ** count, clip=o.clip_gradient_norm,
-                      ema_decay=float(decay), ema_on=bool(ema_on) and state.ema_params is not None)
+                      self._stats, 0, model.layout.kernel_end, lr=0.0, b1=o.b1, b2=o.b2, eps=o.eps, wd=o.weight_decay,
+                      bc1=1.0, bc2=1.0, clip=o.clip_gradient_norm, ema_decay=0.0, ema_on=False, hyper=self._hyper)
+        ops.sqrt_scalar(self._stats, 2, 3)
         model.refresh_embed_split()
+
+    def apply_gradients(self, state: TrainState, step: int) -> dict:
+        """Eager optimizer step for callers that produced model.G themselves."""
+        self._set_hyper(state, step)
+        self._apply_gradients_device(state)
         state.step = step + 1
-        stats = self._stats.clone()
-        return {"grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[2].sqrt()}
+        stats = self._stats
+        return {"grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
 
 def train_step(config: TrainConfig, rng, state: TrainState, batch, step: int | None = None):

@@ -16,7 +16,7 @@ torch.cuda.synchronize()
 print(f"init {time.time()-t0:.1f}s  mem {torch.cuda.memory_allocated()/2**30:.1f} GiB", flush=True)
 runner = TrainingStepRunner(tc)
 model = state.model
-for i in range(steps):
+for i in range(steps + 3):
     b = synthetic_batch(tc.model, B, step=i)
     obs, actions, extra = batch_from_dict(b)
     torch.cuda.synchronize(); t0 = time.time()
@@ -36,6 +36,12 @@ print(f"forward+loss: {e[0].elapsed_time(e[1]):.1f} ms", flush=True)
 e[2].record(); model.forward_backward(st); e[3].record(); torch.cuda.synchronize()
 print(f"forward+backward: {e[2].elapsed_time(e[3]):.1f} ms", flush=True)
 e[4].record(); runner.apply_gradients(state, 5); e[5].record(); torch.cuda.synchronize()
+for _ in range(3): runner.step_staged(state, st)
+torch.cuda.synchronize()
+e[0].record()
+for _ in range(5): runner.step_staged(state, st)
+e[1].record(); torch.cuda.synchronize()
+print(f"graphed step_staged: {e[0].elapsed_time(e[1])/5:.1f} ms/step", flush=True)
 print(f"optimizer: {e[4].elapsed_time(e[5]):.1f} ms", flush=True)
 # host-side time of a step (python overhead)
 t0 = time.time(); model.forward_backward(st); t1 = time.time(); torch.cuda.synchronize(); t2 = time.time()
