@@ -173,6 +173,17 @@ int lapb200_mse_fwd_bwd(const float* v, const float* u, float* loss, float* dv, 
 int lapb200_weighted_sum(const float* x, const float* w, float* out, int64_t n, float alpha, int64_t accumulate,
                          lapb_stream_t s);
 
+/* Inference (lap.py:634-667): weight-streaming GEMM for M <= 16 rows (the 10 action tokens of one denoise step) with the
+ * same fused epilogues as the tile GEMM (NONE/bias, RESID, GATED_RESID, GEGLU), and attention of a few query tokens
+ * against the KV cache (gemma.py:227-272). */
+int lapb200_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, int64_t M, int64_t N, int64_t K,
+                        void* Y, int64_t ldy, int64_t y_fp32, int64_t epi, const float* bias, const void* resid,
+                        int64_t ldr, const void* gate, int64_t ldg, int64_t gate_rows, void* Y2, int64_t ldy2,
+                        lapb_stream_t s);
+int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* O, int64_t B,
+                        int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
+                        lapb_stream_t s);
+
 /* buf[dst] = sqrt(buf[src]) on the device (param_norm = sqrt(sum p^2), scripts/train.py:411) */
 int lapb200_sqrt_scalar(float* buf, int64_t src, int64_t dst, lapb_stream_t s);
 

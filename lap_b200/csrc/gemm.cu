@@ -706,6 +706,13 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
   }
   // 2-CTA pairs (256-row tiles) whenever there are at least two 128-row blocks to pair up
   int CG = (p->cta_group == 1 || p->cta_group == 2) ? p->cta_group : (p->M > 128 ? 2 : 1);
+  if (p->cta_group == 0 && p->block_n == 0 && !dual && CG == 2) {
+    // small problems (inference prefix pass, expert rows): if 256x256 pair tiles would leave most SMs idle, fall back
+    // to 128x128 single-CTA tiles to put more CTAs (and more TMA streams) to work
+    long t2 = (long)cdiv(p->M, 256) * cdiv(p->N, BN) * bi * bo * 2;
+    long t1 = (long)cdiv(p->M, 128) * cdiv(p->N, 128) * bi * bo;
+    if (t2 < num_sms() / 2 && t1 > t2) { CG = 1; BN = 128; }
+  }
   const int TILE_M = BM * CG;
 
   GemmKArgs ka;

@@ -90,6 +90,9 @@ class LAP:
         self._io: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}  # persistent (pinned host, device) input buffers
         self._io_event = None
         self.R_cap: int | None = None
+        self.use_cuda_graph = True
+        self._infer_graphs: dict = {}
+        self._infer_warm: dict = {}
         hd = cfg.gemma.head_dim
         ts = (10_000.0 ** ((2.0 / hd) * torch.arange(hd // 2, dtype=torch.float32))).to(self.device)
         self.timescale = ts
@@ -307,6 +310,17 @@ class LAP:
         ops.gemm(dY, X, dW, M=N, N=K, K=M, a_major=1, b_major=1, lda=lddy if lddy is not None else N,
                  ldb=ldx if ldx is not None else K, ldc=K, accumulate=accumulate)
 
+    @staticmethod
+    def _lin(A, W, C, M, N, K, **kw):
+        """C = epi(A @ W^T).  M <= 16 rows (one denoise step at batch 1) take the weight-streaming kernel."""
+        if M <= 16 and K % 32 == 0 and kw.get("epi", ops.EPI_NONE) in (ops.EPI_NONE, ops.EPI_RESID,
+                                                                       ops.EPI_GATED_RESID, ops.EPI_GEGLU):
+            ops.skinny_gemm(A, W, C, M=M, N=N, K=K, epi=kw.get("epi", ops.EPI_NONE), bias=kw.get("bias"),
+                            resid=kw.get("resid"), gate=kw.get("gate"), ldg=kw.get("ldg", 0),
+                            gate_rows=kw.get("gate_rows", 1), Y2=kw.get("C2"), ldy2=kw.get("ldc2", 0))
+        else:
+            ops.gemm(A, W, C, M=M, N=N, K=K, **kw)
+
     # ------------------------------------------------------------------------------------------
     # SigLIP tower (OP/models/siglip.py), all cameras in one pass, rows ordered (b, cam, patch)
     # ------------------------------------------------------------------------------------------
@@ -462,7 +476,7 @@ class LAP:
         # all 2L+1 adaRMS modulation Dense layers in one GEMM: mod[b, i*3D1 : (i+1)*3D1]
         nm = P.n_mod(cfg)
         mod = self.buf("suf.mod", (B, nm * 3 * D1))
-        ops.gemm(cond16, self.w("e.mod_w"), mod, M=B, N=nm * 3 * D1, K=D1, bias=self.p("e.mod_b").view(-1))
+        self._lin(cond16, self.w("e.mod_w"), mod, B, nm * 3 * D1, D1, bias=self.p("e.mod_b").view(-1))
 
     # ------------------------------------------------------------------------------------------
     # Gemma multi-expert transformer (src/lap/models/backbones/gemma.py:455-531)
@@ -508,18 +522,25 @@ class LAP:
                 rstdE = self.buf(sv("rstdE", l), (Me,), F32)
                 ops.rmsnorm_fwd(XE, hE, rstdE, Me, D1, mod=mod.view(-1)[(2 * l) * 3 * D1:], ldmod=nm3, rows_per_sample=A)
                 qkv1 = self.buf(f"{tag}.qkv1", (Me, QKV))
-                ops.gemm(hE, self.w("e.qkv_w", l), qkv1, M=Me, N=QKV, K=D1)
+                self._lin(hE, self.w("e.qkv_w", l), qkv1, Me, QKV, D1)
             Q = self.buf(sv("Q", l), (B, Tq, NH, hd))
             ops.rope_fwd(qkv0, qkv1, positions, self.timescale, Q, Kc, Vc, B, Pn, A, Tpad, NH, hd, t_begin, qscale)
             R = Tq * NH
-            S = self.buf(f"{tag}.S", (B, R, Tpad), F32)
-            ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
-                     c_bs=(R * Tpad, 0))
-            Pm = self.buf(sv("P", l), (B, R, Tpad))
-            ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, T, Tpad, W32)
-            Oc = self.buf(f"{tag}.Oc", (B, R, hd))
-            ops.gemm(Pm, Vc, Oc, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
-                     a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
+            if X is None and kv_cache is not None and Me <= 16:
+                # suffix-only denoise step: a handful of query tokens against the cache
+                Oc = self.buf(f"{tag}.Oc", (B, R, hd))
+                ops.decode_attn(Q, Kc, Vc, bits, Oc, B, Tq, NH, hd, T, Tpad, W32)
+                S = None
+            else:
+                S = self.buf(f"{tag}.S", (B, R, Tpad), F32)
+            if S is not None:
+                ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
+                         c_bs=(R * Tpad, 0))
+                Pm = self.buf(sv("P", l), (B, R, Tpad))
+                ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, T, Tpad, W32)
+                Oc = self.buf(f"{tag}.Oc", (B, R, hd))
+                ops.gemm(Pm, Vc, Oc, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                         a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
             if X is not None:
                 O0 = self.buf(sv("O0", l), (Mg, NH * hd))
                 O0.view(B, Pn * NH * hd).copy_(Oc.view(B, R * hd)[:, : Pn * NH * hd])
@@ -544,19 +565,20 @@ class LAP:
                 gate_f = mod.view(-1)[(2 * l + 1) * 3 * D1 + 2 * D1:]
                 XE1 = self.buf(sv("XE1", l), (Me, D1))
                 yEa = self.buf(sv("yEa", l), (Me, D1))
-                ops.gemm(O1, self.w("e.o_w", l), XE1, M=Me, N=D1, K=NH * hd, epi=ops.EPI_GATED_RESID, resid=XE,
-                         gate=gate_a, ldg=nm3, gate_rows=A, C2=yEa, ldc2=D1)
+                self._lin(O1, self.w("e.o_w", l), XE1, Me, D1, NH * hd, epi=ops.EPI_GATED_RESID, resid=XE,
+                          gate=gate_a, ldg=nm3, gate_rows=A, C2=yEa if save else None, ldc2=D1)
                 hE2 = self.buf(sv("hE2", l), (Me, D1))
                 rstdE2 = self.buf(sv("rstdE2", l), (Me,), F32)
                 ops.rmsnorm_fwd(XE1, hE2, rstdE2, Me, D1, mod=mod.view(-1)[(2 * l + 1) * 3 * D1:], ldmod=nm3,
                                 rows_per_sample=A)
                 actE = self.buf(sv("actE", l), (Me, F1))
                 GUE = self.buf(sv("GUE", l), (Me, 2 * F1))
-                ops.gemm(hE2, self.w("e.gu_w", l), actE, M=Me, N=F1, K=D1, epi=ops.EPI_GEGLU, C2=GUE, ldc2=2 * F1)
+                self._lin(hE2, self.w("e.gu_w", l), actE, Me, F1, D1, epi=ops.EPI_GEGLU, C2=GUE if save else None,
+                          ldc2=2 * F1)
                 XE2 = self.buf(sv("XE", l + 1), (Me, D1))
                 yEf = self.buf(sv("yEf", l), (Me, D1))
-                ops.gemm(actE, self.w("e.down_w", l), XE2, M=Me, N=D1, K=F1, epi=ops.EPI_GATED_RESID, resid=XE1,
-                         gate=gate_f, ldg=nm3, gate_rows=A, C2=yEf, ldc2=D1)
+                self._lin(actE, self.w("e.down_w", l), XE2, Me, D1, F1, epi=ops.EPI_GATED_RESID, resid=XE1,
+                          gate=gate_f, ldg=nm3, gate_rows=A, C2=yEf if save else None, ldc2=D1)
                 XE = XE2
         return X, XE
 
@@ -642,6 +664,22 @@ class LAP:
     # ------------------------------------------------------------------------------------------
     def forward_backward(self, st: Staged, *, zero_grads: bool = True, softmax_mode: int = 0):
         """Forward + hand-written backward; fills self.G (flat fp32 grads).  Returns the loss (device scalar [1])."""
+        loss = self.forward_backward_llm(st, zero_grads=zero_grads, softmax_mode=softmax_mode)
+        self.backward_vision(st)
+        return loss
+
+    def llm_grad_range(self) -> tuple[int, int]:
+        """Flat-buffer range whose gradients are final once forward_backward_llm returns (Gemma + expert + action
+        projections + embedding): the data-parallel all-reduce of this range overlaps backward_vision."""
+        return self.layout.offsets["g.qkv_w"], self.layout.small_begin
+
+    def backward_vision(self, st: Staged) -> None:
+        """SigLIP tower backward (the last ~12 % of the step); needs forward_backward_llm to have run."""
+        self._siglip_bwd(st, self._bufs["bwd.dX"], self.cfg.prefix_len)
+
+    def forward_backward_llm(self, st: Staged, *, zero_grads: bool = True, softmax_mode: int = 0):
+        """Forward of everything + backward through the loss heads, the transformer stack, the text embedding and
+        the suffix embedding.  Leaves d(prefix tokens) in `bwd.dX` for backward_vision."""
         assert self.G is not None, "allocate model.G (flat grads) first"
         cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
         lay = self.layout
@@ -774,8 +812,6 @@ class LAP:
         x_t = bufs["suf.x_t"]
         ops.sgemm(dXE, x_t, self.g("action_in_w"), D1, ad, Me, 1, D1, 1, ad, ldc=ad)
         ops.colsum(dXE, D1, self.g("action_in_b"), Me, D1)
-        # ---- SigLIP ----
-        self._siglip_bwd(st, dX, Pn)
         return loss
 
     # ------------------------------------------------------------------------------------------
@@ -783,20 +819,43 @@ class LAP:
     # ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def sample_actions(self, rng, observation: Observation, *, num_steps: int = 10, noise=None) -> torch.Tensor:
-        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        """lap.py:605-675.  After one eager call per (batch, num_steps) the whole prefix pass + Euler loop (~2000 kernel
+        launches) is captured as ONE CUDA graph and replayed; inputs/outputs go through persistent device buffers."""
+        cfg = self.cfg
         st = self._stage(observation, with_loss=False)
-        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
-        C, Np = len(cfg.image_keys), cfg.num_patches
-        D, D1, ad = g.width, e.width, cfg.action_dim
-        T = Pn + A
-        Tpad = _round_up(T, 32)
-        W32 = Tpad // 32
+        B, A, ad = st.B, cfg.action_horizon, cfg.action_dim
         if noise is None:
             gen = torch.Generator().manual_seed(int(rng) if rng is not None else 0)
             noise = torch.randn((B, A, ad), generator=gen)
         noise_t = noise if isinstance(noise, torch.Tensor) else torch.from_numpy(np.asarray(noise))
         x = self.buf("inf.x", (B, A * ad), F32)
         x.copy_(noise_t.to(torch.float32).reshape(B, A * ad), non_blocking=True)
+        key = (B, int(num_steps))
+        g = self._infer_graphs.get(key)
+        if g is None and self.use_cuda_graph and self._infer_warm.get(key, 0) >= 1:
+            torch.cuda.synchronize()
+            x_keep = x.clone()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._sample_actions_impl(st, num_steps)
+            self._infer_graphs[key] = g
+            x.copy_(x_keep)
+        if g is None:
+            self._sample_actions_impl(st, num_steps)
+            self._infer_warm[key] = self._infer_warm.get(key, 0) + 1
+        else:
+            g.replay()
+        return x.view(B, A, ad).clone()
+
+    def _sample_actions_impl(self, st: Staged, num_steps: int) -> None:
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
+        C, Np = len(cfg.image_keys), cfg.num_patches
+        D, D1, ad = g.width, e.width, cfg.action_dim
+        T = Pn + A
+        Tpad = _round_up(T, 32)
+        W32 = Tpad // 32
+        x = self.buf("inf.x", (B, A * ad), F32)
         # ---- prefix pass fills the cache ----
         X0 = self.buf("inf.X0", (B * Pn, D))
         self._siglip_fwd(st, X0, Pn)
@@ -834,7 +893,6 @@ class LAP:
             t += dt
             n_iter += 1
         assert n_iter == num_steps
-        return x.view(B, A, ad).clone()
 
     def _gemma_prefix_only(self, B, X0, bits, positions, cache):
         """Prefix-only pass (lap.py:627): expert 0 alone, K/V (post-RoPE) written into the cache."""

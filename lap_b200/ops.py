@@ -17,6 +17,9 @@ EPI_NONE, EPI_BIAS_GELU, EPI_RESID, EPI_GATED_RESID, EPI_GEGLU, EPI_QSCALE, EPI_
 
 # launch counter: every C-ABI kernel entry increments this (bench.py reports it as gpu_launches)
 launch_count = 0
+# default CTA budget of the persistent GEMM (0 = every SM).  The trainer lowers it while an NCCL all-reduce must be
+# co-resident: the GEMM CTAs otherwise own every SM's registers/shared memory and the collective cannot overlap.
+gemm_max_ctas = 0
 
 
 def lib():
@@ -112,7 +115,7 @@ def gemm(
     p.q_cols = q_cols
     p.q_div = q_div
     p.block_n = block_n
-    p.max_ctas = max_ctas
+    p.max_ctas = max_ctas if max_ctas else gemm_max_ctas
     p.cta_group = cta_group
     p.k_splits = k_splits
     prof = _gemm_prof
@@ -316,3 +319,19 @@ def adamw_ema(p, g, m, v, ema, w16, n, gpartials, n_partials, stats, kernel_begi
 
 def sqrt_scalar(buf, src, dst):
     call("sqrt_scalar", buf, src, dst)
+
+
+def num_sms() -> int:
+    return torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+
+
+def skinny_gemm(X, W, Y, *, M, N, K, ldx=None, ldw=None, ldy=None, epi=EPI_NONE, bias=None, resid=None, ldr=None,
+                gate=None, ldg=0, gate_rows=1, Y2=None, ldy2=0):
+    """Y[M<=16, N] = epi(X[M,K] @ W[N,K]^T): weight-streaming kernel of the denoise loop."""
+    call("skinny_gemm", X, ldx if ldx is not None else K, W, ldw if ldw is not None else K, M, N, K, Y,
+         ldy if ldy is not None else N, Y.dtype == torch.float32, epi, bias, resid,
+         ldr if ldr is not None else (ldy if ldy is not None else N), gate, ldg, gate_rows, Y2, ldy2)
+
+
+def decode_attn(Q, Kc, Vc, bits, O, B, Tq, NH, HD, S_len, Tpad, W32):
+    call("decode_attn", Q, Kc, Vc, bits, O, B, Tq, NH, HD, S_len, Tpad, W32)

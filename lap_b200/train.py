@@ -15,6 +15,7 @@ fp32 gradient buffer over NCCL (bucketed so the tail of backward overlaps it).  
 from __future__ import annotations
 
 import dataclasses
+import os
 
 import numpy as np
 import torch
@@ -64,6 +65,7 @@ class TrainingStepRunner:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
         self.use_cuda_graph = use_cuda_graph
+        self.comm_sms = int(os.environ.get("LAPB_COMM_SMS", "16"))  # SMs left to NCCL while it overlaps compute
         self._partials = None
         self._stats = None
         self._hyper_host = None
@@ -81,16 +83,22 @@ class TrainingStepRunner:
             n_active, n_action = (float(x) for x in t.tolist())
         return n_active, n_action
 
-    def _allreduce_grads(self, G: torch.Tensor) -> None:
-        """C1: the one data-path collective — sum of fp32 grads across ranks (NCCL over NVLink/NVSwitch)."""
-        if self.world == 1:
-            return
+    def _allreduce_begin(self, G: torch.Tensor) -> list:
+        """C1: the one data-path collective — sum of fp32 grads across ranks (NCCL over NVLink/NVSwitch), issued
+        asynchronously in buckets; the collective runs on NCCL's stream and overlaps whatever is enqueued next."""
+        if self.world == 1 or G.numel() == 0:
+            return []
         step = self.bucket_bytes // 4
-        works = []
-        for o in range(0, G.numel(), step):
-            works.append(dist.all_reduce(G[o : o + step], op=dist.ReduceOp.SUM, async_op=True))
+        return [dist.all_reduce(G[o : o + step], op=dist.ReduceOp.SUM, async_op=True)
+                for o in range(0, G.numel(), step)]
+
+    @staticmethod
+    def _allreduce_end(works: list) -> None:
         for w in works:
             w.wait()
+
+    def _allreduce_grads(self, G: torch.Tensor) -> None:
+        self._allreduce_end(self._allreduce_begin(G))
 
     def __call__(self, rng, state: TrainState, batch, step: int | None = None, *, with_metrics: bool = True):
         cfg = self.config
@@ -124,8 +132,9 @@ class TrainingStepRunner:
     def step_staged(self, state: TrainState, st, step: int | None = None) -> dict:
         """One optimisation step on inputs already staged in HBM (model._stage) — no host<->device traffic except
         the 20-byte per-step hyper-parameter vector.  After two eager steps (which allocate every workspace) the
-        forward+backward and the optimizer are captured as CUDA graphs and replayed: ~1700 kernel launches become
-        two graph launches (plus the NCCL all-reduce between them when world > 1)."""
+        three phases — forward+LLM backward, SigLIP backward, optimizer — are captured as CUDA graphs and replayed:
+        ~1700 kernel launches become three graph launches.  With world > 1 the all-reduce of the LLM gradients (88 %
+        of the bytes) is issued between the first two graphs and overlaps the SigLIP backward."""
         model = state.model
         step = state.step if step is None else int(step)
         self._set_hyper(state, step)
@@ -134,19 +143,35 @@ class TrainingStepRunner:
         if g is None and self.use_cuda_graph and self._warm.get(key, 0) >= 2:
             g = self._capture(state, st)
             self._graphs[key] = g
+        lo, hi = model.llm_grad_range()
         if g is None:
-            loss = model.forward_backward(st)
-            self._allreduce_grads(model.G)
+            loss = model.forward_backward_llm(st)
+            works = self._allreduce_begin(model.G[lo:hi])  # overlaps the SigLIP backward
+            self._backward_vision(model, st)
+            works += self._allreduce_begin(model.G[:lo]) + self._allreduce_begin(model.G[hi:])
+            self._allreduce_end(works)
             self._apply_gradients_device(state)
             self._warm[key] = self._warm.get(key, 0) + 1
         else:
             g[0].replay()
-            self._allreduce_grads(model.G)
+            works = self._allreduce_begin(model.G[lo:hi])
             g[1].replay()
+            works += self._allreduce_begin(model.G[:lo]) + self._allreduce_begin(model.G[hi:])
+            self._allreduce_end(works)
+            g[2].replay()
             loss = model._bufs["loss.total"]
         state.step = step + 1
         stats = self._stats
         return {"loss": loss[0], "grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
+
+    def _backward_vision(self, model, st) -> None:
+        """SigLIP backward; with world > 1 the persistent GEMMs leave `comm_sms` SMs to the concurrent all-reduce."""
+        if self.world > 1:
+            ops.gemm_max_ctas = max(2, (ops.num_sms() - self.comm_sms) // 2 * 2)
+        try:
+            model.backward_vision(st)
+        finally:
+            ops.gemm_max_ctas = 0
 
     def _capture(self, state: TrainState, st):
         model = state.model
@@ -154,13 +179,16 @@ class TrainingStepRunner:
         pool = torch.cuda.graph_pool_handle()
         g1 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1, pool=pool):
-            model.forward_backward(st)
+            model.forward_backward_llm(st)
         g2 = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g2, pool=pool):
+            self._backward_vision(model, st)
+        g3 = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g3, pool=pool):
             self._apply_gradients_device(state)
         torch.cuda.synchronize()
-        # capture does not execute: run the captured step once so this call still performs its optimisation step
-        return (g1, g2)
+        # capture does not execute: the caller replays the three graphs right away to perform this step
+        return (g1, g2, g3)
 
     def _set_hyper(self, state: TrainState, step: int) -> None:
         """Per-step scalars (lr, Adam bias corrections, EMA decay) go to the device as one tiny pinned copy."""

@@ -334,3 +334,60 @@ def test_sgemm_patchify_colsum_embed():
     ops.embed_bwd(ids, Xo, dE, 2, 7, 5, 12, 64, 8.0)
     ref_dE = torch.zeros_like(E).index_add_(0, ids.view(-1).long(), Xo.view(2, 12, 64)[:, 5:].reshape(-1, 64).float() * 8.0)
     assert rel_err(dE, ref_dE) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(10, 1024, 4096), (1, 3072, 1024), (16, 160, 64), (7, 2560, 1024)])
+def test_skinny_gemm_epilogues(M, N, K):
+    torch.manual_seed(M * N)
+    X = torch.randn(M, K, device=DEV).bfloat16()
+    W = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    ref = X.float() @ W.float().T
+    Y = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.skinny_gemm(X, W, Y, M=M, N=N, K=K)
+    assert rel_err(Y, ref.bfloat16()) < 1e-3
+    bias = torch.randn(N, device=DEV)
+    ops.skinny_gemm(X, W, Y, M=M, N=N, K=K, bias=bias)
+    assert rel_err(Y, (ref.bfloat16().float() + bias.bfloat16().float()).bfloat16()) < 1e-3
+    Yf = torch.zeros(M, N, device=DEV)
+    ops.skinny_gemm(X, W, Yf, M=M, N=N, K=K, bias=bias)
+    assert rel_err(Yf, ref + bias) < 1e-5
+    R = torch.randn(M, N, device=DEV).bfloat16()
+    ops.skinny_gemm(X, W, Y, M=M, N=N, K=K, epi=ops.EPI_RESID, resid=R)
+    assert rel_err(Y, (R.float() + ref.bfloat16().float()).bfloat16()) < 1e-3
+    G = torch.randn(2, N, device=DEV).bfloat16()
+    Y2 = torch.zeros_like(Y)
+    rows = (M + 1) // 2
+    ops.skinny_gemm(X, W, Y, M=M, N=N, K=K, epi=ops.EPI_GATED_RESID, resid=R, gate=G, ldg=N, gate_rows=rows, Y2=Y2, ldy2=N)
+    gate = G.float().repeat_interleave(rows, 0)[:M]
+    assert rel_err(Y, (R.float() + (ref.bfloat16().float() * gate).bfloat16().float()).bfloat16()) < 1e-3
+    assert rel_err(Y2, ref.bfloat16()) < 1e-3
+    if N % 16 == 0:
+        F = N // 2
+        act = torch.zeros(M, F, device=DEV, dtype=torch.bfloat16)
+        gu = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        ops.skinny_gemm(X, W, act, M=M, N=F, K=K, epi=ops.EPI_GEGLU, Y2=gu, ldy2=N)
+        g = ref[:, :F].bfloat16().float()
+        u = ref[:, F:].bfloat16().float()
+        assert rel_err(gu, torch.cat([g, u], 1)) < 1e-3
+        assert rel_err(act, torch.nn.functional.gelu(g, approximate="tanh").bfloat16().float() * u) < 3e-3
+
+
+def test_decode_attention_matches_reference():
+    B, Tq, NH, HD, T, Tpad = 2, 10, 8, 256, 702, 704
+    W32 = Tpad // 32
+    Q = (torch.randn(B, Tq, NH, HD, device=DEV) * 0.1).bfloat16()
+    Kc = torch.randn(B, Tpad, HD, device=DEV).bfloat16()
+    Vc = torch.randn(B, Tpad, HD, device=DEV).bfloat16()
+    dense = torch.rand(B, Tq, T, device=DEV) < 0.7
+    dense[1, 3] = False
+    bits = torch.zeros(B, Tq, W32, dtype=torch.int64, device=DEV)
+    for j in range(T):
+        bits[:, :, j // 32] |= dense[:, :, j].long() << (j % 32)
+    bits32 = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+    O = torch.zeros(B, Tq, NH, HD, device=DEV, dtype=torch.bfloat16)
+    ops.decode_attn(Q, Kc, Vc, bits32, O, B, Tq, NH, HD, T, Tpad, W32)
+    logits = torch.einsum("bqhd,bsd->bhqs", Q.float(), Kc[:, :T].float())
+    logits = torch.where(dense[:, None], logits, torch.tensor(-2.3819763e38, device=DEV))
+    p = torch.softmax(logits, -1).bfloat16().float()
+    ref = torch.einsum("bhqs,bsd->bqhd", p, Vc[:, :T].float())
+    assert rel_err(O, ref) < 4e-3

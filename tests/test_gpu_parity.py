@@ -171,3 +171,19 @@ def test_error_paths():
     bad.pop("action_in_proj/kernel")
     with pytest.raises(ValueError):
         model.load_params(bad)
+
+
+def test_batch1_sampling_uses_streaming_kernels_and_matches_oracle():
+    """B = 1 (the serving case): M = 10 rows per denoise step -> skinny GEMM + decode attention + CUDA graph replay."""
+    from lap_b200.observation import Observation
+    tc, ref, model, b = _setup("debug_small", 1)
+    cfg = tc.model
+    b2 = {k: v for k, v in b.items() if k != "tokenized_langact_mask"}
+    obs = Observation.from_dict(b2)
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    a_o = O.sample_actions(ref, cfg, obs_for_oracle(b, langact=False), t(b["noise"]), num_steps=10, bf16=True)
+    a1 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])  # eager
+    a2 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])  # captures + replays the CUDA graph
+    a3 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])  # replay
+    assert rel_err(a1, a_o) < TOL_ACT
+    assert torch.equal(a1, a2) and torch.equal(a2, a3)
