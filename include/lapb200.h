@@ -180,6 +180,9 @@ int lapb200_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, 
                         void* Y, int64_t ldy, int64_t y_fp32, int64_t epi, const float* bias, const void* resid,
                         int64_t ldr, const void* gate, int64_t ldg, int64_t gate_rows, void* Y2, int64_t ldy2,
                         lapb_stream_t s);
+/* fp32 layers at M <= 16 rows: Y = X W^T + bias (time MLP, action_in/out_proj; pi0.py:159-169, lap.py:665). */
+int lapb200_gemv_f32(const void* X, int64_t x_bf16, int64_t ldx, const float* W, const float* bias, void* Y,
+                     int64_t ldy, int64_t y_bf16, int64_t M, int64_t N, int64_t K, lapb_stream_t s);
 int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* O, int64_t B,
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);

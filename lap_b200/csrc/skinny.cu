@@ -167,32 +167,40 @@ decode_attn_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ Kc, cons
   const uint32_t* mrow = bits + ((long)b * Tq + tq) * W32;
   for (int d = threadIdx.x; d < HD; d += 256) qs[d] = __bfloat162float(q[d]);
   __syncthreads();
-  // ---- logits: one thread per key, the whole K row in flight as independent 16-byte loads ----
+  // ---- logits: one warp per key (coalesced 16-byte loads across the head dimension), 8 keys in flight per warp ----
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   float lmax = -3.4e38f;
-  for (int j = threadIdx.x; j < S_len; j += 256) {
-    const bf16* kr = K + (long)j * HD;
-    float acc = 0.f;
-    for (int d0 = 0; d0 < HD; d0 += 64) {
-      uint4 kv[8];
+  for (int j0 = warp * 8; j0 < S_len; j0 += 64) {
+    float acc[8];
 #pragma unroll
-      for (int u = 0; u < 8; ++u)
-        kv[u] = (d0 + u * 8 < HD) ? *reinterpret_cast<const uint4*>(kr + d0 + u * 8) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        int d = d0 + u * 8;
-        if (d < HD) {
+    for (int u = 0; u < 8; ++u) {
+      acc[u] = 0.f;
+      int j = j0 + u;
+      if (j < S_len) {
+        for (int d = lane * 8; d < HD; d += 256) {
+          uint4 kv = *reinterpret_cast<const uint4*>(K + (long)j * HD + d);
           float2 f;
-          f = unpack_bf16x2(kv[u].x); acc += f.x * qs[d] + f.y * qs[d + 1];
-          f = unpack_bf16x2(kv[u].y); acc += f.x * qs[d + 2] + f.y * qs[d + 3];
-          f = unpack_bf16x2(kv[u].z); acc += f.x * qs[d + 4] + f.y * qs[d + 5];
-          f = unpack_bf16x2(kv[u].w); acc += f.x * qs[d + 6] + f.y * qs[d + 7];
+          f = unpack_bf16x2(kv.x); acc[u] += f.x * qs[d] + f.y * qs[d + 1];
+          f = unpack_bf16x2(kv.y); acc[u] += f.x * qs[d + 2] + f.y * qs[d + 3];
+          f = unpack_bf16x2(kv.z); acc[u] += f.x * qs[d + 4] + f.y * qs[d + 5];
+          f = unpack_bf16x2(kv.w); acc[u] += f.x * qs[d + 6] + f.y * qs[d + 7];
         }
       }
     }
-    bool ok = (mrow[j >> 5] >> (j & 31)) & 1u;
-    float sc = ok ? acc : BIG_NEG;
-    ps[j] = sc;
-    lmax = fmaxf(lmax, sc);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane < 8) {
+      int j = j0 + lane;
+      if (j < S_len) {
+        float sc = acc[0];
+#pragma unroll
+        for (int u = 1; u < 8; ++u) sc = (lane == u) ? acc[u] : sc;
+        bool ok = (mrow[j >> 5] >> (j & 31)) & 1u;
+        sc = ok ? sc : BIG_NEG;
+        ps[j] = sc;
+        lmax = fmaxf(lmax, sc);
+      }
+    }
   }
   __syncthreads();
   float m = block_max(lmax, red);
@@ -243,6 +251,39 @@ decode_attn_kernel(const bf16* __restrict__ Q, const bf16* __restrict__ Kc, cons
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 GEMV-like kernel for the reference's fp32 layers at M <= 16 rows (time MLP, action_in/out_proj; pi0.py:159-169,
+// lap.py:665): Y[M, N] = X[M, K] W[N, K]^T + bias.  One warp per output column; fp32 weights streamed once.
+// ------------------------------------------------------------------------------------------------
+template <typename TX>
+__global__ void __launch_bounds__(256)
+gemv_f32_kernel(const TX* __restrict__ X, long ldx, const float* __restrict__ W, const float* __restrict__ bias,
+                void* __restrict__ Y, long ldy, int y_bf16, int M, int N, int K) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + warp;
+  if (n >= N) return;
+  float acc[16];
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+  const float* w = W + (long)n * K;
+  for (int k = lane; k < K; k += 32) {
+    float wv = w[k];
+#pragma unroll
+    for (int m = 0; m < 16; ++m)
+      if (m < M) acc[m] += wv * (float)X[(long)m * ldx + k];
+  }
+#pragma unroll
+  for (int m = 0; m < 16; ++m) acc[m] = warp_sum(acc[m]);
+  if (lane == 0) {
+    float b = bias ? bias[n] : 0.f;
+    for (int m = 0; m < M; ++m) {
+      float v = acc[m] + b;
+      if (y_bf16) reinterpret_cast<bf16*>(Y)[(long)m * ldy + n] = __float2bfloat16_rn(v);
+      else reinterpret_cast<float*>(Y)[(long)m * ldy + n] = v;
+    }
+  }
+}
+
 }  // namespace lapb
 
 using namespace lapb;
@@ -272,6 +313,19 @@ int lapb200_skinny_gemm(const void* X, int64_t ldx, const void* W, int64_t ldw, 
     skinny_gemm_kernel<1><<<(unsigned)(N / 8), 256, 0, STREAM(s)>>>(a);
   }
   LAPB_LAUNCH_OK("skinny_gemm");
+  return 0;
+}
+
+int lapb200_gemv_f32(const void* X, int64_t x_bf16, int64_t ldx, const float* W, const float* bias, void* Y,
+                     int64_t ldy, int64_t y_bf16, int64_t M, int64_t N, int64_t K, lapb_stream_t s) {
+  LAPB_REQUIRE(M >= 1 && M <= 16, "gemv_f32: M must be in [1,16]");
+  if (x_bf16)
+    gemv_f32_kernel<bf16><<<cdiv(N, 8), 256, 0, STREAM(s)>>>((const bf16*)X, ldx, W, bias, Y, ldy, (int)y_bf16,
+                                                             (int)M, (int)N, (int)K);
+  else
+    gemv_f32_kernel<float><<<cdiv(N, 8), 256, 0, STREAM(s)>>>((const float*)X, ldx, W, bias, Y, ldy, (int)y_bf16,
+                                                              (int)M, (int)N, (int)K);
+  LAPB_LAUNCH_OK("gemv_f32");
   return 0;
 }
 

@@ -465,13 +465,13 @@ class LAP:
             ops.suffix_inputs(st.actions, st.noise, time, x_t, u_t, te, B, A * ad, D1)
         else:
             ops.suffix_inputs(None, None, time, None, None, te, B, A * ad, D1)
-        ops.sgemm(x_t, self.p("action_in_w"), XE, B * A, D1, ad, ad, 1, ad, 1, ldc=D1, bias=self.p("action_in_b"))
+        ops.linear_f32(x_t, self.p("action_in_w"), XE, B * A, D1, ad, bias=self.p("action_in_b"))
         z1, s1 = self.buf("suf.z1", (B, D1), F32), self.buf("suf.s1", (B, D1), F32)
         z2, cond = self.buf("suf.z2", (B, D1), F32), self.buf("suf.cond", (B, D1), F32)
         cond16 = self.buf("suf.cond16", (B, D1))
-        ops.sgemm(te, self.p("time_in_w"), z1, B, D1, D1, D1, 1, D1, 1, bias=self.p("time_in_b"))
+        ops.linear_f32(te, self.p("time_in_w"), z1, B, D1, D1, bias=self.p("time_in_b"))
         ops.swish_fwd(z1, s1, None, B * D1)
-        ops.sgemm(s1, self.p("time_out_w"), z2, B, D1, D1, D1, 1, D1, 1, bias=self.p("time_out_b"))
+        ops.linear_f32(s1, self.p("time_out_w"), z2, B, D1, D1, bias=self.p("time_out_b"))
         ops.swish_fwd(z2, cond, cond16, B * D1)
         # all 2L+1 adaRMS modulation Dense layers in one GEMM: mod[b, i*3D1 : (i+1)*3D1]
         nm = P.n_mod(cfg)
@@ -621,7 +621,7 @@ class LAP:
         ops.rmsnorm_fwd(XE, sufout, rstdEF, Me, D1, mod=mod.view(-1)[(P.n_mod(cfg) - 1) * 3 * D1:], ldmod=nm3,
                         rows_per_sample=A)
         v = self.buf("loss.v", (Me, ad), F32)
-        ops.sgemm(sufout, self.p("action_out_w"), v, Me, ad, D1, D1, 1, D1, 1, ldc=ad, bias=self.p("action_out_b"))
+        ops.linear_f32(sufout, self.p("action_out_w"), v, Me, ad, D1, bias=self.p("action_out_b"))
         aloss = self.buf("loss.aloss", (B,), F32)
         dv = self.buf("loss.dv", (Me, ad), F32) if compute_grad_seed else None
         ops.mse_fwd_bwd(v, self._bufs["suf.u_t"], aloss, dv, B, A * ad, cfg.action_loss_weight / st.n_action)
@@ -887,8 +887,7 @@ class LAP:
             mod = self._bufs["suf.mod"]
             ops.rmsnorm_fwd(XE, sufout, rstd, B * A, D1, mod=mod.view(-1)[(nm - 1) * 3 * D1:], ldmod=nm3,
                             rows_per_sample=A)
-            ops.sgemm(sufout, self.p("action_out_w"), v, B * A, ad, D1, D1, 1, D1, 1, ldc=ad,
-                      bias=self.p("action_out_b"))
+            ops.linear_f32(sufout, self.p("action_out_w"), v, B * A, ad, D1, bias=self.p("action_out_b"))
             ops.axpy(x, v, dt, B * A * ad)
             t += dt
             n_iter += 1

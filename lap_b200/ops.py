@@ -126,7 +126,8 @@ def gemm(
     check(lib().lapb200_gemm_bf16(ctypes.byref(p), _stream()), "gemm_bf16")
     if prof is not None:
         e1.record()
-        prof.append((e0, e1, 2.0 * M * N * K * batch_i * batch_o * (2 if epi == EPI_GEGLU else 1)))
+        prof.append((e0, e1, 2.0 * M * N * K * batch_i * batch_o * (2 if epi == EPI_GEGLU else 1),
+                     (M, N, K, batch_i * batch_o, a_major, b_major, epi)))
     _count()
     return C
 
@@ -140,14 +141,23 @@ def gemm_profile_begin() -> None:
     _gemm_prof = []
 
 
-def gemm_profile_end() -> tuple[float, float, int]:
-    """Returns (algorithmic FLOPs, summed kernel ms, launches) since gemm_profile_begin(); syncs the device."""
+def gemm_profile_end() -> tuple[float, float, int, dict]:
+    """Returns (algorithmic FLOPs, summed kernel ms, launches, per-shape {key: [flops, ms, launches]}) since
+    gemm_profile_begin(); syncs the device.  key = (M, N, K, batches, a_major, b_major, epilogue)."""
     global _gemm_prof
     prof, _gemm_prof = _gemm_prof or [], None
     torch.cuda.synchronize()
-    flops = sum(f for _, _, f in prof)
-    ms = sum(a.elapsed_time(b) for a, b, _ in prof)
-    return flops, ms, len(prof)
+    by_shape: dict = {}
+    flops = ms = 0.0
+    for a, b, f, key in prof:
+        dt = a.elapsed_time(b)
+        flops += f
+        ms += dt
+        ent = by_shape.setdefault(key, [0.0, 0.0, 0])
+        ent[0] += f
+        ent[1] += dt
+        ent[2] += 1
+    return flops, ms, len(prof), by_shape
 
 
 # ---------------------------------------------------------------------------------------------
@@ -335,3 +345,12 @@ def skinny_gemm(X, W, Y, *, M, N, K, ldx=None, ldw=None, ldy=None, epi=EPI_NONE,
 
 def decode_attn(Q, Kc, Vc, bits, O, B, Tq, NH, HD, S_len, Tpad, W32):
     call("decode_attn", Q, Kc, Vc, bits, O, B, Tq, NH, HD, S_len, Tpad, W32)
+
+
+def linear_f32(X, W, Y, M, N, K, bias=None):
+    """Y[M,N] = X[M,K] @ W[N,K]^T + bias with fp32 weights/accumulation (X fp32 or bf16, Y fp32 or bf16).
+    M <= 16 rows take the warp-per-column GEMV kernel, larger M the tiled fp32 GEMM."""
+    if M <= 16:
+        call("gemv_f32", X, X.dtype == torch.bfloat16, K, W, bias, Y, N, Y.dtype == torch.bfloat16, M, N, K)
+    else:
+        sgemm(X, W, Y, M, N, K, K, 1, K, 1, ldc=N, bias=bias)
