@@ -173,6 +173,14 @@ int lapb200_mse_fwd_bwd(const float* v, const float* u, float* loss, float* dv, 
 int lapb200_weighted_sum(const float* x, const float* w, float* out, int64_t n, float alpha, int64_t accumulate,
                          lapb_stream_t s);
 
+/* K1: fused Gemma shared attention forward (gemma.py:234-272), head_dim 256, GQA 8:1 with the query heads stacked into the
+ * MMA M dimension: S = Q K^T and O = P V on tcgen05 with TMEM accumulators, K/V tiles double-buffered in shared
+ * memory by TMA, two-pass fp32 softmax with the packed-bit mask (finite -2.3819763e38 fill), P optionally written out
+ * (bf16, for the backward).  Rows [0, split_row) of each sample go to O0, the rest to O1 (prefix / action expert). */
+int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* P, void* O0,
+                         void* O1, int64_t B, int64_t R, int64_t G, int64_t Tq, int64_t S_len, int64_t Tpad,
+                         int64_t W32, int64_t split_row, int64_t head_dim, lapb_stream_t s);
+
 /* Inference (lap.py:634-667): weight-streaming GEMM for M <= 16 rows (the 10 action tokens of one denoise step) with the
  * same fused epilogues as the tile GEMM (NONE/bias, RESID, GATED_RESID, GEGLU), and attention of a few query tokens
  * against the KV cache (gemma.py:227-272). */

@@ -91,6 +91,7 @@ class LAP:
         self._io_event = None
         self.R_cap: int | None = None
         self.use_cuda_graph = True
+        self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
         self._infer_graphs: dict = {}
         self._infer_warm: dict = {}
         hd = cfg.gemma.head_dim
@@ -490,7 +491,7 @@ class LAP:
         Pn = cfg.prefix_len if (X is not None or kv_cache is not None) else 0
         A = cfg.action_horizon if XE is not None else 0
         T = Pn + A
-        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 32)
+        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 64)
         W32 = Tpad // 32
         D, D1, hd, NH = g.width, e.width, g.head_dim, g.num_heads
         QKV = (NH + 2) * hd
@@ -526,7 +527,18 @@ class LAP:
             Q = self.buf(sv("Q", l), (B, Tq, NH, hd))
             ops.rope_fwd(qkv0, qkv1, positions, self.timescale, Q, Kc, Vc, B, Pn, A, Tpad, NH, hd, t_begin, qscale)
             R = Tq * NH
-            if X is None and kv_cache is not None and Me <= 16:
+            fused = (hd == 256 and self.use_fused_attention and not (X is None and kv_cache is not None and Me <= 16))
+            if fused:
+                # K1: fused tcgen05 attention; writes O straight into the per-expert buffers (and P for the backward)
+                O0 = self.buf(sv("O0", l), (Mg, NH * hd)) if X is not None else None
+                O1f = self.buf(sv("O1", l), (Me, NH * hd)) if XE is not None else None
+                Pm = self.buf(sv("P", l), (B, R, Tpad)) if save else None
+                split = (Pn * NH) if X is not None else 0
+                ops.fa_gemma_fwd(Q, Kc, Vc, bits, Pm, O0 if O0 is not None else O1f, O1f if O1f is not None else O0,
+                                 B, R, NH, Tq, T, Tpad, W32, split, hd)
+                S = None
+                Oc = None
+            elif X is None and kv_cache is not None and Me <= 16:
                 # suffix-only denoise step: a handful of query tokens against the cache
                 Oc = self.buf(f"{tag}.Oc", (B, R, hd))
                 ops.decode_attn(Q, Kc, Vc, bits, Oc, B, Tq, NH, hd, T, Tpad, W32)
@@ -542,8 +554,9 @@ class LAP:
                 ops.gemm(Pm, Vc, Oc, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
                          a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
             if X is not None:
-                O0 = self.buf(sv("O0", l), (Mg, NH * hd))
-                O0.view(B, Pn * NH * hd).copy_(Oc.view(B, R * hd)[:, : Pn * NH * hd])
+                if not fused:
+                    O0 = self.buf(sv("O0", l), (Mg, NH * hd))
+                    O0.view(B, Pn * NH * hd).copy_(Oc.view(B, R * hd)[:, : Pn * NH * hd])
                 X1 = self.buf(sv("X1", l), (Mg, D))
                 ops.gemm(O0, self.w("g.o_w", l), X1, M=Mg, N=D, K=NH * hd, epi=ops.EPI_RESID, resid=X)
                 h2 = self.buf(sv("h2", l), (Mg, D))
@@ -556,8 +569,10 @@ class LAP:
                 ops.gemm(act, self.w("g.down_w", l), X2, M=Mg, N=D, K=F, epi=ops.EPI_RESID, resid=X1)
                 X = X2
             if XE is not None:
-                O1 = self.buf(sv("O1", l), (Me, NH * hd))
-                if X is not None or Pn == 0 or t_begin == 0:
+                if fused:
+                    O1 = O1f
+                elif X is not None or Pn == 0 or t_begin == 0:
+                    O1 = self.buf(sv("O1", l), (Me, NH * hd))
                     O1.view(B, A * NH * hd).copy_(Oc.view(B, R * hd)[:, (Tq - A) * NH * hd:])
                 else:
                     O1 = Oc.view(Me, NH * hd)
@@ -591,7 +606,7 @@ class LAP:
         C, Np = len(cfg.image_keys), cfg.num_patches
         D, D1, ad, V = g.width, e.width, cfg.action_dim, cfg.vocab_size
         T = Pn + A
-        Tpad = _round_up(T, 32)
+        Tpad = _round_up(T, 64)
         Mg, Me = B * Pn, B * A
         sv0 = "g.X.0" if save else "g.X.tmp0"
         X0 = self.buf(sv0, (Mg, D))
@@ -693,7 +708,7 @@ class LAP:
         QKV = (NH + 2) * hd
         F, F1 = g.mlp_dim, e.mlp_dim
         T = Pn + A
-        Tpad = _round_up(T, 32)
+        Tpad = _round_up(T, 64)
         Mg, Me, R = B * Pn, B * A, st.R
         Rq = T * NH
         nm = P.n_mod(cfg)
@@ -853,7 +868,7 @@ class LAP:
         C, Np = len(cfg.image_keys), cfg.num_patches
         D, D1, ad = g.width, e.width, cfg.action_dim
         T = Pn + A
-        Tpad = _round_up(T, 32)
+        Tpad = _round_up(T, 64)
         W32 = Tpad // 32
         x = self.buf("inf.x", (B, A * ad), F32)
         # ---- prefix pass fills the cache ----
@@ -902,7 +917,7 @@ class LAP:
     def _gemma_fwd_prefix(self, B, X, bits, positions, cache):
         cfg, g = self.cfg, self.cfg.gemma
         Pn = cfg.prefix_len
-        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 32)
+        Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 64)
         W32 = Tpad // 32
         D, hd, NH, F = g.width, g.head_dim, g.num_heads, g.mlp_dim
         QKV = (NH + 2) * hd
@@ -918,14 +933,17 @@ class LAP:
             ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
             Q = self.buf("inf.Qp", (B, Pn, NH, hd))
             ops.rope_fwd(qkv0, None, positions, self.timescale, Q, Kc, Vc, B, Pn, 0, Tpad, NH, hd, 0, qscale)
-            S = self.buf("inf.Sp", (B, R, Tpad), F32)
-            ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
-                     c_bs=(R * Tpad, 0))
-            Pm = self.buf("inf.Pp", (B, R, Tpad))
-            ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, Pn, Tpad, W32)
             O0 = self.buf("inf.O0", (Mg, NH * hd))
-            ops.gemm(Pm, Vc, O0, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
-                     a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
+            if hd == 256 and self.use_fused_attention:
+                ops.fa_gemma_fwd(Q, Kc, Vc, bits, None, O0, O0, B, R, NH, Pn, Pn, Tpad, W32, R, hd)
+            else:
+                S = self.buf("inf.Sp", (B, R, Tpad), F32)
+                ops.gemm(Q, Kc, S, M=R, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=(R * hd, 0), b_bs=(Tpad * hd, 0),
+                         c_bs=(R * Tpad, 0))
+                Pm = self.buf("inf.Pp", (B, R, Tpad))
+                ops.attn_softmax_fwd(S, bits, Pm, B, R, NH, Pn, Tpad, W32)
+                ops.gemm(Pm, Vc, O0, M=R, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                         a_bs=(R * Tpad, 0), b_bs=(Tpad * hd, 0), c_bs=(R * hd, 0))
             X1 = self.buf("inf.X1", (Mg, D))
             ops.gemm(O0, self.w("g.o_w", l), X1, M=Mg, N=D, K=NH * hd, epi=ops.EPI_RESID, resid=X)
             h2 = self.buf("inf.h2", (Mg, D))

@@ -354,3 +354,7 @@ def linear_f32(X, W, Y, M, N, K, bias=None):
         call("gemv_f32", X, X.dtype == torch.bfloat16, K, W, bias, Y, N, Y.dtype == torch.bfloat16, M, N, K)
     else:
         sgemm(X, W, Y, M, N, K, K, 1, K, 1, ldc=N, bias=bias)
+
+
+def fa_gemma_fwd(Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim):
+    call("fa_gemma_fwd", Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim)

@@ -391,3 +391,47 @@ def test_decode_attention_matches_reference():
     p = torch.softmax(logits, -1).bfloat16().float()
     ref = torch.einsum("bhqs,bsd->bqhd", p, Vc[:, :T].float())
     assert rel_err(O, ref) < 4e-3
+
+
+@pytest.mark.parametrize("B,Tq,T,split_tok", [(2, 178, 178, 168), (1, 702, 702, 692), (2, 10, 178, 0)])
+def test_fused_attention_matches_unfused(B, Tq, T, split_tok):
+    """K1 fused tcgen05 attention vs GEMM + masked softmax + GEMM on the same inputs (same rounding points)."""
+    NH, HD = 8, 256
+    Tpad = (T + 63) // 64 * 64
+    W32 = Tpad // 32
+    R = Tq * NH
+    torch.manual_seed(T + Tq)
+    Q = (torch.randn(B, Tq, NH, HD, device=DEV) * 0.25).bfloat16()
+    Kc = torch.zeros(B, Tpad, HD, device=DEV, dtype=torch.bfloat16)
+    Vc = torch.zeros_like(Kc)
+    Kc[:, :T] = torch.randn(B, T, HD, device=DEV).bfloat16()
+    Vc[:, :T] = torch.randn(B, T, HD, device=DEV).bfloat16()
+    dense = torch.rand(B, Tq, T, device=DEV) < 0.6
+    dense[0, 1] = False  # fully masked row
+    bits = torch.zeros(B, Tq, W32, dtype=torch.int64, device=DEV)
+    for j in range(T):
+        bits[:, :, j // 32] |= dense[:, :, j].long() << (j % 32)
+    bits32 = torch.where(bits >= 2 ** 31, bits - 2 ** 32, bits).to(torch.int32)
+    # unfused
+    S = torch.zeros(B, R, Tpad, device=DEV)
+    ops.gemm(Q, Kc, S, M=R, N=Tpad, K=HD, ldc=Tpad, batch_i=B, a_bs=(R * HD, 0), b_bs=(Tpad * HD, 0), c_bs=(R * Tpad, 0))
+    P_ref = torch.zeros(B, R, Tpad, device=DEV, dtype=torch.bfloat16)
+    ops.attn_softmax_fwd(S, bits32, P_ref, B, R, NH, T, Tpad, W32)
+    O_ref = torch.zeros(B, R, HD, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(P_ref, Vc, O_ref, M=R, N=HD, K=Tpad, b_major=1, lda=Tpad, ldb=HD, ldc=HD, batch_i=B,
+             a_bs=(R * Tpad, 0), b_bs=(Tpad * HD, 0), c_bs=(R * HD, 0))
+    # fused
+    split = split_tok * NH
+    P = torch.full((B, R, Tpad), 7.0, device=DEV, dtype=torch.bfloat16)
+    O0 = torch.zeros(B, max(split, 1), HD, device=DEV, dtype=torch.bfloat16)
+    O1 = torch.zeros(B, max(R - split, 1), HD, device=DEV, dtype=torch.bfloat16)
+    ops.fa_gemma_fwd(Q, Kc, Vc, bits32, P, O0, O1, B, R, NH, Tq, T, Tpad, W32, split, HD)
+    torch.cuda.synchronize()
+    assert rel_err(P, P_ref) < 2e-3
+    assert (P.float() - P_ref.float()).abs().max() < 2 ** -7  # at most one bf16 ulp of a probability
+    O = torch.cat([O0[:, :split], O1[:, : R - split]], 1) if 0 < split < R else (O0 if split == R else O1)
+    assert rel_err(O, O_ref) < 4e-3
+    # without P output (inference)
+    O0b, O1b = torch.zeros_like(O0), torch.zeros_like(O1)
+    ops.fa_gemma_fwd(Q, Kc, Vc, bits32, None, O0b, O1b, B, R, NH, Tq, T, Tpad, W32, split, HD)
+    assert torch.equal(O0b, O0) and torch.equal(O1b, O1)

@@ -48,7 +48,7 @@ def test_loss_and_sampling_match_golden(name, B):
     # integer/bool work is bit-exact
     cfg = tc.model
     T = cfg.prefix_len + cfg.action_horizon
-    Tpad = (T + 31) // 32 * 32
+    Tpad = (T + 63) // 64 * 64
     dense = torch.zeros(B, T, T, dtype=torch.uint8, device="cuda")
     ops.mask_expand(model._bufs["mask.bits"], dense, B * T, T, Tpad // 32)
     assert np.array_equal(np.packbits(dense.cpu().numpy().astype(bool), axis=-1), g["mask"])

@@ -30,7 +30,7 @@ obs, actions, extra = batch_from_dict(b)
 # ---- masks bit-exact ----
 st = model._stage(obs, actions, noise, tm, with_loss=True)
 loss_e, m_e = model.compute_loss(0, obs, actions, noise=noise, time=tm)
-Pn, A = cfg.prefix_len, cfg.action_horizon; T = Pn + A; Tpad = (T + 31) // 32 * 32
+Pn, A = cfg.prefix_len, cfg.action_horizon; T = Pn + A; Tpad = (T + 63) // 64 * 64
 bits = model._bufs["mask.bits"]; dense = torch.zeros(B, T, T, dtype=torch.uint8, device="cuda")
 ops.mask_expand(bits, dense, B * T, T, Tpad // 32)
 pos_e = model._bufs["mask.pos"].cpu()
