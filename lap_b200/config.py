@@ -299,6 +299,15 @@ _CONFIGS = {
         lr_schedule=CosineDecaySchedule(warmup_steps=2, peak_lr=1e-3, decay_steps=10, decay_lr=1e-4),
         num_train_steps=10, batch_size=4, ema_schedule_choice=EmaScheduleChoice(kind="constant"),
     ),
+    # BASELINE.json's 48-token / 50-step variant (upstream Pi0Config defaults, OP/models/pi0_config.py:25-37) at test size
+    "debug_bj": TrainConfig(
+        name="debug_bj",
+        model=LAPConfig(paligemma_variant="small_2b", action_expert_variant="small_300m", siglip_variant="tiny72/14",
+                        action_dim=32, action_horizon=50, max_token_len=48, enable_action_training=True,
+                        language_loss_weight=1.0, enable_image_augmentation=False, vocab_size=1024, image_size=56),
+        lr_schedule=CosineDecaySchedule(warmup_steps=2, peak_lr=1e-3, decay_steps=10, decay_lr=1e-4),
+        num_train_steps=10, batch_size=4, ema_schedule_choice=EmaScheduleChoice(kind="cosine_delayed", start_step=2),
+    ),
 }
 
 

@@ -187,3 +187,87 @@ def test_batch1_sampling_uses_streaming_kernels_and_matches_oracle():
     a3 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])  # replay
     assert rel_err(a1, a_o) < TOL_ACT
     assert torch.equal(a1, a2) and torch.equal(a2, a3)
+
+
+def _grad_check(tc, ref, model, b, tol=TOL_GRAD):
+    from lap_b200.train import batch_from_dict, init_train_state
+    obs, actions, extra = batch_from_dict(b)
+    init_train_state(tc, model=model)
+    st = model._stage(obs, actions, extra["noise"], extra["time"], with_loss=True)
+    loss = model.forward_backward(st)
+    g_eng = model.params_reference(model.G)
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    z = {k: torch.zeros_like(v) for k, v in ref.items()}
+    state = dict(step=0, params=ref, mu=z, nu=dict(z), ema=None)
+    _, info, g_o = O.train_step(tc, state, obs_for_oracle(b), t(b["actions"]), t(b["noise"]), t(b["time"]), bf16=True)
+    gnorm = float(info["grad_norm"])
+    assert abs(float(loss[0]) - float(info["loss"])) < 2e-3 * abs(float(info["loss"]))
+    for k in g_o:
+        assert torch.isfinite(g_eng[k]).all(), k
+        if g_o[k].norm() < 2e-3 * gnorm:
+            assert (g_eng[k] - g_o[k]).norm() < 4e-3 * gnorm, k
+        else:
+            assert rel_err(g_eng[k], g_o[k]) < tol, (k, rel_err(g_eng[k], g_o[k]))
+
+
+def test_edge_cases_empty_langact_dropped_camera_masked_samples():
+    """Ragged inputs: a sample without lang-action tokens, a sample_mask=False sample, a dropped wrist camera."""
+    tc, ref, model, b = _setup("debug_small", 3, seed=3, step=4)
+    b = {k: (dict(v) if isinstance(v, dict) else v.copy()) for k, v in b.items()}
+    b["tokenized_langact_mask"][0, :] = False                      # no language targets at all for sample 0
+    b["sample_mask"][:] = [True, False, True]                      # sample 1 carries no language loss
+    b["image_mask"] = {k: v.copy() for k, v in b["image_mask"].items()}
+    b["image_mask"]["left_wrist_0_rgb"][2] = False                 # dropped camera: its 64 tokens are masked keys
+    b["image"] = {k: v.copy() for k, v in b["image"].items()}
+    b["image"]["left_wrist_0_rgb"][2] = -1.0
+    _grad_check(tc, ref, model, b)
+
+
+def test_edge_case_no_language_rows_at_all():
+    """Every CE row masked out: the loss is the action term alone and the LM-head path contributes exact zeros."""
+    from lap_b200.train import batch_from_dict, init_train_state
+    tc, ref, model, b = _setup("debug_tiny", 2)
+    b = dict(b)
+    b["sample_mask"] = np.zeros(2, dtype=bool)
+    obs, actions, extra = batch_from_dict(b)
+    init_train_state(tc, model=model)
+    st = model._stage(obs, actions, extra["noise"], extra["time"], with_loss=True)
+    loss = model.forward_backward(st)
+    m = model._metrics(st)
+    assert abs(float(loss[0]) - tc.model.action_loss_weight * float(m["action_loss"])) < 1e-5 * abs(float(loss[0]))
+    assert float(m["lang_loss"]) == 0.0
+    assert torch.isfinite(model.G).all()
+    g = model.params_reference(model.G)
+    assert g["PaliGemma/llm/final_norm/scale"].abs().max() == 0  # only the language head uses the prefix final norm
+
+
+def test_bj_shape_48_tokens_50_step_chunk():
+    """BASELINE.json's 48-token / 50-step shape (action_dim 32) at test size: loss, gradients, sampling."""
+    from lap_b200.observation import Observation
+    tc, ref, model, b = _setup("debug_bj", 2, seed=5, step=2)
+    _grad_check(tc, ref, model, b)
+    model.load_params(ref)
+    b2 = {k: v for k, v in b.items() if k != "tokenized_langact_mask"}
+    a = model.sample_actions(0, Observation.from_dict(b2), num_steps=10, noise=b["noise"])
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    a_o = O.sample_actions(ref, tc.model, obs_for_oracle(b, langact=False), t(b["noise"]), num_steps=10, bf16=True)
+    assert a.shape == (2, 50, 32) and rel_err(a, a_o) < TOL_ACT
+
+
+def test_batch_one_training_step():
+    """B = 1: the expert sees 10 rows, so its forward projections go through the weight-streaming kernel (with the
+    saved branch outputs the backward needs)."""
+    tc, ref, model, b = _setup("debug_small", 1, seed=2, step=9)
+    b = dict(b)
+    b["sample_mask"] = np.ones(1, dtype=bool)
+    _grad_check(tc, ref, model, b)
+
+
+def test_unfused_attention_path_matches_fused():
+    from lap_b200.train import batch_from_dict
+    tc, ref, model, b = _setup("debug_small", 2)
+    obs, actions, extra = batch_from_dict(b)
+    l_fused, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    model.use_fused_attention = False
+    l_unfused, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    assert abs(l_fused.item() - l_unfused.item()) < 2e-4 * abs(l_unfused.item())
