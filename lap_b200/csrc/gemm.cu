@@ -224,6 +224,17 @@ __device__ __forceinline__ void staged_store_bf16(uint8_t* stg, int lane, const 
   }
   __syncwarp();
 }
+// warm L1 with the residual segments a later staged_load_bf16 of the same chunk will read (no registers held)
+__device__ __forceinline__ void staged_prefetch(int lane, const __nv_bfloat16* gbase, long ld, int rows_valid,
+                                                int cols_valid) {
+  const int c = lane & 3;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = (lane >> 2) + 8 * i;
+    if (r < rows_valid && c * 8 < cols_valid)
+      asm volatile("prefetch.global.L1 [%0];" ::"l"(gbase + (long)r * ld + c * 8));
+  }
+}
 __device__ __forceinline__ void staged_load_bf16(uint8_t* stg, int lane, const __nv_bfloat16* gbase, long ld,
                                                  int rows_valid, int cols_valid, float (&out)[32]) {
   const int c = lane & 3;
@@ -545,11 +556,18 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
       int bo, bi, m_blk, n_blk, kb0, kb1;
       decode_tile(tile, a, bo, bi, m_blk, n_blk, kb0, kb1);
-      mbar_wait(&tfull_bar[acc], acc_phase);
-      tc_fence_after();
       const long row = (long)m_blk * TILE_M + cta_rank * BM + q * 32 + lane;
       const long c_boff = bi * a.c_bs_i + bo * a.c_bs_o;
       const long r_boff = bi * a.r_bs_i + bo * a.r_bs_o;
+      const bool has_resid = !DUAL && !a.c_fp32 && (a.epi == LAPB_EPI_RESID || a.epi == LAPB_EPI_GATED_RESID);
+      const long row0w = row - lane;
+      const int rows_valid_w = (int)min(32L, (long)a.M - row0w);
+      if (has_resid && rows_valid_w > 0) {  // residual rows of this warp's first chunk: fetch while the MMAs still run
+        const int col0 = n_blk * BN + half * CH_PER_WARP * 32;
+        staged_prefetch(lane, a.resid + r_boff + row0w * a.ldr + col0, a.ldr, rows_valid_w, min(32, a.N - col0));
+      }
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * Cfg::ACC_COLS;
 #pragma unroll 1
       for (int cc = 0; cc < CH_PER_WARP; ++cc) {
@@ -560,8 +578,38 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (DUAL) tmem_ld_32x32(taddr + BN + c * 32, r2);
         tmem_ld_wait();
         const int col0 = n_blk * BN + c * 32;
+        if (has_resid && rows_valid_w > 0 && cc + 1 < CH_PER_WARP)
+          staged_prefetch(lane, a.resid + r_boff + row0w * a.ldr + col0 + 32, a.ldr, rows_valid_w, min(32, a.N - col0 - 32));
         if (!a.c_fp32) {
           epilogue_chunk_bf16<DUAL>(a, stg, lane, row - lane, col0, c_boff, r_boff, r, r2);
+        } else if (a.k_splits > 1) {
+          // split-K partial sums: transpose 32x16 fp32 halves through the staging buffer so that each
+          // red.global.add.v4.f32 covers 8 rows x 64 contiguous bytes (C was zeroed by the launcher)
+          const int rows_valid = (int)min(32L, (long)a.M - row0w);
+          if (rows_valid > 0) {
+            float* cbase = reinterpret_cast<float*>(a.C) + c_boff + row0w * a.ldc + col0;
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf) {
+#pragma unroll
+              for (int v = 0; v < 4; ++v)
+                *reinterpret_cast<uint4*>(stg + stg_off(lane, v)) =
+                    make_uint4(r[hf * 16 + 4 * v], r[hf * 16 + 4 * v + 1], r[hf * 16 + 4 * v + 2], r[hf * 16 + 4 * v + 3]);
+              __syncwarp();
+              const int cq = lane & 3;
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int rr = (lane >> 2) + 8 * i;
+                const int col = col0 + hf * 16 + cq * 4;
+                if (rr < rows_valid && col < a.N) {
+                  float4 v4 = *reinterpret_cast<const float4*>(stg + stg_off(rr, cq));
+                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (long)rr * a.ldc + hf * 16 + cq * 4),
+                               "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w)
+                               : "memory");
+                }
+              }
+              __syncwarp();
+            }
+          }
         } else if (row < a.M) {
 #pragma unroll
           for (int v = 0; v < 4; ++v) {
@@ -758,7 +806,7 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
   // cut along K into units that add their partial sums atomically.
   ka.k_splits = 1;
   ka.kb_per_split = ka.num_k;
-  if (p->c_fp32 && p->epi == LAPB_EPI_NONE && !p->bias && bi * bo == 1 && p->k_splits > 1) {
+  if (p->c_fp32 && p->epi == LAPB_EPI_NONE && !p->bias && bi * bo == 1 && p->k_splits != 1) {
     const long slots = max_ctas / CG;
     int best = 1;
     if (p->k_splits > 1) {
