@@ -203,84 +203,251 @@ layernorm_fwd_kernel(const bf16* __restrict__ x, const float* __restrict__ scale
   }
 }
 
-// dx = dres + LN'(dy); dscale += sum dy*xhat; dbias += sum dy.
-// One WARP per row, shuffle reductions only.  Two passes over the row (the second read is served by L1/L2) keep
-// the register footprint small so many warps — and many bytes — are in flight per SM.  Each lane owns fixed columns
-// and keeps its dscale/dbias partial sums in registers across the rows of its warp; the warps of a CTA are combined
-// in shared memory and issue one atomicAdd per column per CTA.
-template <int NV>
-__global__ void __launch_bounds__(256)
-layernorm_bwd_kernel(const bf16* __restrict__ dy, const bf16* __restrict__ x, const float* __restrict__ scale,
-                     const float* __restrict__ mean, const float* __restrict__ rstd, const bf16* __restrict__ dres,
-                     bf16* __restrict__ dx, float* __restrict__ dscale, float* __restrict__ dbias, long M, int W) {
-  extern __shared__ float sred[];  // [2][W]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ds[NV][8], db[NV][8];
+// ------------------------------------------------------------------------------------------------
+// Norm backward (LayerNorm: siglip.py:87,98,161; plain RMSNorm: gemma.py:112-131).
+//   LN : dx = dres + rstd*(g - mean(g) - xhat*mean(g*xhat)), g = dy*scale, xhat = (x-mean)*rstd;
+//        dscale += sum_rows dy*xhat; dbias += sum_rows dy
+//   RMS: dx[src] = dres[src] + rstd*(g - xhat*mean(g*xhat)), g = dy*(1+scale), xhat = x*rstd; dscale += sum dy*xhat
+// One persistent CTA per SM, split into SLOTS independent row slots of TPB threads (one 16-byte vector per thread,
+// width <= 2048).  Each slot walks its rows through a 4-deep shared-memory ring filled by 1-D TMA bulk copies that
+// the slot leader issues four rows ahead, so every element crosses HBM once and the bytes in flight per SM (~190 KB)
+// are set by the ring, not by registers.  A slot synchronises on its own named barrier once per row (row reduction +
+// "stage consumed").  The per-column dscale/dbias partial sums stay in registers for the whole kernel; at the end
+// the slots of a CTA are combined in shared memory and each CTA issues width/4 vector reductions
+// (red.global.add.v4.f32): scalar atomics from ~700 CTAs were measured to cost more than the whole streaming pass.
+// Everything the row loop touches is a compile-time constant (TPB, SLOTS, ring offsets) to keep it ~150 instructions.
+// ------------------------------------------------------------------------------------------------
+struct NormBwdArgs {
+  const bf16* dy; long lddy;
+  const bf16* x; long ldx;
+  const long* row_idx;      // RMS only (optional): source/destination row of x, dres, dx
+  const float* scale;
+  const float* mean;        // LN only
+  const float* rstd;
+  const bf16* dres;         // optional
+  bf16* dx;
+  float* dscale;
+  float* dbias;             // LN only
+  long M;
+  int D;
+};
+constexpr int NORM_STAGES = 4, NORM_R = 2;  // ring depth; rows per slot iteration (ILP across independent rows)
+constexpr int norm_slots(int tpb) { return (512 / tpb) < 8 ? (512 / tpb) : 8; }
+constexpr size_t norm_smem(int tpb) {
+  return (size_t)norm_slots(tpb) * NORM_STAGES * NORM_R * 3 * tpb * 8 * sizeof(bf16);
+}
+
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+  v[0] = __uint_as_float(u.x << 16); v[1] = __uint_as_float(u.x & 0xffff0000u);
+  v[2] = __uint_as_float(u.y << 16); v[3] = __uint_as_float(u.y & 0xffff0000u);
+  v[4] = __uint_as_float(u.z << 16); v[5] = __uint_as_float(u.z & 0xffff0000u);
+  v[6] = __uint_as_float(u.w << 16); v[7] = __uint_as_float(u.w & 0xffff0000u);
+}
+
+template <int TPB, bool LN>
+__global__ void __launch_bounds__(norm_slots(TPB) * TPB, 1) norm_bwd_kernel(const NormBwdArgs a) {
+  constexpr int SLOTS = norm_slots(TPB), ROW = TPB * 8, R = NORM_R, STAGE = R * 3 * ROW;
+  extern __shared__ __align__(128) unsigned char ring_raw[];  // [SLOTS][NORM_STAGES][R][3][ROW] bf16
+  __shared__ uint64_t full[SLOTS][NORM_STAGES];
+  __shared__ __align__(16) float red[SLOTS][2][R][2][8];
+  const int slot = threadIdx.x / TPB, t = threadIdx.x % TPB;
+  bf16* ring = reinterpret_cast<bf16*>(ring_raw) + slot * (NORM_STAGES * STAGE);
+  const int c = t * 8;
+  const bool act = c < a.D;
+  const bool has_res = a.dres != nullptr;
+  const uint32_t row_bytes = (uint32_t)a.D * 2;
+  const long stride = (long)gridDim.x * SLOTS * R;
+  auto issue = [&](int stage, long row0) {  // rows row0 .. row0+R-1 (those < M)
+    uint64_t* bar = &full[slot][stage];
+    const int nrows = (int)(a.M - row0 < R ? a.M - row0 : R);
+    mbar_expect_tx(bar, nrows * (has_res ? 3 : 2) * row_bytes);
 #pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) { ds[i][j] = 0.f; db[i][j] = 0.f; }
-  for (int c = threadIdx.x; c < 2 * W; c += 256) sred[c] = 0.f;
-  __syncthreads();
-  const long nwarps = (long)gridDim.x * 8;
-  for (long row = (long)blockIdx.x * 8 + warp; row < M; row += nwarps) {
-    const float mu = mean[row], rs = rstd[row];
-    float sg = 0.f, sgx = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int c = (lane + 32 * i) * 8;
-      if (c < W) {
-        float d[8], xv[8], sc[8];
-        ld8(dy + row * W + c, d);
-        ld8(x + row * W + c, xv);
-        ld8f(scale + c, sc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float xh = (xv[j] - mu) * rs, g = d[j] * sc[j];
-          sg += g;
-          sgx += g * xh;
-          ds[i][j] += d[j] * xh;
-          db[i][j] += d[j];
-        }
+    for (int r = 0; r < R; ++r) {
+      if (r < nrows) {
+        const long row = row0 + r;
+        const long src = (!LN && a.row_idx) ? a.row_idx[row] : row;
+        bf16* dst = ring + stage * STAGE + r * (3 * ROW);
+        bulk_load_1d(dst, a.dy + row * a.lddy, row_bytes, bar);
+        bulk_load_1d(dst + ROW, a.x + src * a.ldx, row_bytes, bar);
+        if (has_res) bulk_load_1d(dst + 2 * ROW, a.dres + src * a.ldx, row_bytes, bar);
       }
     }
-    sg = warp_sum(sg) / W;
-    sgx = warp_sum(sgx) / W;
+  };
+  long row0 = ((long)blockIdx.x * SLOTS + slot) * R;
+  if (t == 0) {
 #pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int c = (lane + 32 * i) * 8;
-      if (c < W) {
-        float d[8], xv[8], sc[8], o[8], rr[8];
-        ld8(dy + row * W + c, d);
-        ld8(x + row * W + c, xv);
-        ld8f(scale + c, sc);
-        if (dres) ld8(dres + row * W + c, rr);
+    for (int s = 0; s < NORM_STAGES; ++s) mbar_init(&full[slot][s], 1);
+    fence_barrier_init();
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float xh = (xv[j] - mu) * rs;
-          o[j] = rs * (d[j] * sc[j] - sg - xh * sgx);
-          if (dres) o[j] += rr[j];
-        }
-        st8(dx + row * W + c, o);
-      }
+    for (int s = 0; s < NORM_STAGES; ++s) {
+      const long r = row0 + s * stride;
+      if (r < a.M) issue(s, r);
     }
   }
+  for (int i = t; i < 2 * R * 2 * 8; i += TPB) (&red[slot][0][0][0][0])[i] = 0.f;
+  float ds[8], db[8], sc[8];
 #pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    int c = (lane + 32 * i) * 8;
-    if (c < W) {
+  for (int j = 0; j < 8; ++j) { ds[j] = 0.f; db[j] = 0.f; sc[j] = 0.f; }
+  if (act) {
+    ld8f(a.scale + c, sc);
+    if (!LN) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) sc[j] += 1.0f;
+    }
+  }
+  __syncthreads();
+  const float invD = 1.0f / a.D;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  int s = 0, ph = 0, par = 0;
+  float nmu[R], nrs[R];
+  long nsrc[R];
+  auto fetch_stats = [&](long base) {  // per-row scalars of the NEXT iteration (consumed one iteration later)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const long row = base + r < a.M ? base + r : a.M - 1;
+      nrs[r] = a.rstd[row];
+      nmu[r] = LN ? a.mean[row] : 0.f;
+      nsrc[r] = (!LN && a.row_idx) ? a.row_idx[row] : row;
+    }
+  };
+  if (row0 < a.M) fetch_stats(row0);
+  for (; row0 < a.M; row0 += stride) {
+    float mu[R], rs[R];
+    long src[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { mu[r] = nmu[r]; rs[r] = nrs[r]; src[r] = nsrc[r]; }
+    if (row0 + stride < a.M) fetch_stats(row0 + stride);
+    mbar_wait(&full[slot][s], ph);
+    float g[R][8], xh[R][8], sg[R], sgx[R];
+    uint4 vr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const bool on = act && (row0 + r < a.M);  // columns past the width / rows past M hold stale ring bytes
+      const bf16* st = ring + s * STAGE + r * (3 * ROW) + c;
+      const uint4 vd = *reinterpret_cast<const uint4*>(st);
+      const uint4 vx = *reinterpret_cast<const uint4*>(st + ROW);
+      vr[r] = has_res ? *reinterpret_cast<const uint4*>(st + 2 * ROW) : zero4;
+      unpack8(vd, g[r]);
+      unpack8(vx, xh[r]);
+      sg[r] = 0.f;
+      sgx[r] = 0.f;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&sred[c + j], ds[i][j]);
-        atomicAdd(&sred[W + c + j], db[i][j]);
+        if (!on) { g[r][j] = 0.f; xh[r][j] = 0.f; }
+        xh[r][j] = LN ? (xh[r][j] - mu[r]) * rs[r] : xh[r][j] * rs[r];
+        if (!on) xh[r][j] = 0.f;
+        ds[j] = fmaf(g[r][j], xh[r][j], ds[j]);
+        if (LN) db[j] += g[r][j];
+        g[r][j] *= sc[j];
+        if (LN) sg[r] += g[r][j];
+        sgx[r] = fmaf(g[r][j], xh[r][j], sgx[r]);
       }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        sgx[r] += __shfl_xor_sync(0xffffffffu, sgx[r], o);
+        if (LN) sg[r] += __shfl_xor_sync(0xffffffffu, sg[r], o);
+      }
+    }
+    if ((t & 31) == 0) {
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        red[slot][par][r][0][t >> 5] = sgx[r];
+        if (LN) red[slot][par][r][1][t >> 5] = sg[r];
+      }
+    }
+    named_bar_sync(1 + slot, TPB);  // also: every thread of the slot has read stage s -> it may be refilled
+    if (t == 0) {
+      const long r = row0 + NORM_STAGES * stride;
+      if (r < a.M) issue(s, r);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float4 r0 = *reinterpret_cast<const float4*>(&red[slot][par][r][0][0]);
+      const float4 r1 = *reinterpret_cast<const float4*>(&red[slot][par][r][0][4]);
+      sgx[r] = (((r0.x + r0.y) + (r0.z + r0.w)) + ((r1.x + r1.y) + (r1.z + r1.w))) * invD;
+      if (LN) {
+        const float4 q0 = *reinterpret_cast<const float4*>(&red[slot][par][r][1][0]);
+        const float4 q1 = *reinterpret_cast<const float4*>(&red[slot][par][r][1][4]);
+        sg[r] = (((q0.x + q0.y) + (q0.z + q0.w)) + ((q1.x + q1.y) + (q1.z + q1.w))) * invD;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      if (act && row0 + r < a.M) {
+        float rr[8];
+        unpack8(vr[r], rr);
+        uint4 o;
+        uint32_t* ow = reinterpret_cast<uint32_t*>(&o);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2) {
+          float o0 = fmaf(-xh[r][j], sgx[r], g[r][j]), o1 = fmaf(-xh[r][j + 1], sgx[r], g[r][j + 1]);
+          if (LN) { o0 -= sg[r]; o1 -= sg[r]; }
+          ow[j >> 1] = pack_bf16x2(fmaf(rs[r], o0, rr[j]), fmaf(rs[r], o1, rr[j + 1]));
+        }
+        *reinterpret_cast<uint4*>(a.dx + src[r] * a.ldx + c) = o;
+      }
+    }
+    par ^= 1;
+    if (++s == NORM_STAGES) { s = 0; ph ^= 1; }
+  }
+  // combine the slots of this CTA (the ring is idle now: every issued copy has been waited on)
+  __syncthreads();
+  float* acc = reinterpret_cast<float*>(ring_raw);  // [SLOTS][2][ROW]
+  if (act) {
+    *reinterpret_cast<float4*>(acc + (slot * 2 + 0) * ROW + c) = make_float4(ds[0], ds[1], ds[2], ds[3]);
+    *reinterpret_cast<float4*>(acc + (slot * 2 + 0) * ROW + c + 4) = make_float4(ds[4], ds[5], ds[6], ds[7]);
+    if (LN) {
+      *reinterpret_cast<float4*>(acc + (slot * 2 + 1) * ROW + c) = make_float4(db[0], db[1], db[2], db[3]);
+      *reinterpret_cast<float4*>(acc + (slot * 2 + 1) * ROW + c + 4) = make_float4(db[4], db[5], db[6], db[7]);
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < W; c += 256) {
-    atomicAdd(dscale + c, sred[c]);
-    atomicAdd(dbias + c, sred[W + c]);
+  const int nq = a.D / 4;
+  for (int i = threadIdx.x; i < (LN ? 2 : 1) * nq; i += SLOTS * TPB) {
+    const int which = i >= nq ? 1 : 0, c4 = (i - which * nq) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int q = 0; q < SLOTS; ++q) {
+      const float4 u = *reinterpret_cast<const float4*>(acc + (q * 2 + which) * ROW + c4);
+      v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+    }
+    red_add_v4((which ? a.dbias : a.dscale) + c4, v.x, v.y, v.z, v.w);
   }
+}
+
+template <bool LN>
+static int launch_norm_bwd(const NormBwdArgs& a, cudaStream_t stream) {
+  const int tpb = (a.D / 8 + 31) / 32 * 32;
+#define NORM_BWD_CASE(T)                                                                                          \
+  case T: {                                                                                                       \
+    static bool attr_set = false;                                                                                 \
+    if (!attr_set) {                                                                                              \
+      LAPB_CUDA_OK(cudaFuncSetAttribute(norm_bwd_kernel<T, LN>, cudaFuncAttributeMaxDynamicSharedMemorySize,      \
+                                        (int)norm_smem(T)));                                                      \
+      attr_set = true;                                                                                            \
+    }                                                                                                             \
+    constexpr int rows_per_cta = norm_slots(T) * NORM_R;                                                         \
+    const int grid = (int)std::min<long>((a.M + rows_per_cta - 1) / rows_per_cta, (long)num_sms());              \
+    norm_bwd_kernel<T, LN><<<grid, norm_slots(T) * T, norm_smem(T), stream>>>(a);                                 \
+    break;                                                                                                        \
+  }
+  switch (tpb) {
+    NORM_BWD_CASE(32)
+    NORM_BWD_CASE(64)
+    NORM_BWD_CASE(96)
+    NORM_BWD_CASE(128)
+    NORM_BWD_CASE(160)
+    NORM_BWD_CASE(192)
+    NORM_BWD_CASE(224)
+    NORM_BWD_CASE(256)
+    default:
+      return set_error(-1, "norm_bwd: width %d not supported (must be <= 2048)", a.D);
+  }
+#undef NORM_BWD_CASE
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -326,74 +493,6 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, long ldx, const long* __restrict_
     st8(y + row * ldy + c, o);
     if (dup) st8(y + row * ldy + D + c, o);  // [y | y] for the split-table LM head
   }
-}
-
-// plain RMSNorm backward: dx[dst] = (dres? dres:0) + rstd*(g - xhat*mean(g*xhat)), g = dy*(1+scale); dscale += dy*xhat
-// (warp per row, two passes, same structure as layernorm_bwd_kernel)
-template <int NV>
-__global__ void __launch_bounds__(256)
-rmsnorm_bwd_kernel(const bf16* __restrict__ dy, long lddy, const bf16* __restrict__ x, long ldx,
-                   const long* __restrict__ row_idx, const float* __restrict__ scale, const float* __restrict__ rstd,
-                   const bf16* __restrict__ dres, bf16* __restrict__ dx, float* __restrict__ dscale, long M, int D) {
-  extern __shared__ float sred[];  // [D]
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float ds[NV][8];
-#pragma unroll
-  for (int i = 0; i < NV; ++i)
-#pragma unroll
-    for (int j = 0; j < 8; ++j) ds[i][j] = 0.f;
-  for (int c = threadIdx.x; c < D; c += 256) sred[c] = 0.f;
-  __syncthreads();
-  const long nwarps = (long)gridDim.x * 8;
-  for (long row = (long)blockIdx.x * 8 + warp; row < M; row += nwarps) {
-    const long src = row_idx ? row_idx[row] : row;
-    const float rs = rstd[row];
-    float sgx = 0.f;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int c = (lane + 32 * i) * 8;
-      if (c < D) {
-        float d[8], xv[8], sc[8];
-        ld8(dy + row * lddy + c, d);
-        ld8(x + src * ldx + c, xv);
-        ld8f(scale + c, sc);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float xh = xv[j] * rs;
-          sgx += d[j] * (1.0f + sc[j]) * xh;
-          ds[i][j] += d[j] * xh;
-        }
-      }
-    }
-    sgx = warp_sum(sgx) / D;
-#pragma unroll
-    for (int i = 0; i < NV; ++i) {
-      int c = (lane + 32 * i) * 8;
-      if (c < D) {
-        float d[8], xv[8], sc[8], o[8], rr[8];
-        ld8(dy + row * lddy + c, d);
-        ld8(x + src * ldx + c, xv);
-        ld8f(scale + c, sc);
-        if (dres) ld8(dres + src * ldx + c, rr);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          o[j] = rs * (d[j] * (1.0f + sc[j]) - xv[j] * rs * sgx);
-          if (dres) o[j] += rr[j];
-        }
-        st8(dx + src * ldx + c, o);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < NV; ++i) {
-    int c = (lane + 32 * i) * 8;
-    if (c < D) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) atomicAdd(&sred[c + j], ds[i][j]);
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < D; c += 256) atomicAdd(dscale + c, sred[c]);
 }
 
 // adaptive RMSNorm backward, one CTA per sample (rows_per_sample rows):
@@ -786,16 +885,10 @@ int lapb200_layernorm_bwd(const void* dy, const void* x, const float* scale, con
                           const void* dres, void* dx, float* dscale, float* dbias, int64_t M, int64_t W,
                           lapb_stream_t s) {
   LAPB_REQUIRE(W % 8 == 0 && W <= 2048, "layernorm_bwd: W must be a multiple of 8 and <= 2048");
-  int grid = (int)std::min<long>((M + 7) / 8, 148L * 8);
-  size_t smem = 2 * (size_t)W * sizeof(float);
-#define LN_BWD(NV)                                                                                                  \
-  layernorm_bwd_kernel<NV><<<grid, 256, smem, STREAM(s)>>>((const bf16*)dy, (const bf16*)x, scale, mean, rstd,      \
-                                                           (const bf16*)dres, (bf16*)dx, dscale, dbias, M, (int)W)
-  if (W <= 256) LN_BWD(1);
-  else if (W <= 1024) LN_BWD(4);
-  else if (W <= 1280) LN_BWD(5);
-  else LN_BWD(8);
-#undef LN_BWD
+  NormBwdArgs a{(const bf16*)dy, W, (const bf16*)x, W, nullptr, scale, mean, rstd, (const bf16*)dres, (bf16*)dx, dscale,
+                dbias, M, (int)W};
+  if (M <= 0) return 0;
+  if (int rc = launch_norm_bwd<true>(a, STREAM(s))) return rc;
   LAPB_LAUNCH_OK("layernorm_bwd");
   return 0;
 }
@@ -818,17 +911,11 @@ int lapb200_rmsnorm_bwd(const void* dy, int64_t lddy, const void* x, int64_t ldx
                         const float* scale, const float* rstd, const void* dres, void* dx, float* dscale, int64_t M,
                         int64_t D, lapb_stream_t s) {
   LAPB_REQUIRE(D % 8 == 0 && D <= 2048, "rmsnorm_bwd: D must be a multiple of 8 and <= 2048");
-  int grid = (int)std::min<long>((M + 7) / 8, 148L * 8);
-  size_t smem = (size_t)D * sizeof(float);
-#define RMS_BWD(NV)                                                                                              \
-  rmsnorm_bwd_kernel<NV><<<grid, 256, smem, STREAM(s)>>>((const bf16*)dy, lddy, (const bf16*)x, ldx,              \
-                                                         (const long*)row_idx, scale, rstd, (const bf16*)dres,    \
-                                                         (bf16*)dx, dscale, M, (int)D)
-  if (D <= 256) RMS_BWD(1);
-  else if (D <= 1024) RMS_BWD(4);
-  else if (D <= 1280) RMS_BWD(5);
-  else RMS_BWD(8);
-#undef RMS_BWD
+  LAPB_REQUIRE(lddy % 8 == 0 && ldx % 8 == 0, "rmsnorm_bwd: leading dimensions must be multiples of 8");
+  NormBwdArgs a{(const bf16*)dy, lddy, (const bf16*)x, ldx, (const long*)row_idx, scale, nullptr, rstd, (const bf16*)dres,
+                (bf16*)dx, dscale, nullptr, M, (int)D};
+  if (M <= 0) return 0;
+  if (int rc = launch_norm_bwd<false>(a, STREAM(s))) return rc;
   LAPB_LAUNCH_OK("rmsnorm_bwd");
   return 0;
 }
