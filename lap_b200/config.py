@@ -47,6 +47,16 @@ def get_gemma_config(variant: str) -> GemmaConfig:
         return GemmaConfig(width=256, depth=2, mlp_dim=512, num_heads=8, num_kv_heads=1, head_dim=256)
     if variant == "small_300m":
         return GemmaConfig(width=128, depth=2, mlp_dim=256, num_heads=8, num_kv_heads=1, head_dim=256)
+    # variants of tests/golden/make_reference_golden.py: the reference's JAX->PyTorch converter only handles
+    # width == num_heads * head_dim for the PaliGemma tower (convert_jax_model_to_pytorch.py:205-212)
+    if variant == "pin_a":
+        return GemmaConfig(width=128, depth=3, mlp_dim=256, num_heads=8, num_kv_heads=1, head_dim=16)
+    if variant == "pin_a_expert":
+        return GemmaConfig(width=64, depth=3, mlp_dim=128, num_heads=8, num_kv_heads=1, head_dim=16)
+    if variant == "pin_b":
+        return GemmaConfig(width=256, depth=2, mlp_dim=384, num_heads=8, num_kv_heads=1, head_dim=32)
+    if variant == "pin_b_expert":
+        return GemmaConfig(width=96, depth=2, mlp_dim=160, num_heads=8, num_kv_heads=1, head_dim=32)
     raise ValueError(f"Unknown variant: {variant}")
 
 

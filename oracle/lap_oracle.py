@@ -3,12 +3,24 @@
 THIS IS TEST INFRASTRUCTURE, NOT PRODUCT CODE.  Only tests/, __graft_entry__.smoke() and bench.py's
 cpu_baseline / --impl reference legs may import it; nothing under lap_b200/ does.
 
-PARITY UNPINNED: the reference (lihzha/lap, JAX/Flax) cannot be imported in this environment (no jax/flax/
-optax wheels, no network) and its own tests hold no numeric golden vector for this path.
-This file therefore restates the arithmetic by reading the reference source; every function cites the
-file:line it follows (`OP/` = third_party/openpi/src/openpi/).  What IS pinned: the three worked
-`make_attn_mask` examples of OP/models/pi0.py:26-33 (tests/test_oracle.py) and structural invariants
-(training-path == cached-inference-path, shapes of model_test.py).
+PARITY PIN (what the restatement has been checked against, tests/test_reference_golden.py):
+  * the reference's own PyTorch port of the π0.5 arithmetic LAP shares (OP/models_pytorch/pi0_pytorch.py,
+    gemma_pytorch.py, transformers_replace/**), run UNMODIFIED in the build container on seeded weights mapped by the
+    reference's JAX->PyTorch converter: SigLIP tower, token embedding, suffix embedding / adaRMS condition,
+    make_attn_mask + positions (bit-exact), the joint two-expert Gemma stack, the flow-matching squared error and
+    sample_actions (KV cache + Euler loop) agree with the fp32 mode of this file to <= 3e-5 normwise
+    (fixtures tests/golden/reference_pi05_*.npz, generator tests/golden/make_reference_golden.py);
+  * LAP.compute_loss / embed_prefix / prepare_suffix / the lang-action mask builders / the language CE and loss
+    weighting / sample_actions, executed from src/lap/models/lap.py's own source with numpy standing in for
+    jax.numpy and the PyTorch port as leaf modules: masks and positions bit-exact, loss and metrics to <= 2e-4
+    (fixtures tests/golden/reference_lap_*.npz, generator tests/golden/make_reference_lap_golden.py);
+  * the three worked `make_attn_mask` examples of OP/models/pi0.py:26-33 and structural invariants
+    (tests/test_oracle.py).
+STILL UNPINNED (the JAX/Flax program itself cannot run here: no jax/flax/optax wheels, no network; the reference's
+tests hold no numeric vector): WHERE the JAX program rounds to bfloat16 (the bf16=True mode follows SURVEY.md
+Appendix A by reading the source), and the optax/EMA train-step arithmetic (third-party optax, restated from its
+published definitions; closed-form one-step checks only).  Every function cites the file:line it follows
+(`OP/` = third_party/openpi/src/openpi/).
 
 Two precision modes:
   bf16=False : everything in fp32 (the "mathematical" function).

@@ -1,0 +1,200 @@
+"""The oracle (and, with -m gpu, the CUDA engine) against outputs of the REFERENCE'S OWN CODE run in the build container.
+
+Fixtures:
+  tests/golden/reference_pi05_{a,b}.npz  — the reference's PyTorch port (PI0Pytorch / PaliGemmaWithExpertModel / patched HF
+      Gemma + SigLIP) on a π0.5-shaped model;  generator tests/golden/make_reference_golden.py
+  tests/golden/reference_lap_{a,b}.npz   — LAP.compute_loss / embed_prefix / sample_actions / mask builders executed from
+      src/lap/models/lap.py with numpy for jax.numpy and the PyTorch port as leaf modules;  generator
+      tests/golden/make_reference_lap_golden.py
+Parameters and inputs are regenerated here from seeds (tests/golden/reference_cases.py, numpy PCG64) and checked against the
+sha256 stored in the fixture, so nothing under /root/reference is read at test time.
+
+Tolerances: the reference ran in fp32 — the fp32 oracle must agree to 2e-4 normwise (observed ≤ 3e-5: fp32 summation order),
+integer / boolean outputs bit-exactly.  The bf16 engine is compared with the same fp32 reference outputs at bf16
+tolerances (3 x the engine-vs-bf16-oracle tolerances of tests/test_gpu_parity.py).
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import reference_cases as RC  # noqa: E402
+from oracle import lap_oracle as O  # noqa: E402
+from tests.helpers import rel_err  # noqa: E402
+
+TOL_F32 = 2e-4
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _load(kind, case):
+    g = np.load(os.path.join(HERE, "golden", f"reference_{kind}_{case}.npz"))
+    if kind == "pi05":
+        cfg = RC.lap_config(case)
+        _, _, batch, _, _, seed = RC.CASES[case]
+        inp = RC.seeded_inputs(cfg, batch, seed)
+    else:
+        cfg = RC.lap_case_config(case)
+        batch, seed = RC.LAP_CASES[case]["batch"], RC.LAP_CASES[case]["seed"]
+        inp = RC.lap_case_inputs(cfg, batch, seed)
+    params = RC.seeded_reference_params(cfg, seed)
+    assert RC.params_digest(params) == bytes(g["params_sha256"]).decode(), "seeded parameters drifted from the fixture"
+    return cfg, {k: _t(v) for k, v in params.items()}, inp, g
+
+
+def _oracle_obs(cfg, inp, langact="zeros"):
+    pm = _t(inp["tokenized_prompt_mask"])
+    if langact == "zeros":
+        la = torch.zeros_like(pm)
+    elif langact == "none":
+        la = None
+    else:
+        la = _t(inp["tokenized_langact_mask"])
+    return dict(images={k: _t(inp["image/" + k]) for k in cfg.image_keys},
+                image_masks={k: _t(inp["image_mask/" + k]) for k in cfg.image_keys},
+                tokenized_prompt=_t(inp["tokenized_prompt"]), tokenized_prompt_mask=pm, tokenized_langact_mask=la,
+                token_loss_mask=_t(inp["token_loss_mask"]) if "token_loss_mask" in inp else torch.ones_like(pm),
+                sample_mask=_t(inp["sample_mask"]) if "sample_mask" in inp else None)
+
+
+def _rows(x, g):
+    return x[:, RC.row_index(x.shape[1], int(g["row_stride"]))]
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# oracle vs the reference's PyTorch port (π0.5-common arithmetic: SURVEY §8a rows a9-a18, a20, a21)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(RC.CASES))
+def test_oracle_matches_reference_pytorch_port(case):
+    cfg, p, inp, g = _load("pi05", case)
+    obs = _oracle_obs(cfg, inp)
+    sig = O.siglip_forward(p, cfg, obs["images"]["base_0_rgb"], bf16=False)
+    assert rel_err(_rows(sig, g), g["siglip_tokens"]) < TOL_F32
+    actions, noise, time = _t(inp["actions"]), _t(inp["noise"]), _t(inp["time"])
+    _, _, aux = O.compute_loss(p, cfg, obs, actions, noise, time, bf16=False, return_aux=True)
+    assert rel_err(_rows(aux["prefix_tokens"], g), g["prefix_tokens"]) < TOL_F32
+    assert rel_err(aux["suffix_tokens"], g["suffix_tokens"]) < TOL_F32
+    assert rel_err(aux["cond"], g["adarms_cond"]) < TOL_F32
+    # integer / boolean work: bit-exact
+    assert np.array_equal(np.packbits(aux["mask"].numpy(), axis=-1), g["attn_mask"])
+    assert np.array_equal(aux["positions"].numpy(), g["positions"])
+    # transformer outputs: rows of padded tokens are unconstrained (their queries see nothing)
+    valid = _rows(_t(g["prefix_pad_mask"])[..., None], g)[..., 0]
+    assert rel_err(_rows(aux["prefix_out"], g)[valid], _t(g["prefix_out"])[valid]) < TOL_F32
+    assert rel_err(aux["suffix_out"], g["suffix_out"]) < TOL_F32
+    assert rel_err((aux["v_t"] - (noise - actions)) ** 2, g["mse"]) < TOL_F32
+    obs_s = _oracle_obs(cfg, inp, langact="none")
+    assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=10, bf16=False), g["sampled_actions"]) < TOL_F32
+    assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=3, bf16=False), g["sampled_actions_3"]) < TOL_F32
+    assert rel_err(O.posemb_sincos(_t(g["posemb_t"]), 32, 4e-3, 4.0), g["posemb"]) < TOL_F32
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# oracle vs LAP.compute_loss / sample_actions executed from the reference's source (LAP-specific rows a5, a10, a13, a19)
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(RC.LAP_CASES))
+def test_oracle_matches_reference_lap_source(case):
+    cfg, p, inp, g = _load("lap", case)
+    obs = _oracle_obs(cfg, inp, langact="real")
+    pre_tok, pre_mask, pre_ar = O.embed_prefix(p, cfg, obs, bf16=False)
+    assert rel_err(_rows(pre_tok, g), g["prefix_tokens"]) < TOL_F32
+    assert np.array_equal(pre_mask.numpy(), g["prefix_mask"]) and np.array_equal(pre_ar.numpy(), g["prefix_ar_mask"])
+    loss, m, aux = O.compute_loss(p, cfg, obs, _t(inp["actions"]), _t(inp["noise"]), _t(inp["time"]), bf16=False,
+                                  return_aux=True)
+    assert np.array_equal(np.packbits(aux["mask"].numpy(), axis=-1), g["attn_mask"])
+    assert np.array_equal(aux["positions"].numpy().astype(np.int32), g["positions"])
+    assert abs(float(loss) - float(g["loss"])) < TOL_F32 * abs(float(g["loss"]))
+    for k in ("lang_loss", "langact_loss", "action_loss"):
+        assert abs(float(m[k]) - float(g[k])) < TOL_F32 * abs(float(g[k])), k
+    noise = _t(inp["noise"])
+    a = O.sample_actions(p, cfg, obs, noise, num_steps=10, bf16=False)
+    assert rel_err(a, g["sampled_actions_eval"]) < TOL_F32
+    obs_s = _oracle_obs(cfg, inp, langact="none")
+    assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=10, bf16=False), g["sampled_actions_serve"]) < TOL_F32
+    assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=4, bf16=False), g["sampled_actions_serve_4"]) < TOL_F32
+    assert np.array_equal(O.make_attn_mask(_t(g["kat_input_mask"]), _t(g["kat_ar_mask"])).numpy(), g["kat_attn_mask"])
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# the CUDA engine vs the same reference outputs
+# ----------------------------------------------------------------------------------------------------------------
+def _engine(cfg, p):
+    from lap_b200.model import LAP
+
+    model = LAP(cfg, init=False)
+    model.load_params(p)
+    return model
+
+
+def _engine_batch(cfg, inp, langact):
+    b = dict(image={k: inp["image/" + k] for k in cfg.image_keys},
+             image_mask={k: inp["image_mask/" + k] for k in cfg.image_keys},
+             state=inp["state"], tokenized_prompt=inp["tokenized_prompt"], tokenized_prompt_mask=inp["tokenized_prompt_mask"],
+             token_loss_mask=inp.get("token_loss_mask", np.ones_like(inp["tokenized_prompt_mask"])),
+             sample_mask=inp.get("sample_mask", np.ones((inp["state"].shape[0],), dtype=bool)),
+             actions=inp["actions"], noise=inp["noise"], time=inp["time"])
+    if langact == "zeros":
+        b["tokenized_langact_mask"] = np.zeros_like(inp["tokenized_prompt_mask"])
+    elif langact == "real":
+        b["tokenized_langact_mask"] = inp["tokenized_langact_mask"]
+    return b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(RC.CASES))
+def test_engine_matches_reference_pytorch_port(case):
+    from lap_b200 import ops
+    from lap_b200.observation import Observation
+    from lap_b200.train import batch_from_dict
+
+    cfg, p, inp, g = _load("pi05", case)
+    model = _engine(cfg, p)
+    B = inp["actions"].shape[0]
+    obs, actions, extra = batch_from_dict(_engine_batch(cfg, inp, "zeros"))
+    model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    T = cfg.prefix_len + cfg.action_horizon
+    Tpad = (T + 63) // 64 * 64
+    dense = torch.zeros(B, T, T, dtype=torch.uint8, device="cuda")
+    ops.mask_expand(model._bufs["mask.bits"], dense, B * T, T, Tpad // 32)
+    assert np.array_equal(np.packbits(dense.cpu().numpy().astype(bool), axis=-1), g["attn_mask"])
+    assert np.array_equal(model._bufs["mask.pos"].cpu().numpy(), g["positions"])
+    v = model._bufs["loss.v"].view(B, cfg.action_horizon, -1).float().cpu()
+    u = _t(inp["noise"]) - _t(inp["actions"])
+    assert rel_err(v - u, torch.sign(v - u) * torch.sqrt(_t(g["mse"]))) < 1.5e-2  # bf16 engine vs fp32 reference
+    b2 = _engine_batch(cfg, inp, "none")
+    for steps, key in ((10, "sampled_actions"), (3, "sampled_actions_3")):
+        a = model.sample_actions(0, Observation.from_dict(b2), num_steps=steps, noise=inp["noise"])
+        assert rel_err(a, g[key]) < 1.5e-2, key
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", list(RC.LAP_CASES))
+def test_engine_matches_reference_lap_source(case):
+    from lap_b200 import ops
+    from lap_b200.observation import Observation
+    from lap_b200.train import batch_from_dict
+
+    cfg, p, inp, g = _load("lap", case)
+    model = _engine(cfg, p)
+    B = inp["actions"].shape[0]
+    obs, actions, extra = batch_from_dict(_engine_batch(cfg, inp, "real"))
+    loss, m = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    T = cfg.prefix_len + cfg.action_horizon
+    Tpad = (T + 63) // 64 * 64
+    dense = torch.zeros(B, T, T, dtype=torch.uint8, device="cuda")
+    ops.mask_expand(model._bufs["mask.bits"], dense, B * T, T, Tpad // 32)
+    assert np.array_equal(np.packbits(dense.cpu().numpy().astype(bool), axis=-1), g["attn_mask"])
+    assert np.array_equal(model._bufs["mask.pos"].cpu().numpy(), g["positions"])
+    assert abs(loss.item() - float(g["loss"])) < 3e-3 * abs(float(g["loss"]))
+    for k in ("lang_loss", "langact_loss", "action_loss"):
+        assert abs(m[k].item() - float(g[k])) < 6e-3 * abs(float(g[k])), k
+    a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, "real")), num_steps=10, noise=inp["noise"])
+    assert rel_err(a, g["sampled_actions_eval"]) < 1.5e-2
+    a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, "none")), num_steps=10, noise=inp["noise"])
+    assert rel_err(a, g["sampled_actions_serve"]) < 1.5e-2
