@@ -195,6 +195,44 @@ int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uin
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);
 
+/* K10: the whole flow-matching Euler loop of LAP.sample_actions (lap.py:634-672: embed_suffix pi0.py:139-186, the
+ * action-expert half of gemma.Module gemma.py:455-531 against the prefix KV cache, action_out_proj, x += dt*v) for ONE
+ * sample as ONE persistent cooperative kernel (one CTA per SM, grid barriers between dependent phases, next-phase weights
+ * prefetched into L2 while waiting).  All pointers are device pointers; bf16 tensors are row-major [out, in] weights /
+ * [rows, features] activations; `*_ls` = element stride between consecutive layers.  Scratch buffers are caller-owned. */
+typedef struct {
+  int32_t A, ad, D1, NH, HD, F1, L, Pn, Tpad, TpadK, W32, nm, num_steps; /* TpadK = round_up(Pn, 64) = row length of VcT */
+  float dt, qscale;                  /* Euler step (-1/num_steps), head_dim^-0.5 */
+  float times[16];                   /* t of every step (1, 1+dt, ...) */
+  const void *qkv_w, *o_w, *gu_w, *down_w; /* expert weights, layer 0: [(NH+2)HD, D1] [D1, NH*HD] [2*F1, D1] [D1, F1] */
+  int64_t qkv_ls, o_ls, gu_ls, down_ls;
+  const void* mod_w;                 /* [nm*3*D1, D1] bf16: all adaRMS modulation Dense layers stacked */
+  const float* mod_b;                /* [nm*3*D1] */
+  const float *ain_w, *ain_b, *tin_w, *tin_b, *tout_w, *tout_b, *aout_w, *aout_b; /* fp32 suffix projections */
+  const void* Kc;                    /* [L][Tpad][HD] bf16 prefix keys (post-RoPE) */
+  const void* VcT;                   /* [L][HD][TpadK] bf16 prefix values, transposed (lapb200_transpose_v) */
+  int64_t kc_ls, vct_ls;
+  const uint32_t* bits;              /* [A][W32] packed attention mask of the suffix rows over P+A keys */
+  const int32_t* pos;                /* [A] RoPE positions of the suffix rows */
+  const float* timescale;            /* [HD/2] */
+  float* x;                          /* [A*ad] in: noise, out: actions */
+  float* s1;                         /* scratch [num_steps*D1] */
+  void *cond16, *mod;                /* scratch bf16 [num_steps*D1], [num_steps * nm*3*D1] */
+  void *XE, *XE1, *qkv, *O, *act;    /* scratch bf16 [16*D1] x2, [16*(NH+2)*HD], [16*NH*HD], [16*F1] */
+  float *part_o, *part_ml;           /* scratch [NH*(TpadK/64+1)*16*HD], [NH*(TpadK/64+1)*16*2] */
+  uint32_t* sync;                    /* [2]: barrier counter, error flag (set if a barrier timed out) */
+  unsigned long long* prof;          /* optional [16]: ns per phase slot seen by CTA 0 (0 prologue, 1 action_in, 2/3 P1 work /
+                                        barrier, 4/5 P2, 6/7 P2b, 8/9 P3, 10/11 P4, 12/13 P5, 14 final); NULL = off */
+} lapb_denoise_params_t;
+/* 1 if the shape is supported by the persistent kernel (B == 1, A <= 16, num_steps <= 16, head_dim <= 256 ...). */
+int lapb200_denoise_supported(int64_t B, int64_t A, int64_t ad, int64_t D1, int64_t NH, int64_t HD, int64_t F1,
+                              int64_t Pn, int64_t Tpad, int64_t num_steps);
+int lapb200_denoise_grid(void);
+int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s);
+/* VcT[l][d][j] = Vc[l][j][d] for j < Pn, 0 for Pn <= j < TpadK. */
+int lapb200_transpose_v(const void* Vc, void* VcT, int64_t L, int64_t Tpad, int64_t TpadK, int64_t HD, int64_t Pn,
+                        lapb_stream_t s);
+
 /* buf[dst] = sqrt(buf[src]) on the device (param_norm = sqrt(sum p^2), scripts/train.py:411) */
 int lapb200_sqrt_scalar(float* buf, int64_t src, int64_t dst, lapb_stream_t s);
 

@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "liblapb200.so"
 INCLUDE = Path(__file__).resolve().parent.parent / "include"
-SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "loss.cu", "optimizer.cu", "skinny.cu", "fa_gemma.cu"]
+SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "loss.cu", "optimizer.cu", "skinny.cu", "fa_gemma.cu", "denoise.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -41,7 +41,7 @@ def needs_build() -> bool:
     if not LIB_PATH.exists():
         return True
     t = LIB_PATH.stat().st_mtime
-    deps = [p for p in CSRC.iterdir() if p.suffix in (".cu", ".cuh", ".h")] + list(INCLUDE.glob("*.h"))
+    deps = [p for p in CSRC.iterdir() if p.suffix in (".cu", ".cuh", ".h")] + list(INCLUDE.glob("*.h")) + [Path(__file__)]
     return any(p.stat().st_mtime > t for p in deps)
 
 
@@ -94,6 +94,23 @@ class GemmParams(ctypes.Structure):
         ("gate", c_vp), ("ldg", c_i64), ("gate_rows", c_i32),
         ("C2", c_vp), ("ldc2", c_i64), ("q_cols", c_i32), ("q_div", c_f32),
         ("block_n", c_i32), ("max_ctas", c_i32), ("cta_group", c_i32), ("k_splits", c_i32),
+    ]
+
+
+class DenoiseParams(ctypes.Structure):
+    """lapb_denoise_params_t (include/lapb200.h)."""
+    _fields_ = [
+        *[(n, c_i32) for n in ("A", "ad", "D1", "NH", "HD", "F1", "L", "Pn", "Tpad", "TpadK", "W32", "nm", "num_steps")],
+        ("dt", c_f32), ("qscale", c_f32), ("times", c_f32 * 16),
+        ("qkv_w", c_vp), ("o_w", c_vp), ("gu_w", c_vp), ("down_w", c_vp),
+        ("qkv_ls", c_i64), ("o_ls", c_i64), ("gu_ls", c_i64), ("down_ls", c_i64),
+        ("mod_w", c_vp), ("mod_b", c_vp),
+        *[(n, c_vp) for n in ("ain_w", "ain_b", "tin_w", "tin_b", "tout_w", "tout_b", "aout_w", "aout_b")],
+        ("Kc", c_vp), ("VcT", c_vp), ("kc_ls", c_i64), ("vct_ls", c_i64),
+        ("bits", c_vp), ("pos", c_vp), ("timescale", c_vp), ("x", c_vp), ("s1", c_vp),
+        ("cond16", c_vp), ("mod", c_vp),
+        *[(n, c_vp) for n in ("XE", "XE1", "qkv", "O", "act")],
+        ("part_o", c_vp), ("part_ml", c_vp), ("sync", c_vp), ("prof", c_vp),
     ]
 
 

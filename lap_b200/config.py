@@ -47,6 +47,8 @@ def get_gemma_config(variant: str) -> GemmaConfig:
         return GemmaConfig(width=256, depth=2, mlp_dim=512, num_heads=8, num_kv_heads=1, head_dim=256)
     if variant == "small_300m":
         return GemmaConfig(width=128, depth=2, mlp_dim=256, num_heads=8, num_kv_heads=1, head_dim=256)
+    if variant == "mid_2b":  # depth / head geometry of gemma_2b at a quarter of the width (pairs with the real gemma_300m)
+        return GemmaConfig(width=512, depth=18, mlp_dim=1024, num_heads=8, num_kv_heads=1, head_dim=256)
     # variants of tests/golden/make_reference_golden.py: the reference's JAX->PyTorch converter only handles
     # width == num_heads * head_dim for the PaliGemma tower (convert_jax_model_to_pytorch.py:205-212)
     if variant == "pin_a":

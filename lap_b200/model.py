@@ -92,6 +92,8 @@ class LAP:
         self.R_cap: int | None = None
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
+        self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
+        self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
         self._infer_graphs: dict = {}
         self._infer_warm: dict = {}
         hd = cfg.gemma.head_dim
@@ -886,6 +888,10 @@ class LAP:
         pos_s = self.buf("inf.pos_s", (B, A), torch.int32)
         ops.mask_build(st.pm, st.par, st.pm, st.sm, st.sar, bits_s, pos_s, B, Pn, A, W32, row_begin=Pn, infer_rows=True)
         dt = -1.0 / num_steps
+        if self.use_denoise_megakernel and ops.denoise_supported(B, A, ad, D1, e.num_heads, e.head_dim, e.mlp_dim, Pn, Tpad,
+                                                                 num_steps):
+            self._denoise_loop_fused(x, Kc, Vc, bits_s, pos_s, num_steps, dt)
+            return
         t = 1.0
         tbuf = self.buf("inf.t", (B,), F32)
         XE0 = self.buf("inf.XE0", (B * A, D1))
@@ -907,6 +913,53 @@ class LAP:
             t += dt
             n_iter += 1
         assert n_iter == num_steps
+
+    def _denoise_loop_fused(self, x, Kc, Vc, bits_s, pos_s, num_steps: int, dt: float) -> None:
+        """K10 (csrc/denoise.cu): all Euler steps of lap.py:634-672 for one sample in ONE persistent cooperative kernel.
+        The prefix values are transposed once ([L, hd, keys]) so that P·V reads keys contiguously."""
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        Pn, A, ad, D1, L = cfg.prefix_len, cfg.action_horizon, cfg.action_dim, e.width, g.depth
+        NH, HD, F1 = e.num_heads, e.head_dim, e.mlp_dim
+        Tpad = Kc.shape[2]
+        TpadK = _round_up(Pn, 64)
+        nm = P.n_mod(cfg)
+        VcT = self.buf("inf.VcT", (L, HD, TpadK))
+        ops.transpose_v(Vc, VcT, L, Tpad, TpadK, HD, Pn)
+        nch = TpadK // 64 + 1
+        times, t = [], 1.0
+        while t >= -dt / 2:  # lap.py:669-672
+            times.append(t)
+            t += dt
+        assert len(times) == num_steps
+        S = num_steps
+        ptrs = dict(
+            qkv_w=self.w("e.qkv_w", 0), o_w=self.w("e.o_w", 0), gu_w=self.w("e.gu_w", 0), down_w=self.w("e.down_w", 0),
+            mod_w=self.w("e.mod_w"), mod_b=self.p("e.mod_b"),
+            ain_w=self.p("action_in_w"), ain_b=self.p("action_in_b"), tin_w=self.p("time_in_w"), tin_b=self.p("time_in_b"),
+            tout_w=self.p("time_out_w"), tout_b=self.p("time_out_b"), aout_w=self.p("action_out_w"),
+            aout_b=self.p("action_out_b"), Kc=Kc, VcT=VcT, bits=bits_s, pos=pos_s, timescale=self.timescale, x=x,
+            s1=self.buf("dn.s1", (S, D1), F32), cond16=self.buf("dn.cond16", (S, D1)),
+            mod=self.buf("dn.mod", (S, nm * 3 * D1)), XE=self.buf("dn.XE", (16, D1)), XE1=self.buf("dn.XE1", (16, D1)),
+            qkv=self.buf("dn.qkv", (16, (NH + 2) * HD)), O=self.buf("dn.O", (16, NH * HD)), act=self.buf("dn.act", (16, F1)),
+            part_o=self.buf("dn.part_o", (NH * nch, 16, HD), F32), part_ml=self.buf("dn.part_ml", (NH * nch, 16, 2), F32),
+            sync=self.buf("dn.sync", (2,), torch.int32, zero=True))
+        if self.denoise_profile:
+            ptrs["prof"] = self.buf("dn.prof", (16,), torch.int64, zero=True)
+
+        def lstride(name):
+            return self.w(name, 1).data_ptr() - self.w(name, 0).data_ptr() >> 1 if L > 1 else 0
+
+        ops.denoise_loop(
+            ints=dict(A=A, ad=ad, D1=D1, NH=NH, HD=HD, F1=F1, L=L, Pn=Pn, Tpad=Tpad, TpadK=TpadK, W32=Tpad // 32, nm=nm,
+                      num_steps=S),
+            dt=dt, qscale=HD ** -0.5, times=times, ptrs=ptrs,
+            strides=dict(qkv_ls=lstride("e.qkv_w"), o_ls=lstride("e.o_w"), gu_ls=lstride("e.gu_w"),
+                         down_ls=lstride("e.down_w"), kc_ls=Tpad * HD, vct_ls=HD * TpadK))
+
+    def denoise_error_flag(self) -> int:
+        """1 if a grid barrier of the last fused denoise loop timed out (never expected; checked by the tests)."""
+        b = self._bufs.get("dn.sync")
+        return int(b[1].item()) if b is not None else 0
 
     def _gemma_prefix_only(self, B, X0, bits, positions, cache):
         """Prefix-only pass (lap.py:627): expert 0 alone, K/V (post-RoPE) written into the cache."""

@@ -356,5 +356,32 @@ def linear_f32(X, W, Y, M, N, K, bias=None):
         sgemm(X, W, Y, M, N, K, K, 1, K, 1, ldc=N, bias=bias)
 
 
+def denoise_supported(B, A, ad, D1, NH, HD, F1, Pn, Tpad, num_steps) -> bool:
+    return bool(lib().lapb200_denoise_supported(*(ctypes.c_int64(int(v)) for v in (B, A, ad, D1, NH, HD, F1, Pn, Tpad,
+                                                                                  num_steps))))
+
+
+def transpose_v(Vc, VcT, L, Tpad, TpadK, HD, Pn):
+    call("transpose_v", Vc, VcT, L, Tpad, TpadK, HD, Pn)
+
+
+def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, strides: dict) -> None:
+    """K10: every Euler step of sample_actions in one persistent cooperative kernel (csrc/denoise.cu)."""
+    p = _lib.DenoiseParams()
+    for k, v in ints.items():
+        setattr(p, k, int(v))
+    p.dt, p.qscale = float(dt), float(qscale)
+    for i, t in enumerate(times):
+        p.times[i] = float(t)
+    for k, v in ptrs.items():
+        if not v.is_cuda:
+            raise RuntimeError("lap_b200 ops require CUDA tensors (there is no CPU fallback)")
+        setattr(p, k, v.data_ptr())
+    for k, v in strides.items():
+        setattr(p, k, int(v))
+    check(lib().lapb200_denoise_loop(ctypes.byref(p), _stream()), "denoise_loop")
+    _count()
+
+
 def fa_gemma_fwd(Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim):
     call("fa_gemma_fwd", Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim)

@@ -189,6 +189,52 @@ def test_batch1_sampling_uses_streaming_kernels_and_matches_oracle():
     assert torch.equal(a1, a2) and torch.equal(a2, a3)
 
 
+@pytest.mark.parametrize("which", ["debug_small", "expert_full_size"])
+def test_fused_denoise_loop_matches_per_op_path(which):
+    """K10: the persistent Euler-loop kernel (csrc/denoise.cu) against the kernel-per-op path it replaces, on the same
+    prefix cache.  Differences: summation order and the bf16 rounding grid of the attention probabilities."""
+    from lap_b200.config import LAPConfig
+    from lap_b200.model import LAP
+    from lap_b200.observation import Observation
+    if which == "debug_small":
+        cfg = get_config("debug_small").model
+    else:  # the real action expert (gemma_300m: 18 x [1024 / 4096 / 8 x 256]) and the real prefix length (692 keys)
+        cfg = LAPConfig(paligemma_variant="mid_2b", action_expert_variant="gemma_300m", siglip_variant="tiny72/14",
+                        action_dim=7, action_horizon=10, max_token_len=180, enable_action_training=True,
+                        enable_image_augmentation=False, vocab_size=4096)
+    ref = P.init_reference_params(cfg, 3, reference_zero_init=False)
+    model = LAP(cfg, init=False)
+    model.load_params(ref)
+    b = synthetic_batch(cfg, 1, step=5, with_langact=False)
+    obs = Observation.from_dict(b)
+    model.use_cuda_graph = False
+    model.use_denoise_megakernel = False
+    n0 = ops.launch_count
+    a_ref = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+    n_per_op = ops.launch_count - n0
+    model.use_denoise_megakernel = True
+    n0 = ops.launch_count
+    a_fused = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+    n_fused = ops.launch_count - n0
+    assert model.denoise_error_flag() == 0
+    assert torch.isfinite(a_fused).all()
+    assert rel_err(a_fused, a_ref) < TOL_ACT, rel_err(a_fused, a_ref)
+    assert n_fused < n_per_op - 100 * cfg.gemma.depth // 2  # ~150 launches per step collapse into one
+    for steps in (1, 4, 16):
+        model.use_denoise_megakernel = False
+        r = model.sample_actions(0, obs, num_steps=steps, noise=b["noise"])
+        model.use_denoise_megakernel = True
+        f = model.sample_actions(0, obs, num_steps=steps, noise=b["noise"])
+        assert rel_err(f, r) < TOL_ACT, (steps, rel_err(f, r))
+    # CUDA-graph capture of the cooperative launch, and determinism
+    model.use_cuda_graph = True
+    g1 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+    g2 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+    g3 = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
+    assert torch.equal(g1, a_fused) and torch.equal(g2, g1) and torch.equal(g3, g1)
+    assert model.denoise_error_flag() == 0
+
+
 def _grad_check(tc, ref, model, b, tol=TOL_GRAD):
     from lap_b200.train import batch_from_dict, init_train_state
     obs, actions, extra = batch_from_dict(b)
