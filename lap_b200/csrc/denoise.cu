@@ -86,7 +86,7 @@ struct GridBarrier {
     if (threadIdx.x == 0) {
       target += nblocks;
       __threadfence();
-      atomicAdd(counter, 1u);
+      asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
       unsigned v, spins = 0;
       do {
         asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
@@ -99,7 +99,6 @@ struct GridBarrier {
           }
         }
       } while (v < target);
-      __threadfence();
     }
     __syncthreads();
   }
@@ -111,11 +110,39 @@ __device__ __forceinline__ void dn_range(int n, int& begin, int& end) {
   end = (int)(((long)(blockIdx.x + 1) * n) / gridDim.x);
 }
 
-// One pass of the skinny product for up to NT n8 weight tiles: red[warp][tile][lane][4] <- partial sums of
-// X[16 x K] * W_tile[8 x K]^T over this warp's K groups.  wt[i] = first row of tile i (nullptr = no tile).
-template <int NT, bool A_SMEM>
-__device__ __forceinline__ void dn_mma_pass(const bf16* X, long ldx, int M, int K, const bf16* const (&wt)[NT], long ldw,
-                                            float* red) {
+// cp.async (LDGSTS, L2-only) staging of activations written by other CTAs: any number in flight, no registers held
+__device__ __forceinline__ void dn_cp16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void dn_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// rows x cols bf16 (cols % 8 == 0) from global (row stride lds) to shared (row stride ldd); caller waits + syncs
+__device__ __forceinline__ void dn_stage(const bf16* src, long lds, bf16* dst, int ldd, int rows, int cols) {
+  const int nvec = cols >> 3;
+  for (int i = threadIdx.x; i < rows * nvec; i += DN_THREADS) {
+    const int r = i / nvec, c = (i % nvec) * 8;
+    dn_cp16(dst + (long)r * ldd + c, src + (long)r * lds + c);
+  }
+}
+
+// Weight fragments of up to NT n8 tiles for this warp's K groups kg0 + 8u (u < U): issued early (before the grid
+// barrier of the previous phase) so that their DRAM/L2 latency overlaps the barrier.  wt[i] = first row of tile i.
+template <int NT, int U>
+__device__ __forceinline__ void dn_load_w(uint4 (&b)[U][NT], const bf16* const (&wt)[NT], long ldw, int ngroups, int kg0) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int kg = kg0 + 8 * u;
+#pragma unroll
+    for (int i = 0; i < NT; ++i)
+      b[u][i] = (wt[i] != nullptr && kg < ngroups) ? dn_ld_stream(wt[i] + (long)g * ldw + 8 * t + kg * 32)
+                                                  : make_uint4(0, 0, 0, 0);
+  }
+}
+// One pass of the skinny product: red[warp][tile][lane][4] <- partial sums of As[M x K] * W_tile[8 x K]^T over this warp's
+// K groups.  As is in shared memory; b holds the fragments of the first K iteration (dn_load_w(..., kg0 = warp)).
+template <int NT, int U>
+__device__ __forceinline__ void dn_mma_pass(const bf16* As, int lda, int M, int K, const bf16* const (&wt)[NT], long ldw,
+                                            uint4 (&b)[U][NT], float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float acc[NT][4];
@@ -123,40 +150,23 @@ __device__ __forceinline__ void dn_mma_pass(const bf16* X, long ldx, int M, int 
   for (int i = 0; i < NT; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const bf16* xlo = X + (long)g * ldx + 8 * t;
-  const bf16* xhi = X + (long)(g + 8) * ldx + 8 * t;
+  const bf16* xlo = As + (long)g * lda + 8 * t;
+  const bf16* xhi = As + (long)(g + 8) * lda + 8 * t;
   const bool vlo = g < M, vhi = (g + 8) < M;
-  const bf16* wr[NT];
-#pragma unroll
-  for (int i = 0; i < NT; ++i) wr[i] = wt[i] ? wt[i] + (long)g * ldw + 8 * t : nullptr;
   const int ngroups = K >> 5;
-  constexpr int U = 4;
   const uint4 zero = make_uint4(0, 0, 0, 0);
   for (int kg0 = warp; kg0 < ngroups; kg0 += 8 * U) {
-    uint4 b[U][NT], alo[U], ahi[U];
+    if (kg0 != warp) dn_load_w<NT, U>(b, wt, ldw, ngroups, kg0);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int kg = kg0 + 8 * u;
       if (kg < ngroups) {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) b[u][i] = wr[i] ? dn_ld_stream(wr[i] + kg * 32) : zero;
-        if (A_SMEM) {
-          alo[u] = vlo ? *reinterpret_cast<const uint4*>(xlo + kg * 32) : zero;
-          ahi[u] = vhi ? *reinterpret_cast<const uint4*>(xhi + kg * 32) : zero;
-        } else {
-          alo[u] = vlo ? dn_ldcg(xlo + kg * 32) : zero;
-          ahi[u] = vhi ? dn_ldcg(xhi + kg * 32) : zero;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int kg = kg0 + 8 * u;
-      if (kg < ngroups) {
+        const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(xlo + kg * 32) : zero;
+        const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(xhi + kg * 32) : zero;
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
-          dn_mma(acc[i], alo[u].x, ahi[u].x, alo[u].y, ahi[u].y, b[u][i].x, b[u][i].y);
-          dn_mma(acc[i], alo[u].z, ahi[u].z, alo[u].w, ahi[u].w, b[u][i].z, b[u][i].w);
+          dn_mma(acc[i], alo.x, ahi.x, alo.y, ahi.y, b[u][i].x, b[u][i].y);
+          dn_mma(acc[i], alo.z, ahi.z, alo.w, ahi.w, b[u][i].z, b[u][i].w);
         }
       }
     }
@@ -177,14 +187,11 @@ __device__ __forceinline__ float dn_tile_val(const float* red, int tile, int m, 
   return s;
 }
 
-// adaptive RMSNorm of the rows in xe_s (gemma.py:112-131 with cond): h = bf16( x*rstd * bf16(1+scale) + shift ); warp per row.
+// adaptive RMSNorm of rows [0, A) of xe_s (gemma.py:112-131 with cond): h = bf16( x*rstd * bf16(1+scale) + shift ); warp
+// per row; scale/shift come from shared memory (mod_row = [scale | shift | gate], staged with the rows).
 __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh, int A, int D1, const bf16* mod_row) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int m = warp; m < 16; m += 8) {
-    if (m >= A) {
-      for (int c = lane * 8; c < D1; c += 256) *reinterpret_cast<uint4*>(h_s + (long)m * ldh + c) = make_uint4(0, 0, 0, 0);
-      continue;
-    }
+  for (int m = warp; m < A; m += 8) {
     float s2 = 0.f;
     for (int c = lane * 8; c < D1; c += 256) {
       float v[8];
@@ -197,8 +204,8 @@ __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh
     for (int c = lane * 8; c < D1; c += 256) {
       float v[8], sc[8], sh[8], o[8];
       dn_unpack8(*reinterpret_cast<const uint4*>(xe_s + (long)m * D1 + c), v);
-      dn_unpack8(dn_ldcg(mod_row + c), sc);
-      dn_unpack8(dn_ldcg(mod_row + D1 + c), sh);
+      dn_unpack8(*reinterpret_cast<const uint4*>(mod_row + c), sc);
+      dn_unpack8(*reinterpret_cast<const uint4*>(mod_row + D1 + c), sh);
 #pragma unroll
       for (int j = 0; j < 8; ++j) o[j] = (v[j] * rstd) * bf16r(1.0f + sc[j]) + sh[j];
       *reinterpret_cast<uint4*>(h_s + (long)m * ldh + c) = dn_pack8(o);
@@ -206,18 +213,9 @@ __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh
   }
 }
 
-// copy [A x D1] bf16 rows from global (written by other CTAs: L2 loads) into shared memory, zero rows >= A
-__device__ __forceinline__ void dn_load_rows(const bf16* src, bf16* dst, int A, int D1) {
-  const int nvec = D1 >> 3;
-  for (int i = threadIdx.x; i < 16 * nvec; i += DN_THREADS) {
-    const int m = i / nvec, c = (i % nvec) * 8;
-    *reinterpret_cast<uint4*>(dst + (long)m * D1 + c) = (m < A) ? dn_ldcg(src + (long)m * D1 + c) : make_uint4(0, 0, 0, 0);
-  }
-}
-
 // fp32 GEMV block used by the time MLP: out[r, n] = swish( sum_k W[n,k] * in_s[r,k] + bias[n] ), warp per column
-__device__ __forceinline__ void dn_time_mlp(const float* in_s, int R, int D1, const float* W, const float* bias, float* out_f32,
-                                            bf16* out_bf16) {
+__device__ __noinline__ void dn_time_mlp(const float* in_s, int R, int D1, const float* W, const float* bias, float* out_f32,
+                                         bf16* out_bf16) {
   const int lane = threadIdx.x & 31;
   const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
   for (int n = gw; n < D1; n += nw) {
@@ -245,31 +243,50 @@ __device__ __forceinline__ void dn_time_mlp(const float* in_s, int R, int D1, co
   }
 }
 
-// bytes of the region that holds h_s and, between P1 and P4, the attention scratch
-__host__ __device__ inline size_t dn_hreg_bytes(int D1, int HD) {
-  const size_t h = (size_t)16 * (D1 + 8) * 2;
-  const size_t attn = (size_t)16 * (HD + 8) * 2 + (size_t)16 * DN_CK * 4 + (size_t)16 * (DN_CK + 8) * 2 + (size_t)16 * HD * 4;
-  return ((h > attn ? h : attn) + 15) & ~(size_t)15;
+// ---- shared-memory carve-up (bytes), shared by the kernel and the host launcher ----
+__host__ __device__ inline size_t dn_align16(size_t x) { return (x + 15) & ~(size_t)15; }
+__host__ __device__ inline size_t dn_attn_bytes(int HD) {
+  return (size_t)16 * (HD + 8) * 2      /* q_s  */ + (size_t)16 * DN_CK * 4 /* s_s */ + (size_t)16 * (DN_CK + 8) * 2 /* p_s */ +
+         (size_t)16 * HD * 4            /* ks_s */ + (size_t)3 * 16 * HD * 2 /* raw q, k, v rows */;
+}
+// region holding, in turn: normalised rows h (P1, P4, final), attention scratch (P2), staged O (P3), staged act (P5)
+__host__ __device__ inline size_t dn_big_bytes(int D1, int HD, int OD, int F1) {
+  size_t b = (size_t)16 * (D1 + 8) * 2;
+  const size_t a = dn_attn_bytes(HD), o = (size_t)16 * (OD + 8) * 2, f = (size_t)16 * (F1 + 8) * 2;
+  b = b > a ? b : a;
+  b = b > o ? b : o;
+  b = b > f ? b : f;
+  return dn_align16(b);
+}
+__host__ __device__ inline size_t dn_smem_bytes(int D1, int HD, int OD, int F1) {
+  // xe_s | big | red | x_s | rope table | mod rows (attn + ffn) | mask bits     (prologue fp32 [16][D1] aliases xe_s + big)
+  return (size_t)16 * D1 * 2 + dn_big_bytes(D1, HD, OD, F1) + (size_t)8 * 4 * 32 * 4 * 4 + (size_t)16 * 32 * 4 +
+         (size_t)16 * (HD / 2) * 8 + (size_t)6 * D1 * 2 + (size_t)16 * 32 * 4 + 16;
 }
 
 __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_denoise_params_t p) {
   extern __shared__ __align__(16) unsigned char dn_smem[];
-  const int A = p.A, ad = p.ad, D1 = p.D1, NH = p.NH, HD = p.HD, F1 = p.F1, L = p.L, Pn = p.Pn;
+  const int A = p.A, ad = p.ad, D1 = p.D1, NH = p.NH, HD = p.HD, F1 = p.F1, L = p.L, Pn = p.Pn, W32 = p.W32;
   const int QKV = (NH + 2) * HD, OD = NH * HD, nm3 = p.nm * 3 * D1, S = p.num_steps;
-  const int ldh = D1 + 8;
-  // ---- shared memory carve-up ----
-  bf16* xe_s = reinterpret_cast<bf16*>(dn_smem);                          // [16][D1]   residual stream copy
-  bf16* h_s = xe_s + 16 * D1;                                              // [16][D1+8] normalised rows (A operand)
-  float* red = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(h_s) + dn_hreg_bytes(D1, HD));  // [8][4][32][4]
-  float* x_s = red + 8 * 4 * 32 * 4;                                       // [16*32]    x_t
-  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);               // [16][HD/2] (cos, sin) of the suffix positions
-  float* te_s = reinterpret_cast<float*>(dn_smem);                         // prologue only: [16][D1] fp32 (aliases xe_s+h_s)
-  // attention scratch aliases h_s (dead between P1 and P4)
-  bf16* q_s = h_s;                                                         // [16][HD+8]
-  float* s_s = reinterpret_cast<float*>(q_s + 16 * (HD + 8));              // [16][64]
-  bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * DN_CK);                   // [16][72]
-  float* ks_s = reinterpret_cast<float*>(p_s + 16 * (DN_CK + 8));          // [16][HD]
-  const int ldq = HD + 8, ldp = DN_CK + 8;
+  const int ldh = D1 + 8, ldo = OD + 8, ldf = F1 + 8, ldq = HD + 8, ldp = DN_CK + 8, half = HD / 2;
+  // ---- shared memory ----
+  bf16* xe_s = reinterpret_cast<bf16*>(dn_smem);                                     // [16][D1] residual stream copy
+  unsigned char* big = dn_smem + (size_t)16 * D1 * 2;
+  bf16* h_s = reinterpret_cast<bf16*>(big);                                           // [16][D1+8] / staged O / staged act
+  float* red = reinterpret_cast<float*>(big + dn_big_bytes(D1, HD, OD, F1));          // [8][4][32][4]
+  float* x_s = red + 8 * 4 * 32 * 4;                                                  // [16*32] x_t
+  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);                          // [16][HD/2] (cos, sin)
+  bf16* mod_sm = reinterpret_cast<bf16*>(rope_s + 16 * half);                         // [2][3*D1]: attn-norm, ffn-norm rows
+  uint32_t* bits_s = reinterpret_cast<uint32_t*>(mod_sm + 6 * D1);                    // [16][32]
+  float* te_s = reinterpret_cast<float*>(dn_smem);                                    // prologue only
+  // attention scratch (inside `big`)
+  bf16* q_s = reinterpret_cast<bf16*>(big);                                           // [16][HD+8]
+  float* s_s = reinterpret_cast<float*>(q_s + 16 * ldq);                              // [16][64]
+  bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * DN_CK);                              // [16][72]
+  float* ks_s = reinterpret_cast<float*>(p_s + 16 * ldp);                             // [16][HD]
+  bf16* qraw = reinterpret_cast<bf16*>(ks_s + 16 * HD);                               // [16][HD] x3
+  bf16* kraw = qraw + 16 * HD;
+  bf16* vraw = kraw + 16 * HD;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
@@ -293,20 +310,39 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   bf16* Obuf = reinterpret_cast<bf16*>(p.O);
   bf16* act = reinterpret_cast<bf16*>(p.act);
   const int NCHP = (Pn + DN_CK - 1) / DN_CK, NCH = NCHP + 1;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+
+  // this CTA's share of every phase (contiguous n8 tiles / GeGLU pairs / attention item)
+  int q_tb, q_te, o_tb, o_te, f_pb, f_pe;
+  dn_range(QKV / 8, q_tb, q_te);
+  dn_range(D1 / 8, o_tb, o_te);
+  dn_range(F1 / 8, f_pb, f_pe);
+  auto qkv_tiles = [&](const bf16* W, int t0, const bf16* (&wt)[4]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) wt[i] = (t0 + i < q_te) ? W + (long)(t0 + i) * 8 * D1 : nullptr;
+  };
+  auto gu_tiles = [&](const bf16* W, int p0, const bf16* (&wt)[4]) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = p0 + i < f_pe;
+      wt[2 * i] = ok ? W + (long)(p0 + i) * 8 * D1 : nullptr;
+      wt[2 * i + 1] = ok ? W + ((long)F1 + (long)(p0 + i) * 8) * D1 : nullptr;
+    }
+  };
 
   // =========================== prologue: time conditioning of every step ===========================
   {
     // T1: time_emb (pi0.py:47-63) for all steps, then s1 = swish(time_mlp_in(time_emb))
-    const int half = D1 / 2;
-    for (int i = threadIdx.x; i < S * half; i += DN_THREADS) {
-      const int r = i / half, c = i % half;
-      const float fraction = (half > 1) ? (float)c / (float)(half - 1) : 0.f;
+    const int halfw = D1 / 2;
+    for (int i = threadIdx.x; i < S * halfw; i += DN_THREADS) {
+      const int r = i / halfw, c = i % halfw;
+      const float fraction = (halfw > 1) ? (float)c / (float)(halfw - 1) : 0.f;
       const float period = 4e-3f * powf(4.0f / 4e-3f, fraction);
       const float inp = p.times[r] * (1.0f / period * 2.0f * 3.14159265358979323846f);
       float sn, cs;
       sincosf(inp, &sn, &cs);
       te_s[r * D1 + c] = sn;
-      te_s[r * D1 + half + c] = cs;
+      te_s[r * D1 + halfw + c] = cs;
     }
     __syncthreads();
     dn_time_mlp(te_s, S, D1, p.tin_w, p.tin_b, p.s1, nullptr);
@@ -317,20 +353,25 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
     dn_time_mlp(te_s, S, D1, p.tout_w, p.tout_b, nullptr, reinterpret_cast<bf16*>(p.cond16));
     bar.sync();
     // T3: mod = cond16 @ mod_w^T + mod_b  (rows = steps)
-    for (int i = threadIdx.x; i < 16 * (D1 >> 3); i += DN_THREADS) {
-      const int m = i / (D1 >> 3), c = (i % (D1 >> 3)) * 8;
-      *reinterpret_cast<uint4*>(h_s + (long)m * ldh + c) =
-          (m < S) ? dn_ldcg(reinterpret_cast<const bf16*>(p.cond16) + (long)m * D1 + c) : make_uint4(0, 0, 0, 0);
-    }
-    __syncthreads();
+    dn_stage(reinterpret_cast<const bf16*>(p.cond16), D1, h_s, ldh, S, D1);
     int tb, te;
     dn_range(nm3 / 8, tb, te);
     const bf16* mw = reinterpret_cast<const bf16*>(p.mod_w);
-    for (int t0 = tb; t0 < te; t0 += 4) {
-      const bf16* wt[4];
+    auto mod_tiles = [&](int t0, const bf16* (&wt)[4]) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) wt[i] = (t0 + i < te) ? mw + (long)(t0 + i) * 8 * D1 : nullptr;
-      dn_mma_pass<4, true>(h_s, ldh, S, D1, wt, D1, red);
+    };
+    uint4 b[4][4];
+    const bf16* wt[4];
+    mod_tiles(tb, wt);
+    dn_load_w<4, 4>(b, wt, D1, D1 >> 5, warp);
+    dn_cp_wait_all();
+    __syncthreads();
+    for (int t0 = tb; t0 < te; t0 += 4) {
+      dn_mma_pass<4, 4>(h_s, ldh, S, D1, wt, D1, b, red);
+      const bf16* wn[4];
+      mod_tiles(t0 + 4, wn);
+      if (t0 + 4 < te) dn_load_w<4, 4>(b, wn, D1, D1 >> 5, warp);  // next pass's weights fly during this epilogue
       for (int e = threadIdx.x; e < 16 * 32; e += DN_THREADS) {
         const int m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
         if (m < S && t0 + tile < te) {
@@ -340,32 +381,37 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
         }
       }
       __syncthreads();
+#pragma unroll
+      for (int i = 0; i < 4; ++i) wt[i] = wn[i];
     }
-    // x_t <- noise; (cos, sin) of the suffix positions (constant over steps and layers)
+    // x_t <- noise; (cos, sin) of the suffix positions and the mask words (constant over steps and layers)
     for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) x_s[i] = p.x[i];
-    for (int i = threadIdx.x; i < A * (HD / 2); i += DN_THREADS) {
-      const int m = i / (HD / 2), d = i % (HD / 2);
+    for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+      const int m = i / half, d = i % half;
       float sn, cs;
       sincosf((float)p.pos[m] / p.timescale[d], &sn, &cs);
       rope_s[i] = make_float2(cs, sn);
     }
+    for (int i = threadIdx.x; i < A * W32; i += DN_THREADS) bits_s[(i / W32) * 32 + (i % W32)] = p.bits[i];
     bar.sync();
     tick(0);
   }
+
+  // weights of the first P1 (layer 0): in flight while action_in_proj is computed
+  uint4 w1[4][4];
+  const bf16* wt1[4];
+  qkv_tiles(reinterpret_cast<const bf16*>(p.qkv_w), q_tb, wt1);
+  dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
 
   // =========================== Euler loop ===========================
   for (int step = 0; step < S; ++step) {
     const bf16* mod_s = mod + (long)step * nm3;
     // XE = bf16(action_in_proj(x_t)) (pi0.py:159), every CTA holds the full copy
-    __syncthreads();
-    for (int i = threadIdx.x; i < 16 * D1; i += DN_THREADS) {
+    for (int i = threadIdx.x; i < A * D1; i += DN_THREADS) {
       const int m = i / D1, n = i % D1;
       float v = 0.f;
-      if (m < A) {
-        for (int j = 0; j < ad; ++j) v += x_s[m * ad + j] * p.ain_w[(long)n * ad + j];
-        v += p.ain_b[n];
-      }
-      xe_s[i] = __float2bfloat16_rn(v);
+      for (int j = 0; j < ad; ++j) v += x_s[m * ad + j] * __ldg(p.ain_w + (long)n * ad + j);
+      xe_s[i] = __float2bfloat16_rn(v + __ldg(p.ain_b + n));
     }
     __syncthreads();
     tick(1);
@@ -377,36 +423,50 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       const bf16* Wd = reinterpret_cast<const bf16*>(p.down_w) + (long)l * p.down_ls;
       const bf16* Kc = reinterpret_cast<const bf16*>(p.Kc) + (long)l * p.kc_ls;
       const bf16* VcT = reinterpret_cast<const bf16*>(p.VcT) + (long)l * p.vct_ls;
-      const bf16* mod_a = mod_s + (long)(2 * l) * 3 * D1;
-      const bf16* mod_f = mod_s + (long)(2 * l + 1) * 3 * D1;
+      const bf16* mod_a = mod_sm;           // [scale | shift | gate] of the attention norm
+      const bf16* mod_f = mod_sm + 3 * D1;  // ... of the ffn norm
 
       // ---------------- P1: h = adaRMS(XE); qkv = h Wqkv^T ----------------
-      if (l > 0) {
-        dn_load_rows(XE, xe_s, A, D1);
-        __syncthreads();
-      }
+      if (l > 0) dn_stage(XE, D1, xe_s, D1, A, D1);
+      dn_stage(mod_s + (long)(2 * l) * 3 * D1, 0, mod_sm, 0, 1, 6 * D1);
+      dn_cp_wait_all();
+      __syncthreads();
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_a);
       __syncthreads();
-      {
-        int tb, te;
-        dn_range(QKV / 8, tb, te);
-        for (int t0 = tb; t0 < te; t0 += 4) {
-          const bf16* wt[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) wt[i] = (t0 + i < te) ? Wqkv + (long)(t0 + i) * 8 * D1 : nullptr;
-          dn_mma_pass<4, true>(h_s, ldh, A, D1, wt, D1, red);
-          for (int e = threadIdx.x; e < 16 * 32; e += DN_THREADS) {
-            const int m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
-            if (m < A && t0 + tile < te)
-              qkv[(long)m * QKV + (t0 + tile) * 8 + cc] = __float2bfloat16_rn(dn_tile_val<4>(red, tile, m, cc));
-          }
-          __syncthreads();
+      for (int t0 = q_tb; t0 < q_te; t0 += 4) {
+        dn_mma_pass<4, 4>(h_s, ldh, A, D1, wt1, D1, w1, red);
+        const bf16* wn[4];
+        qkv_tiles(Wqkv, t0 + 4, wn);
+        if (t0 + 4 < q_te) dn_load_w<4, 4>(w1, wn, D1, D1 >> 5, warp);
+        for (int e = threadIdx.x; e < 16 * 32; e += DN_THREADS) {
+          const int m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
+          if (m < A && t0 + tile < q_te)
+            qkv[(long)m * QKV + (t0 + tile) * 8 + cc] = __float2bfloat16_rn(dn_tile_val<4>(red, tile, m, cc));
         }
-        // next weights this CTA will stream: its o-proj tile(s)
-        int ob, oe;
-        dn_range(D1 / 8, ob, oe);
-        if (oe > ob) dn_prefetch_l2(Wo + (long)ob * 8 * OD, (long)(oe - ob) * 8 * OD * 2);
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) wt1[i] = wn[i];
       }
+      // this CTA's attention item: K / V^T fragments of its key chunk do not depend on this step -> load them now
+      const int item0 = blockIdx.x;
+      const bool item0_prefix = item0 < NH * NCH && (item0 % NCH) < NCHP;
+      uint4 kf[8], vf[4][2];
+      if (item0_prefix) {
+        const int key0 = (item0 % NCH) * DN_CK;
+        const bf16* kr = Kc + (long)(key0 + 8 * warp + g) * HD + 8 * t4;
+#pragma unroll
+        for (int kg = 0; kg < 8; ++kg) kf[kg] = (kg < HD / 32) ? *reinterpret_cast<const uint4*>(kr + kg * 32) : zero4;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int n0 = warp + 8 * i;
+#pragma unroll
+          for (int kg = 0; kg < 2; ++kg)
+            vf[i][kg] = (n0 < HD / 8)
+                            ? *reinterpret_cast<const uint4*>(VcT + (long)(n0 * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32)
+                            : zero4;
+        }
+      }
+      if (o_te > o_tb) dn_prefetch_l2(Wo + (long)o_tb * 8 * OD, (long)(o_te - o_tb) * 8 * OD * 2);
       tick(2);
       bar.sync();
       tick(3);
@@ -414,50 +474,65 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       // ---------------- P2: attention partials, item = (head, key chunk) ----------------
       for (int item = blockIdx.x; item < NH * NCH; item += gridDim.x) {
         const int h = item / NCH, c = item % NCH;
+        const bool prefix = c < NCHP;
         __syncthreads();
-        // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ), rows >= A zero (gemma.py:215-218, 548-564)
-        const int half = HD / 2;
-        for (int i = threadIdx.x; i < 16 * half; i += DN_THREADS) {
-          const int m = i / half, d = i % half;
-          float o1 = 0.f, o2 = 0.f;
-          if (m < A) {
-            const float x1 = __bfloat162float(__ldcg(qkv + (long)m * QKV + h * HD + d));
-            const float x2 = __bfloat162float(__ldcg(qkv + (long)m * QKV + h * HD + half + d));
-            const float cs = rope_s[m * half + d].x, sn = rope_s[m * half + d].y;
-            o1 = bf16r(x1 * cs - x2 * sn) * p.qscale;
-            o2 = bf16r(x2 * cs + x1 * sn) * p.qscale;
-          }
-          q_s[m * ldq + d] = __float2bfloat16_rn(o1);
-          q_s[m * ldq + half + d] = __float2bfloat16_rn(o2);
+        dn_stage(qkv + h * HD, QKV, qraw, HD, A, HD);
+        if (!prefix) {
+          dn_stage(qkv + NH * HD, QKV, kraw, HD, A, HD);
+          dn_stage(qkv + (NH + 1) * HD, QKV, vraw, HD, A, HD);
         }
+        dn_cp_wait_all();
+        __syncthreads();
+        // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ) (gemma.py:215-218, 548-564); suffix item: ks_s <- bf16(rope(k))
+        for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+          const int m = i / half, d = i % half;
+          const float cs = rope_s[i].x, sn = rope_s[i].y;
+          const float x1 = __bfloat162float(qraw[m * HD + d]), x2 = __bfloat162float(qraw[m * HD + half + d]);
+          q_s[m * ldq + d] = __float2bfloat16_rn(bf16r(x1 * cs - x2 * sn) * p.qscale);
+          q_s[m * ldq + half + d] = __float2bfloat16_rn(bf16r(x2 * cs + x1 * sn) * p.qscale);
+          if (!prefix) {
+            const float k1 = __bfloat162float(kraw[m * HD + d]), k2 = __bfloat162float(kraw[m * HD + half + d]);
+            ks_s[m * HD + d] = bf16r(k1 * cs - k2 * sn);
+            ks_s[m * HD + half + d] = bf16r(k2 * cs + k1 * sn);
+          }
+        }
+        __syncthreads();
         float* po = p.part_o + (long)item * 16 * HD;
         float* pml = p.part_ml + (long)item * 16 * 2;
-        if (c < NCHP) {
+        if (prefix) {
           // ---- prefix chunk: keys [key0, key0 + 64) of the cache, tensor cores ----
           const int key0 = c * DN_CK;
-          for (int i = threadIdx.x; i < 16 * ldp; i += DN_THREADS) p_s[i] = __float2bfloat16_rn(0.f);
-          __syncthreads();
+          if (item != item0) {  // (only when there are more items than CTAs) fragments were not preloaded
+            const bf16* kr = Kc + (long)(key0 + 8 * warp + g) * HD + 8 * t4;
+#pragma unroll
+            for (int kg = 0; kg < 8; ++kg) kf[kg] = (kg < HD / 32) ? *reinterpret_cast<const uint4*>(kr + kg * 32) : zero4;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int n0 = warp + 8 * i;
+#pragma unroll
+              for (int kg = 0; kg < 2; ++kg)
+                vf[i][kg] = (n0 < HD / 8) ? *reinterpret_cast<const uint4*>(VcT + (long)(n0 * 8 + g) * p.TpadK + key0 +
+                                                                              8 * t4 + kg * 32)
+                                          : zero4;
+            }
+          }
           {  // S tile: warp w -> keys key0 + 8w .. + 8, full K = HD
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const bf16* kr = Kc + (long)(key0 + 8 * warp + g) * HD + 8 * t4;
-            uint4 b[8];  // HD <= 256: all K loads of the tile in flight before the first MMA
-#pragma unroll
-            for (int kg = 0; kg < 8; ++kg)
-              if (kg < HD / 32) b[kg] = *reinterpret_cast<const uint4*>(kr + kg * 32);
+            const bool vlo = g < A, vhi = (g + 8) < A;
 #pragma unroll
             for (int kg = 0; kg < 8; ++kg) {
               if (kg < HD / 32) {
-                const uint4 alo = *reinterpret_cast<const uint4*>(q_s + g * ldq + kg * 32 + 8 * t4);
-                const uint4 ahi = *reinterpret_cast<const uint4*>(q_s + (g + 8) * ldq + kg * 32 + 8 * t4);
-                dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, b[kg].x, b[kg].y);
-                dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, b[kg].z, b[kg].w);
+                const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(q_s + g * ldq + kg * 32 + 8 * t4) : zero4;
+                const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(q_s + (g + 8) * ldq + kg * 32 + 8 * t4) : zero4;
+                dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, kf[kg].x, kf[kg].y);
+                dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, kf[kg].z, kf[kg].w);
               }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const int m = g + (j >> 1) * 8, kk = 8 * warp + 2 * t4 + (j & 1), key = key0 + kk;
               bool ok = false;
-              if (m < A && key < Pn) ok = (p.bits[(long)m * p.W32 + (key >> 5)] >> (key & 31)) & 1u;
+              if (m < A && key < Pn) ok = (bits_s[m * 32 + (key >> 5)] >> (key & 31)) & 1u;
               s_s[m * DN_CK + kk] = ok ? acc[j] : DN_BIG_NEG;
             }
           }
@@ -478,34 +553,34 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           }
           __syncthreads();
           // O_c = P V : n8 tiles over the head dims, warp w -> tiles w, w+8, ...; K = 64 keys (2 groups)
-          for (int n0 = warp; n0 < HD / 8; n0 += 8) {
-            float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            const bf16* vr = VcT + (long)(n0 * 8 + g) * p.TpadK + key0 + 8 * t4;
+          {
+            const bool vlo = g < A, vhi = (g + 8) < A;
+            uint4 alo[2], ahi[2];
 #pragma unroll
-            for (int kg = 0; kg < DN_CK / 32; ++kg) {
-              const uint4 b = *reinterpret_cast<const uint4*>(vr + kg * 32);
-              const uint4 alo = *reinterpret_cast<const uint4*>(p_s + g * ldp + kg * 32 + 8 * t4);
-              const uint4 ahi = *reinterpret_cast<const uint4*>(p_s + (g + 8) * ldp + kg * 32 + 8 * t4);
-              dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
-              dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+            for (int kg = 0; kg < 2; ++kg) {
+              alo[kg] = vlo ? *reinterpret_cast<const uint4*>(p_s + g * ldp + kg * 32 + 8 * t4) : zero4;
+              ahi[kg] = vhi ? *reinterpret_cast<const uint4*>(p_s + (g + 8) * ldp + kg * 32 + 8 * t4) : zero4;
             }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              const int m = g + (j >> 1) * 8, d = n0 * 8 + 2 * t4 + (j & 1);
-              if (m < A) po[m * HD + d] = acc[j];
+            for (int i = 0; i < 4; ++i) {
+              const int n0 = warp + 8 * i;
+              if (n0 < HD / 8) {
+                float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                for (int kg = 0; kg < 2; ++kg) {
+                  dn_mma(acc, alo[kg].x, ahi[kg].x, alo[kg].y, ahi[kg].y, vf[i][kg].x, vf[i][kg].y);
+                  dn_mma(acc, alo[kg].z, ahi[kg].z, alo[kg].w, ahi[kg].w, vf[i][kg].z, vf[i][kg].w);
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int m = g + (j >> 1) * 8, d = n0 * 8 + 2 * t4 + (j & 1);
+                  if (m < A) po[m * HD + d] = acc[j];
+                }
+              }
             }
           }
         } else {
-          // ---- suffix keys (this step's own A tokens): CUDA cores ----
-          for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
-            const int m = i / half, d = i % half;
-            const float x1 = __bfloat162float(__ldcg(qkv + (long)m * QKV + NH * HD + d));
-            const float x2 = __bfloat162float(__ldcg(qkv + (long)m * QKV + NH * HD + half + d));
-            const float cs = rope_s[m * half + d].x, sn = rope_s[m * half + d].y;
-            ks_s[m * HD + d] = bf16r(x1 * cs - x2 * sn);
-            ks_s[m * HD + half + d] = bf16r(x2 * cs + x1 * sn);
-          }
-          __syncthreads();
+          // ---- suffix keys (this step's own A tokens): CUDA cores on shared memory ----
           for (int pr = warp; pr < A * A; pr += 8) {  // logits: warp per (query a, key a2)
             const int a = pr / A, a2 = pr % A;
             float s = 0.f;
@@ -513,7 +588,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
             s = warp_sum(s);
             if (lane == 0) {
               const int key = Pn + a2;
-              const bool ok = (p.bits[(long)a * p.W32 + (key >> 5)] >> (key & 31)) & 1u;
+              const bool ok = (bits_s[a * 32 + (key >> 5)] >> (key & 31)) & 1u;
               s_s[a * DN_CK + a2] = ok ? s : DN_BIG_NEG;
             }
           }
@@ -532,19 +607,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
             pml[a * 2 + 1] = sum;
           }
           __syncthreads();
-          for (int d = threadIdx.x; d < HD; d += DN_THREADS) {
-            float o[16];
-#pragma unroll
-            for (int a = 0; a < 16; ++a) o[a] = 0.f;
-            for (int a2 = 0; a2 < A; ++a2) {
-              const float v = __bfloat162float(__ldcg(qkv + (long)a2 * QKV + (NH + 1) * HD + d));
-#pragma unroll
-              for (int a = 0; a < 16; ++a)
-                if (a < A) o[a] += s_s[a * DN_CK + a2] * v;
-            }
-#pragma unroll
-            for (int a = 0; a < 16; ++a)
-              if (a < A) po[a * HD + d] = o[a];
+          for (int i = threadIdx.x; i < A * HD; i += DN_THREADS) {
+            const int a = i / HD, d = i % HD;
+            float o = 0.f;
+            for (int a2 = 0; a2 < A; ++a2) o += s_s[a * DN_CK + a2] * __bfloat162float(vraw[a2 * HD + d]);
+            po[a * HD + d] = o;
           }
         }
       }
@@ -555,107 +622,129 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       // ---------------- P2b: combine the chunks -> O [A, NH*HD] ----------------
       for (int i = blockIdx.x * DN_THREADS + threadIdx.x; i < A * OD; i += gridDim.x * DN_THREADS) {
         const int m = i / OD, h = (i / HD) % NH, d = i % HD;
+        float mc[17], lc[17], oc[17];  // NCH <= 17 (Tpad <= 1024): every load issued before the first use
+#pragma unroll
+        for (int c = 0; c < 17; ++c) {
+          if (c < NCH) {
+            const long it = (long)(h * NCH + c);
+            mc[c] = __ldcg(p.part_ml + (it * 16 + m) * 2);
+            lc[c] = __ldcg(p.part_ml + (it * 16 + m) * 2 + 1);
+            oc[c] = __ldcg(p.part_o + (it * 16 + m) * HD + d);
+          }
+        }
         float mx = -3.4e38f;
-        for (int c = 0; c < NCH; ++c) mx = fmaxf(mx, __ldcg(p.part_ml + ((long)(h * NCH + c) * 16 + m) * 2));
+#pragma unroll
+        for (int c = 0; c < 17; ++c)
+          if (c < NCH) mx = fmaxf(mx, mc[c]);
         float den = 0.f, num = 0.f;
-        for (int c = 0; c < NCH; ++c) {
-          const long it = (long)(h * NCH + c);
-          const float w = __expf(__ldcg(p.part_ml + (it * 16 + m) * 2) - mx);
-          den += w * __ldcg(p.part_ml + (it * 16 + m) * 2 + 1);
-          num += w * __ldcg(p.part_o + (it * 16 + m) * HD + d);
+#pragma unroll
+        for (int c = 0; c < 17; ++c) {
+          if (c < NCH) {
+            const float w = __expf(mc[c] - mx);
+            den += w * lc[c];
+            num += w * oc[c];
+          }
         }
         Obuf[(long)m * OD + h * HD + d] = __float2bfloat16_rn(num / den);
       }
-      {  // prefetch the gate/up tiles of P4 while waiting (largest slice of the layer)
-        int pb, pe;
-        dn_range(F1 / 8, pb, pe);
-        if (pe > pb) {
-          dn_prefetch_l2(Wgu + (long)pb * 8 * D1, (long)(pe - pb) * 8 * D1 * 2);
-          dn_prefetch_l2(Wgu + ((long)F1 + (long)pb * 8) * D1, (long)(pe - pb) * 8 * D1 * 2);
-        }
+      // P3's weights (one n8 tile of Wo per CTA): in flight across the barrier
+      uint4 w3[8][1];
+      const bf16* wt3[1] = {o_te > o_tb ? Wo + (long)o_tb * 8 * OD : nullptr};
+      dn_load_w<1, 8>(w3, wt3, OD, OD >> 5, warp);
+      if (f_pe > f_pb) {
+        dn_prefetch_l2(Wgu + (long)f_pb * 8 * D1, (long)(f_pe - f_pb) * 8 * D1 * 2);
+        dn_prefetch_l2(Wgu + ((long)F1 + (long)f_pb * 8) * D1, (long)(f_pe - f_pb) * 8 * D1 * 2);
       }
       tick(6);
       bar.sync();
       tick(7);
 
       // ---------------- P3: XE1 = XE + gate_a * (O Wo^T) ----------------
-      {
-        int tb, te;
-        dn_range(D1 / 8, tb, te);
-        for (int t0 = tb; t0 < te; ++t0) {
-          const bf16* wt[1] = {Wo + (long)t0 * 8 * OD};
-          dn_mma_pass<1, false>(Obuf, OD, A, OD, wt, OD, red);
+      uint4 w4[4][4];
+      const bf16* wt4[4];
+      gu_tiles(Wgu, f_pb, wt4);
+      if (o_te > o_tb) {
+        dn_stage(Obuf, OD, h_s, ldo, A, OD);
+        dn_cp_wait_all();
+        __syncthreads();
+        for (int t0 = o_tb; t0 < o_te; ++t0) {
+          dn_mma_pass<1, 8>(h_s, ldo, A, OD, wt3, OD, w3, red);
+          if (t0 + 1 < o_te) {
+            wt3[0] = Wo + (long)(t0 + 1) * 8 * OD;
+            dn_load_w<1, 8>(w3, wt3, OD, OD >> 5, warp);
+          } else {
+            dn_load_w<4, 4>(w4, wt4, D1, D1 >> 5, warp);  // P4's first pass
+          }
           if (threadIdx.x < 16 * 8) {
             const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
             if (m < A) {
               const int n = t0 * 8 + cc;
               const float y = bf16r(dn_tile_val<1>(red, 0, m, cc));
-              const float gt = __bfloat162float(__ldcg(mod_a + 2 * D1 + n));
+              const float gt = __bfloat162float(mod_a[2 * D1 + n]);
               const float r = __bfloat162float(xe_s[m * D1 + n]);
               XE1[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
             }
           }
           __syncthreads();
         }
-        int db, de;
-        dn_range(D1 / 8, db, de);
-        if (de > db) dn_prefetch_l2(Wd + (long)db * 8 * F1, (long)(de - db) * 8 * F1 * 2);
+      } else {
+        dn_load_w<4, 4>(w4, wt4, D1, D1 >> 5, warp);
       }
+      if (o_te > o_tb) dn_prefetch_l2(Wd + (long)o_tb * 8 * F1, (long)(o_te - o_tb) * 8 * F1 * 2);
       tick(8);
       bar.sync();
       tick(9);
 
       // ---------------- P4: h = adaRMS(XE1); act = gelu(h Wg^T) * (h Wu^T) ----------------
-      dn_load_rows(XE1, xe_s, A, D1);
+      dn_stage(XE1, D1, xe_s, D1, A, D1);
+      dn_cp_wait_all();
       __syncthreads();
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_f);
       __syncthreads();
-      {
-        int pb, pe;
-        dn_range(F1 / 8, pb, pe);
-        for (int p0 = pb; p0 < pe; p0 += 2) {
-          const bf16* wt[4];
+      uint4 w5[16][1];
+      const bf16* wt5[1] = {o_te > o_tb ? Wd + (long)o_tb * 8 * F1 : nullptr};
+      for (int p0 = f_pb; p0 < f_pe; p0 += 2) {
+        dn_mma_pass<4, 4>(h_s, ldh, A, D1, wt4, D1, w4, red);
+        const bf16* wn[4];
+        gu_tiles(Wgu, p0 + 2, wn);
+        if (p0 + 2 < f_pe) dn_load_w<4, 4>(w4, wn, D1, D1 >> 5, warp);
+        {
+          const int e = threadIdx.x;  // 16 rows x 2 pairs x 8 columns = 256 outputs
+          const int m = e >> 4, pi = (e >> 3) & 1, cc = e & 7;
+          if (m < A && p0 + pi < f_pe) {
+            const float gv = bf16r(dn_tile_val<4>(red, 2 * pi, m, cc));
+            const float uv = bf16r(dn_tile_val<4>(red, 2 * pi + 1, m, cc));
+            act[(long)m * F1 + (p0 + pi) * 8 + cc] = __float2bfloat16_rn(bf16r(gelu_tanh(gv)) * uv);
+          }
+        }
+        __syncthreads();
 #pragma unroll
-          for (int i = 0; i < 2; ++i) {
-            const bool ok = p0 + i < pe;
-            wt[2 * i] = ok ? Wgu + (long)(p0 + i) * 8 * D1 : nullptr;
-            wt[2 * i + 1] = ok ? Wgu + ((long)F1 + (long)(p0 + i) * 8) * D1 : nullptr;
-          }
-          dn_mma_pass<4, true>(h_s, ldh, A, D1, wt, D1, red);
-          {
-            const int e = threadIdx.x;  // 16 rows x 2 pairs x 8 columns = 256 outputs
-            const int m = e >> 4, pi = (e >> 3) & 1, cc = e & 7;
-            if (m < A && p0 + pi < pe) {
-              const float gv = bf16r(dn_tile_val<4>(red, 2 * pi, m, cc));
-              const float uv = bf16r(dn_tile_val<4>(red, 2 * pi + 1, m, cc));
-              act[(long)m * F1 + (p0 + pi) * 8 + cc] = __float2bfloat16_rn(bf16r(gelu_tanh(gv)) * uv);
-            }
-          }
-          __syncthreads();
-        }
-        if (l + 1 < L) {  // next layer's qkv tiles
-          int qb, qe;
-          dn_range(QKV / 8, qb, qe);
-          if (qe > qb) dn_prefetch_l2(Wqkv + p.qkv_ls + (long)qb * 8 * D1, (long)(qe - qb) * 8 * D1 * 2);
-        }
+        for (int i = 0; i < 4; ++i) wt4[i] = wn[i];
       }
+      dn_load_w<1, 16>(w5, wt5, F1, F1 >> 5, warp);  // P5's tile of Wd: in flight across the barrier
+      if (l + 1 < L && q_te > q_tb)
+        dn_prefetch_l2(Wqkv + p.qkv_ls + (long)q_tb * 8 * D1, (long)(q_te - q_tb) * 8 * D1 * 2);
       tick(10);
       bar.sync();
       tick(11);
 
       // ---------------- P5: XE = XE1 + gate_f * (act Wd^T) ----------------
-      {
-        int tb, te;
-        dn_range(D1 / 8, tb, te);
-        for (int t0 = tb; t0 < te; ++t0) {
-          const bf16* wt[1] = {Wd + (long)t0 * 8 * F1};
-          dn_mma_pass<1, false>(act, F1, A, F1, wt, F1, red);
+      if (o_te > o_tb) {
+        dn_stage(act, F1, h_s, ldf, A, F1);
+        dn_cp_wait_all();
+        __syncthreads();
+        for (int t0 = o_tb; t0 < o_te; ++t0) {
+          dn_mma_pass<1, 16>(h_s, ldf, A, F1, wt5, F1, w5, red);
+          if (t0 + 1 < o_te) {
+            wt5[0] = Wd + (long)(t0 + 1) * 8 * F1;
+            dn_load_w<1, 16>(w5, wt5, F1, F1 >> 5, warp);
+          }
           if (threadIdx.x < 16 * 8) {
             const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
             if (m < A) {
               const int n = t0 * 8 + cc;
               const float y = bf16r(dn_tile_val<1>(red, 0, m, cc));
-              const float gt = __bfloat162float(__ldcg(mod_f + 2 * D1 + n));
+              const float gt = __bfloat162float(mod_f[2 * D1 + n]);
               const float r = __bfloat162float(xe_s[m * D1 + n]);
               XE[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
             }
@@ -663,22 +752,34 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           __syncthreads();
         }
       }
+      // next layer's qkv tiles: in flight across the barrier (the next step's layer 0 is loaded in the final phase)
+      if (l + 1 < L) {
+        qkv_tiles(Wqkv + p.qkv_ls, q_tb, wt1);
+        dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
+      }
       tick(12);
       bar.sync();
       tick(13);
     }
 
     // ---------------- final: v = action_out_proj(adaRMS(XE)); x += dt * v (lap.py:665-667) ----------------
-    dn_load_rows(XE, xe_s, A, D1);
+    if (step + 1 < S) {
+      qkv_tiles(reinterpret_cast<const bf16*>(p.qkv_w), q_tb, wt1);
+      dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
+    }
+    dn_stage(XE, D1, xe_s, D1, A, D1);
+    dn_stage(mod_s + (long)(p.nm - 1) * 3 * D1, 0, mod_sm, 0, 1, 2 * D1);
+    dn_cp_wait_all();
     __syncthreads();
-    dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_s + (long)(p.nm - 1) * 3 * D1);
+    dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_sm);
     __syncthreads();
     for (int o = warp; o < A * ad; o += 8) {
       const int m = o / ad, j = o % ad;
       float acc = 0.f;
-      for (int k = lane; k < D1; k += 32) acc += p.aout_w[(long)j * D1 + k] * __bfloat162float(h_s[m * ldh + k]);
+#pragma unroll 8
+      for (int k = lane; k < D1; k += 32) acc += __ldg(p.aout_w + (long)j * D1 + k) * __bfloat162float(h_s[m * ldh + k]);
       acc = warp_sum(acc);
-      if (lane == 0) x_s[o] += p.dt * (acc + p.aout_b[j]);
+      if (lane == 0) x_s[o] += p.dt * (acc + __ldg(p.aout_b + j));
     }
     __syncthreads();
     tick(14);
@@ -706,13 +807,6 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ Vc, bf16* __restrict
   }
 }
 
-static size_t dn_smem_bytes(int D1, int HD) {
-  // xe_s | h region | red | x_s | rope table   (the prologue's [16][D1] fp32 time-embedding aliases xe_s + h region,
-  // which is always >= 64*D1 bytes)
-  return (size_t)16 * D1 * 2 + dn_hreg_bytes(D1, HD) + (size_t)8 * 4 * 32 * 4 * 4 + (size_t)16 * 32 * 4 +
-         (size_t)16 * (HD / 2) * 8 + 16;
-}
-
 }  // namespace lapb
 
 using namespace lapb;
@@ -724,7 +818,8 @@ int lapb200_denoise_supported(int64_t B, int64_t A, int64_t ad, int64_t D1, int6
                               int64_t Pn, int64_t Tpad, int64_t num_steps) {
   return B == 1 && A >= 1 && A <= 16 && ad >= 1 && ad <= 32 && num_steps >= 1 && num_steps <= 16 && D1 % 32 == 0 &&
          D1 >= 64 && D1 <= 2048 && HD % 32 == 0 && HD >= 32 && HD <= 256 && F1 % 32 == 0 && (NH * HD) % 32 == 0 &&
-         NH >= 1 && Pn >= 1 && Tpad >= ((Pn + DN_CK - 1) / DN_CK) * DN_CK && Tpad % 8 == 0;
+         NH >= 1 && Pn >= 1 && Tpad >= ((Pn + DN_CK - 1) / DN_CK) * DN_CK && Tpad % 32 == 0 && Tpad <= 1024 &&
+         dn_smem_bytes((int)D1, (int)HD, (int)(NH * HD), (int)F1) <= (size_t)227 * 1024;
 }
 
 int lapb200_denoise_grid(void) { return num_sms(); }
@@ -744,7 +839,8 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
                "denoise_loop: unsupported shape (A=%d ad=%d D1=%d NH=%d HD=%d F1=%d Pn=%d Tpad=%d steps=%d)", p.A, p.ad,
                p.D1, p.NH, p.HD, p.F1, p.Pn, p.Tpad, p.num_steps);
   LAPB_REQUIRE(p.TpadK == ((p.Pn + DN_CK - 1) / DN_CK) * DN_CK, "denoise_loop: TpadK must be round_up(Pn, 64)");
-  const size_t smem = dn_smem_bytes(p.D1, p.HD);
+  const size_t smem = dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
+  LAPB_REQUIRE(smem <= 227 * 1024, "denoise_loop: needs %zu bytes of shared memory (> 227 KB)", smem);
   static size_t configured = 0;
   if (smem > configured) {
     LAPB_CUDA_OK(cudaFuncSetAttribute(denoise_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
