@@ -221,7 +221,7 @@ typedef struct {
   void *XE, *XE1, *qkv, *O, *act;    /* scratch bf16 [16*D1] x2, [16*(NH+2)*HD], [16*NH*HD], [16*F1] */
   float *part_o, *part_ml;           /* scratch [NH*(TpadK/64+1)*16*HD], [NH*(TpadK/64+1)*16*2] */
   uint32_t* sync;                    /* [2]: barrier counter, error flag (set if a barrier timed out) */
-  unsigned long long* prof;          /* optional [16]: ns per phase slot seen by CTA 0 (0 prologue, 1 action_in, 2/3 P1 work /
+  unsigned long long* prof;          /* optional [32]: ns per phase slot seen by CTA 0 (16.. = sub-phase marks); (0 prologue, 1 action_in, 2/3 P1 work /
                                         barrier, 4/5 P2, 6/7 P2b, 8/9 P3, 10/11 P4, 12/13 P5, 14 final); NULL = off */
 } lapb_denoise_params_t;
 /* 1 if the shape is supported by the persistent kernel (B == 1, A <= 16, num_steps <= 16, head_dim <= 256 ...). */

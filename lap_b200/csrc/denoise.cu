@@ -35,7 +35,8 @@ namespace lapb {
 
 typedef __nv_bfloat16 bf16;
 #define DN_BIG_NEG (-2.3819763e38f)
-constexpr int DN_THREADS = 256;
+constexpr int DN_THREADS = 1024;
+constexpr int DN_WARPS = DN_THREADS / 32;
 constexpr int DN_CK = 64;  // keys per attention chunk
 
 __device__ __forceinline__ uint4 dn_ld_stream(const void* p) {
@@ -54,8 +55,10 @@ __device__ __forceinline__ void dn_mma(float (&c)[4], uint32_t a0, uint32_t a1, 
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 // L2 prefetch of a contiguous byte range (16-byte aligned, multiple of 16), 16 KB per issuing thread
-__device__ __forceinline__ void dn_prefetch_l2(const void* p, long bytes) {
-  for (long off = (long)threadIdx.x * 16384; off < bytes; off += (long)DN_THREADS * 16384) {
+__device__ __forceinline__ void dn_prefetch_l2(const void* p, long bytes, int first_thread) {
+  const int t = (int)threadIdx.x - first_thread;
+  if (t < 0) return;
+  for (long off = (long)t * 16384; off < bytes; off += (long)(DN_THREADS - first_thread) * 16384) {
     const uint32_t n = (uint32_t)((bytes - off) < 16384 ? (bytes - off) : 16384);
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(reinterpret_cast<const char*>(p) + off), "r"(n)
                  : "memory");
@@ -124,66 +127,65 @@ __device__ __forceinline__ void dn_stage(const bf16* src, long lds, bf16* dst, i
   }
 }
 
-// Weight fragments of up to NT n8 tiles for this warp's K groups kg0 + 8u (u < U): issued early (before the grid
-// barrier of the previous phase) so that their DRAM/L2 latency overlaps the barrier.  wt[i] = first row of tile i.
-template <int NT, int U>
-__device__ __forceinline__ void dn_load_w(uint4 (&b)[U][NT], const bf16* const (&wt)[NT], long ldw, int ngroups, int kg0) {
+// ---- skinny products with 32 warps ----
+// A pass multiplies the staged rows As[M<=16 x K] (shared memory) with up to four n8 weight tiles.  Warp roles:
+//   tile mode   (P1, P4, modulation GEMM): warp = (tslot = warp >> 3, kpart = warp & 7): tile `tslot` of the pass, K groups
+//               kpart, kpart + 8, ...           (8-way K split per tile)
+//   ksplit mode (P3, P5: one tile per CTA, long K): every warp works on the same tile, K groups warp, warp + 32, ...
+// Either way warp w deposits its 16x8 partial tile in red[kpart][tslot] and the epilogue sums 8 (tile mode) or 32
+// (ksplit mode) partials.  The weight fragments b[U] of the first K iteration are loaded by dn_load_w BEFORE the grid
+// barrier that precedes the phase, so their DRAM/L2 latency overlaps the barrier.
+template <int U>
+__device__ __forceinline__ void dn_load_w(uint4 (&b)[U], const bf16* wtile, long ldw, int ngroups, int kg_first,
+                                          int kg_stride) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
-    const int kg = kg0 + 8 * u;
-#pragma unroll
-    for (int i = 0; i < NT; ++i)
-      b[u][i] = (wt[i] != nullptr && kg < ngroups) ? dn_ld_stream(wt[i] + (long)g * ldw + 8 * t + kg * 32)
-                                                  : make_uint4(0, 0, 0, 0);
+    const int kg = kg_first + kg_stride * u;
+    b[u] = (wtile != nullptr && kg < ngroups) ? dn_ld_stream(wtile + (long)g * ldw + 8 * t + kg * 32)
+                                              : make_uint4(0, 0, 0, 0);
   }
 }
-// One pass of the skinny product: red[warp][tile][lane][4] <- partial sums of As[M x K] * W_tile[8 x K]^T over this warp's
-// K groups.  As is in shared memory; b holds the fragments of the first K iteration (dn_load_w(..., kg0 = warp)).
-template <int NT, int U>
-__device__ __forceinline__ void dn_mma_pass(const bf16* As, int lda, int M, int K, const bf16* const (&wt)[NT], long ldw,
-                                            uint4 (&b)[U][NT], float* red) {
+template <int U>
+__device__ __forceinline__ void dn_mma_warp(const bf16* As, int lda, int M, int ngroups, int kg_first, int kg_stride,
+                                            uint4 (&b)[U], const bf16* wtile, long ldw, float* red) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  float acc[NT][4];
-#pragma unroll
-  for (int i = 0; i < NT; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
   const bf16* xlo = As + (long)g * lda + 8 * t;
   const bf16* xhi = As + (long)(g + 8) * lda + 8 * t;
   const bool vlo = g < M, vhi = (g + 8) < M;
-  const int ngroups = K >> 5;
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (int kg0 = warp; kg0 < ngroups; kg0 += 8 * U) {
-    if (kg0 != warp) dn_load_w<NT, U>(b, wt, ldw, ngroups, kg0);
+  for (int base = kg_first; base < ngroups; base += kg_stride * U) {
+    if (base != kg_first) dn_load_w<U>(b, wtile, ldw, ngroups, base, kg_stride);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int kg = kg0 + 8 * u;
+      const int kg = base + kg_stride * u;
       if (kg < ngroups) {
         const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(xlo + kg * 32) : zero;
         const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(xhi + kg * 32) : zero;
-#pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          dn_mma(acc[i], alo.x, ahi.x, alo.y, ahi.y, b[u][i].x, b[u][i].y);
-          dn_mma(acc[i], alo.z, ahi.z, alo.w, ahi.w, b[u][i].z, b[u][i].w);
-        }
+        dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, b[u].x, b[u].y);
+        dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, b[u].z, b[u].w);
       }
     }
   }
-#pragma unroll
-  for (int i = 0; i < NT; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) red[((warp * NT + i) * 32 + lane) * 4 + j] = acc[i][j];
-  __syncthreads();
+  // red[kpart = warp & 7][tslot = warp >> 3][lane][4]
+  *reinterpret_cast<float4*>(red + ((((warp & 7) * 4 + (warp >> 3)) * 32 + lane) << 2)) =
+      make_float4(acc[0], acc[1], acc[2], acc[3]);
 }
-// element (m, cc) of tile `tile` after dn_mma_pass: sum of the 8 K-split warps
-template <int NT>
-__device__ __forceinline__ float dn_tile_val(const float* red, int tile, int m, int cc) {
+// element (m, cc) of tile slot `tslot` (sum of its 8 K parts); ksplit mode sums all four slots as well
+__device__ __forceinline__ float dn_tile_val(const float* red, int tslot, int m, int cc, bool all_slots) {
   const int src_lane = (m & 7) * 4 + (cc >> 1), idx = (m >> 3) * 2 + (cc & 1);
   float s = 0.f;
 #pragma unroll
-  for (int w = 0; w < 8; ++w) s += red[((w * NT + tile) * 32 + src_lane) * 4 + idx];
+  for (int w = 0; w < 8; ++w) {
+    if (all_slots) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) s += red[((w * 4 + q) * 32 + src_lane) * 4 + idx];
+    } else {
+      s += red[((w * 4 + tslot) * 32 + src_lane) * 4 + idx];
+    }
+  }
   return s;
 }
 
@@ -191,7 +193,7 @@ __device__ __forceinline__ float dn_tile_val(const float* red, int tile, int m, 
 // per row; scale/shift come from shared memory (mod_row = [scale | shift | gate], staged with the rows).
 __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh, int A, int D1, const bf16* mod_row) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int m = warp; m < A; m += 8) {
+  for (int m = warp; m < A; m += DN_WARPS) {
     float s2 = 0.f;
     for (int c = lane * 8; c < D1; c += 256) {
       float v[8];
@@ -217,7 +219,7 @@ __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh
 __device__ __noinline__ void dn_time_mlp(const float* in_s, int R, int D1, const float* W, const float* bias, float* out_f32,
                                          bf16* out_bf16) {
   const int lane = threadIdx.x & 31;
-  const int gw = blockIdx.x * 8 + (threadIdx.x >> 5), nw = gridDim.x * 8;
+  const int gw = blockIdx.x * DN_WARPS + (threadIdx.x >> 5), nw = gridDim.x * DN_WARPS;
   for (int n = gw; n < D1; n += nw) {
     float acc[16];
 #pragma unroll
@@ -247,7 +249,8 @@ __device__ __noinline__ void dn_time_mlp(const float* in_s, int R, int D1, const
 __host__ __device__ inline size_t dn_align16(size_t x) { return (x + 15) & ~(size_t)15; }
 __host__ __device__ inline size_t dn_attn_bytes(int HD) {
   return (size_t)16 * (HD + 8) * 2      /* q_s  */ + (size_t)16 * DN_CK * 4 /* s_s */ + (size_t)16 * (DN_CK + 8) * 2 /* p_s */ +
-         (size_t)16 * HD * 4            /* ks_s */ + (size_t)3 * 16 * HD * 2 /* raw q, k, v rows */;
+         (size_t)16 * HD * 4            /* ks_s */ + (size_t)3 * 16 * HD * 2 /* raw q, k, v rows */ +
+         (size_t)4 * 16 * DN_CK * 4     /* sp_s */;
 }
 // region holding, in turn: normalised rows h (P1, P4, final), attention scratch (P2), staged O (P3), staged act (P5)
 __host__ __device__ inline size_t dn_big_bytes(int D1, int HD, int OD, int F1) {
@@ -287,9 +290,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   bf16* qraw = reinterpret_cast<bf16*>(ks_s + 16 * HD);                               // [16][HD] x3
   bf16* kraw = qraw + 16 * HD;
   bf16* vraw = kraw + 16 * HD;
+  float* sp_s = reinterpret_cast<float*>(vraw + 16 * HD);                             // [4][16][64] S partials (K quarters)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
+  const int tslot = warp >> 3, kpart = warp & 7;
   GridBarrier bar{p.sync, p.sync + 1, 0u, gridDim.x};
   // optional phase profile (CTA 0, thread 0): nanoseconds accumulated per phase slot
   unsigned long long prof_last = 0;
@@ -311,23 +316,18 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   bf16* act = reinterpret_cast<bf16*>(p.act);
   const int NCHP = (Pn + DN_CK - 1) / DN_CK, NCH = NCHP + 1;
   const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int ng1 = D1 >> 5, ngo = OD >> 5, ngf = F1 >> 5;
 
   // this CTA's share of every phase (contiguous n8 tiles / GeGLU pairs / attention item)
   int q_tb, q_te, o_tb, o_te, f_pb, f_pe;
   dn_range(QKV / 8, q_tb, q_te);
   dn_range(D1 / 8, o_tb, o_te);
   dn_range(F1 / 8, f_pb, f_pe);
-  auto qkv_tiles = [&](const bf16* W, int t0, const bf16* (&wt)[4]) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) wt[i] = (t0 + i < q_te) ? W + (long)(t0 + i) * 8 * D1 : nullptr;
-  };
-  auto gu_tiles = [&](const bf16* W, int p0, const bf16* (&wt)[4]) {
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const bool ok = p0 + i < f_pe;
-      wt[2 * i] = ok ? W + (long)(p0 + i) * 8 * D1 : nullptr;
-      wt[2 * i + 1] = ok ? W + ((long)F1 + (long)(p0 + i) * 8) * D1 : nullptr;
-    }
+  // this warp's weight tile in a tile-mode pass
+  auto qkv_tile = [&](const bf16* W, int t0) { return (t0 + tslot < q_te) ? W + (long)(t0 + tslot) * 8 * D1 : nullptr; };
+  auto gu_tile = [&](const bf16* W, int p0) {  // slots: gate p0, up p0, gate p0+1, up p0+1
+    const int pr = p0 + (tslot >> 1);
+    return (pr < f_pe) ? W + ((long)(tslot & 1) * F1 + (long)pr * 8) * D1 : nullptr;
   };
 
   // =========================== prologue: time conditioning of every step ===========================
@@ -357,32 +357,26 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
     int tb, te;
     dn_range(nm3 / 8, tb, te);
     const bf16* mw = reinterpret_cast<const bf16*>(p.mod_w);
-    auto mod_tiles = [&](int t0, const bf16* (&wt)[4]) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) wt[i] = (t0 + i < te) ? mw + (long)(t0 + i) * 8 * D1 : nullptr;
-    };
-    uint4 b[4][4];
-    const bf16* wt[4];
-    mod_tiles(tb, wt);
-    dn_load_w<4, 4>(b, wt, D1, D1 >> 5, warp);
+    auto mod_tile = [&](int t0) { return (t0 + tslot < te) ? mw + (long)(t0 + tslot) * 8 * D1 : nullptr; };
+    uint4 b[4];
+    const bf16* wt = mod_tile(tb);
+    dn_load_w<4>(b, wt, D1, ng1, kpart, 8);
     dn_cp_wait_all();
     __syncthreads();
     for (int t0 = tb; t0 < te; t0 += 4) {
-      dn_mma_pass<4, 4>(h_s, ldh, S, D1, wt, D1, b, red);
-      const bf16* wn[4];
-      mod_tiles(t0 + 4, wn);
-      if (t0 + 4 < te) dn_load_w<4, 4>(b, wn, D1, D1 >> 5, warp);  // next pass's weights fly during this epilogue
-      for (int e = threadIdx.x; e < 16 * 32; e += DN_THREADS) {
-        const int m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
+      dn_mma_warp<4>(h_s, ldh, S, ng1, kpart, 8, b, wt, D1, red);
+      __syncthreads();
+      wt = mod_tile(t0 + 4);
+      if (t0 + 4 < te) dn_load_w<4>(b, wt, D1, ng1, kpart, 8);  // next pass's weights fly during this epilogue
+      if (threadIdx.x < 16 * 32) {
+        const int e = threadIdx.x, m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
         if (m < S && t0 + tile < te) {
           const int n = (t0 + tile) * 8 + cc;
-          const float v = bf16r(dn_tile_val<4>(red, tile, m, cc)) + bf16r(p.mod_b[n]);
+          const float v = bf16r(dn_tile_val(red, tile, m, cc, false)) + bf16r(p.mod_b[n]);
           reinterpret_cast<bf16*>(p.mod)[(long)m * nm3 + n] = __float2bfloat16_rn(v);
         }
       }
       __syncthreads();
-#pragma unroll
-      for (int i = 0; i < 4; ++i) wt[i] = wn[i];
     }
     // x_t <- noise; (cos, sin) of the suffix positions and the mask words (constant over steps and layers)
     for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) x_s[i] = p.x[i];
@@ -398,10 +392,9 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   }
 
   // weights of the first P1 (layer 0): in flight while action_in_proj is computed
-  uint4 w1[4][4];
-  const bf16* wt1[4];
-  qkv_tiles(reinterpret_cast<const bf16*>(p.qkv_w), q_tb, wt1);
-  dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
+  uint4 w1[4];
+  const bf16* wt1 = qkv_tile(reinterpret_cast<const bf16*>(p.qkv_w), q_tb);
+  dn_load_w<4>(w1, wt1, D1, ng1, kpart, 8);
 
   // =========================== Euler loop ===========================
   for (int step = 0; step < S; ++step) {
@@ -427,46 +420,66 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       const bf16* mod_f = mod_sm + 3 * D1;  // ... of the ffn norm
 
       // ---------------- P1: h = adaRMS(XE); qkv = h Wqkv^T ----------------
+      {  // L2 prefetch of this CTA's weight slices of the NEXT layer (next step's layer 0 after the last one): the HBM
+         // traffic of a layer is spread over the whole previous layer instead of arriving as one burst per phase
+        const int ln = (l + 1 < L) ? l + 1 : 0;
+        if (l + 1 < L || step + 1 < S) {
+          const bf16* nq = reinterpret_cast<const bf16*>(p.qkv_w) + (long)ln * p.qkv_ls;
+          const bf16* no = reinterpret_cast<const bf16*>(p.o_w) + (long)ln * p.o_ls;
+          const bf16* ng = reinterpret_cast<const bf16*>(p.gu_w) + (long)ln * p.gu_ls;
+          const bf16* nd = reinterpret_cast<const bf16*>(p.down_w) + (long)ln * p.down_ls;
+          if (q_te > q_tb) dn_prefetch_l2(nq + (long)q_tb * 8 * D1, (long)(q_te - q_tb) * 8 * D1 * 2, 0);
+          if (o_te > o_tb) dn_prefetch_l2(no + (long)o_tb * 8 * OD, (long)(o_te - o_tb) * 8 * OD * 2, 8);
+          if (f_pe > f_pb) {
+            dn_prefetch_l2(ng + (long)f_pb * 8 * D1, (long)(f_pe - f_pb) * 8 * D1 * 2, 16);
+            dn_prefetch_l2(ng + ((long)F1 + (long)f_pb * 8) * D1, (long)(f_pe - f_pb) * 8 * D1 * 2, 24);
+          }
+          if (o_te > o_tb) dn_prefetch_l2(nd + (long)o_tb * 8 * F1, (long)(o_te - o_tb) * 8 * F1 * 2, 32);
+        }
+      }
       if (l > 0) dn_stage(XE, D1, xe_s, D1, A, D1);
       dn_stage(mod_s + (long)(2 * l) * 3 * D1, 0, mod_sm, 0, 1, 6 * D1);
       dn_cp_wait_all();
       __syncthreads();
+      tick(16);
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_a);
       __syncthreads();
+      tick(17);
       for (int t0 = q_tb; t0 < q_te; t0 += 4) {
-        dn_mma_pass<4, 4>(h_s, ldh, A, D1, wt1, D1, w1, red);
-        const bf16* wn[4];
-        qkv_tiles(Wqkv, t0 + 4, wn);
-        if (t0 + 4 < q_te) dn_load_w<4, 4>(w1, wn, D1, D1 >> 5, warp);
-        for (int e = threadIdx.x; e < 16 * 32; e += DN_THREADS) {
-          const int m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
+        dn_mma_warp<4>(h_s, ldh, A, ng1, kpart, 8, w1, wt1, D1, red);
+        __syncthreads();
+        tick(18);
+        wt1 = qkv_tile(Wqkv, t0 + 4);
+        if (t0 + 4 < q_te) dn_load_w<4>(w1, wt1, D1, ng1, kpart, 8);
+        if (threadIdx.x < 16 * 32) {
+          const int e = threadIdx.x, m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
           if (m < A && t0 + tile < q_te)
-            qkv[(long)m * QKV + (t0 + tile) * 8 + cc] = __float2bfloat16_rn(dn_tile_val<4>(red, tile, m, cc));
+            qkv[(long)m * QKV + (t0 + tile) * 8 + cc] = __float2bfloat16_rn(dn_tile_val(red, tile, m, cc, false));
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wt1[i] = wn[i];
       }
       // this CTA's attention item: K / V^T fragments of its key chunk do not depend on this step -> load them now
+      // (S tile: warps 0..7, one 8-key tile each; P V: one n8 tile of the head dims per warp)
+      tick(19);
       const int item0 = blockIdx.x;
       const bool item0_prefix = item0 < NH * NCH && (item0 % NCH) < NCHP;
-      uint4 kf[8], vf[4][2];
-      if (item0_prefix) {
-        const int key0 = (item0 % NCH) * DN_CK;
-        const bf16* kr = Kc + (long)(key0 + 8 * warp + g) * HD + 8 * t4;
+      uint4 kf[2], vf[2];
+      auto load_kv = [&](int key0) {
+        // S tile: warp = (key tile kpart, K quarter tslot): groups tslot, tslot + 4 of the head dim
+        const bf16* kr = Kc + (long)(key0 + 8 * kpart + g) * HD + 8 * t4;
 #pragma unroll
-        for (int kg = 0; kg < 8; ++kg) kf[kg] = (kg < HD / 32) ? *reinterpret_cast<const uint4*>(kr + kg * 32) : zero4;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int n0 = warp + 8 * i;
-#pragma unroll
-          for (int kg = 0; kg < 2; ++kg)
-            vf[i][kg] = (n0 < HD / 8)
-                            ? *reinterpret_cast<const uint4*>(VcT + (long)(n0 * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32)
-                            : zero4;
+        for (int u = 0; u < 2; ++u) {
+          const int kg = tslot + 4 * u;
+          kf[u] = (kg < HD / 32) ? *reinterpret_cast<const uint4*>(kr + kg * 32) : zero4;
         }
-      }
-      if (o_te > o_tb) dn_prefetch_l2(Wo + (long)o_tb * 8 * OD, (long)(o_te - o_tb) * 8 * OD * 2);
+#pragma unroll
+        for (int kg = 0; kg < 2; ++kg)
+          vf[kg] = (warp < HD / 8)
+                       ? *reinterpret_cast<const uint4*>(VcT + (long)(warp * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32)
+                       : zero4;
+      };
+      if (item0_prefix) load_kv((item0 % NCH) * DN_CK);
+      tick(20);
       tick(2);
       bar.sync();
       tick(3);
@@ -483,6 +496,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
         }
         dn_cp_wait_all();
         __syncthreads();
+        tick(24);
         // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ) (gemma.py:215-218, 548-564); suffix item: ks_s <- bf16(rope(k))
         for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
           const int m = i / half, d = i % half;
@@ -497,50 +511,48 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           }
         }
         __syncthreads();
+        tick(25);
         float* po = p.part_o + (long)item * 16 * HD;
         float* pml = p.part_ml + (long)item * 16 * 2;
         if (prefix) {
           // ---- prefix chunk: keys [key0, key0 + 64) of the cache, tensor cores ----
           const int key0 = c * DN_CK;
-          if (item != item0) {  // (only when there are more items than CTAs) fragments were not preloaded
-            const bf16* kr = Kc + (long)(key0 + 8 * warp + g) * HD + 8 * t4;
-#pragma unroll
-            for (int kg = 0; kg < 8; ++kg) kf[kg] = (kg < HD / 32) ? *reinterpret_cast<const uint4*>(kr + kg * 32) : zero4;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n0 = warp + 8 * i;
-#pragma unroll
-              for (int kg = 0; kg < 2; ++kg)
-                vf[i][kg] = (n0 < HD / 8) ? *reinterpret_cast<const uint4*>(VcT + (long)(n0 * 8 + g) * p.TpadK + key0 +
-                                                                              8 * t4 + kg * 32)
-                                          : zero4;
-            }
-          }
-          {  // S tile: warp w -> keys key0 + 8w .. + 8, full K = HD
+          if (item != item0) load_kv(key0);  // (only when there are more items than CTAs)
+          {  // S partial tile: warp (kpart, tslot) -> keys key0 + 8*kpart .. + 8, head-dim groups tslot, tslot + 4
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
             const bool vlo = g < A, vhi = (g + 8) < A;
 #pragma unroll
-            for (int kg = 0; kg < 8; ++kg) {
+            for (int u = 0; u < 2; ++u) {
+              const int kg = tslot + 4 * u;
               if (kg < HD / 32) {
                 const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(q_s + g * ldq + kg * 32 + 8 * t4) : zero4;
                 const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(q_s + (g + 8) * ldq + kg * 32 + 8 * t4) : zero4;
-                dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, kf[kg].x, kf[kg].y);
-                dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, kf[kg].z, kf[kg].w);
+                dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, kf[u].x, kf[u].y);
+                dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, kf[u].z, kf[u].w);
               }
             }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const int m = g + (j >> 1) * 8, kk = 8 * warp + 2 * t4 + (j & 1), key = key0 + kk;
-              bool ok = false;
-              if (m < A && key < Pn) ok = (bits_s[m * 32 + (key >> 5)] >> (key & 31)) & 1u;
-              s_s[m * DN_CK + kk] = ok ? acc[j] : DN_BIG_NEG;
+              const int m = g + (j >> 1) * 8, kk = 8 * kpart + 2 * t4 + (j & 1);
+              sp_s[(tslot * 16 + m) * DN_CK + kk] = acc[j];
             }
           }
           __syncthreads();
-          // chunk-local softmax: warp w -> rows 2w, 2w+1; lane -> keys lane, lane+32
-          for (int m = 2 * warp; m < 2 * warp + 2; ++m) {
-            if (m >= A) continue;
-            const float v0 = s_s[m * DN_CK + lane], v1 = s_s[m * DN_CK + 32 + lane];
+          tick(26);
+          // chunk-local softmax: warp m -> row m; lane -> keys lane, lane+32 (sum of the 4 K-quarter partials, mask)
+          if (warp < A) {
+            const int m = warp;
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v0 += sp_s[(q * 16 + m) * DN_CK + lane];
+              v1 += sp_s[(q * 16 + m) * DN_CK + 32 + lane];
+            }
+            const int k0 = key0 + lane, k1 = key0 + 32 + lane;
+            const bool ok0 = k0 < Pn && ((bits_s[m * 32 + (k0 >> 5)] >> (k0 & 31)) & 1u);
+            const bool ok1 = k1 < Pn && ((bits_s[m * 32 + (k1 >> 5)] >> (k1 & 31)) & 1u);
+            v0 = ok0 ? v0 : DN_BIG_NEG;
+            v1 = ok1 ? v1 : DN_BIG_NEG;
             const float mx = warp_max(fmaxf(v0, v1));
             const float e0 = __expf(v0 - mx), e1 = __expf(v1 - mx);
             const float sum = warp_sum(e0 + e1);
@@ -552,59 +564,49 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
             }
           }
           __syncthreads();
-          // O_c = P V : n8 tiles over the head dims, warp w -> tiles w, w+8, ...; K = 64 keys (2 groups)
-          {
+          tick(27);
+          // O_c = P V : warp w -> n8 tile w of the head dims; K = 64 keys (2 groups)
+          if (warp < HD / 8) {
             const bool vlo = g < A, vhi = (g + 8) < A;
-            uint4 alo[2], ahi[2];
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int kg = 0; kg < 2; ++kg) {
-              alo[kg] = vlo ? *reinterpret_cast<const uint4*>(p_s + g * ldp + kg * 32 + 8 * t4) : zero4;
-              ahi[kg] = vhi ? *reinterpret_cast<const uint4*>(p_s + (g + 8) * ldp + kg * 32 + 8 * t4) : zero4;
+              const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(p_s + g * ldp + kg * 32 + 8 * t4) : zero4;
+              const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(p_s + (g + 8) * ldp + kg * 32 + 8 * t4) : zero4;
+              dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, vf[kg].x, vf[kg].y);
+              dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, vf[kg].z, vf[kg].w);
             }
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int n0 = warp + 8 * i;
-              if (n0 < HD / 8) {
-                float acc[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-                for (int kg = 0; kg < 2; ++kg) {
-                  dn_mma(acc, alo[kg].x, ahi[kg].x, alo[kg].y, ahi[kg].y, vf[i][kg].x, vf[i][kg].y);
-                  dn_mma(acc, alo[kg].z, ahi[kg].z, alo[kg].w, ahi[kg].w, vf[i][kg].z, vf[i][kg].w);
-                }
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const int m = g + (j >> 1) * 8, d = n0 * 8 + 2 * t4 + (j & 1);
-                  if (m < A) po[m * HD + d] = acc[j];
-                }
-              }
+            for (int j = 0; j < 4; ++j) {
+              const int m = g + (j >> 1) * 8, d = warp * 8 + 2 * t4 + (j & 1);
+              if (m < A) po[m * HD + d] = acc[j];
             }
           }
         } else {
           // ---- suffix keys (this step's own A tokens): CUDA cores on shared memory ----
-          for (int pr = warp; pr < A * A; pr += 8) {  // logits: warp per (query a, key a2)
+          for (int pr = warp; pr < A * A; pr += DN_WARPS) {  // logits: warp per (query a, key a2)
             const int a = pr / A, a2 = pr % A;
-            float s = 0.f;
-            for (int d = lane; d < HD; d += 32) s += __bfloat162float(q_s[a * ldq + d]) * ks_s[a2 * HD + d];
-            s = warp_sum(s);
+            float sacc = 0.f;
+            for (int d = lane; d < HD; d += 32) sacc += __bfloat162float(q_s[a * ldq + d]) * ks_s[a2 * HD + d];
+            sacc = warp_sum(sacc);
             if (lane == 0) {
               const int key = Pn + a2;
               const bool ok = (bits_s[a * 32 + (key >> 5)] >> (key & 31)) & 1u;
-              s_s[a * DN_CK + a2] = ok ? s : DN_BIG_NEG;
+              s_s[a * DN_CK + a2] = ok ? sacc : DN_BIG_NEG;
             }
           }
           __syncthreads();
-          if (threadIdx.x < A) {
-            const int a = threadIdx.x;
-            float mx = -3.4e38f;
-            for (int a2 = 0; a2 < A; ++a2) mx = fmaxf(mx, s_s[a * DN_CK + a2]);
-            float sum = 0.f;
-            for (int a2 = 0; a2 < A; ++a2) {
-              const float e = __expf(s_s[a * DN_CK + a2] - mx);
-              sum += e;
-              s_s[a * DN_CK + a2] = bf16r(e);
+          if (warp < A) {  // warp a -> row a; lane a2 -> key a2 (A <= 16)
+            const int a = warp;
+            const float v = (lane < A) ? s_s[a * DN_CK + lane] : -3.4e38f;
+            const float mx = warp_max(v);
+            const float e = (lane < A) ? __expf(v - mx) : 0.f;
+            const float sum = warp_sum(e);
+            if (lane < A) s_s[a * DN_CK + lane] = bf16r(e);
+            if (lane == 0) {
+              pml[a * 2] = mx;
+              pml[a * 2 + 1] = sum;
             }
-            pml[a * 2] = mx;
-            pml[a * 2 + 1] = sum;
           }
           __syncthreads();
           for (int i = threadIdx.x; i < A * HD; i += DN_THREADS) {
@@ -619,67 +621,57 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       bar.sync();
       tick(5);
 
-      // ---------------- P2b: combine the chunks -> O [A, NH*HD] ----------------
-      for (int i = blockIdx.x * DN_THREADS + threadIdx.x; i < A * OD; i += gridDim.x * DN_THREADS) {
+      // ---------------- P2b: combine the chunks -> O [A, NH*HD]; outputs interleaved over the grid ----------------
+      const int per_cta = (A * OD + gridDim.x - 1) / gridDim.x;
+      for (int i0 = threadIdx.x; i0 < per_cta; i0 += DN_THREADS) {
+        const int i = blockIdx.x * per_cta + i0;
+        if (i >= A * OD) break;
         const int m = i / OD, h = (i / HD) % NH, d = i % HD;
-        float mc[17], lc[17], oc[17];  // NCH <= 17 (Tpad <= 1024): every load issued before the first use
-#pragma unroll
-        for (int c = 0; c < 17; ++c) {
-          if (c < NCH) {
-            const long it = (long)(h * NCH + c);
-            mc[c] = __ldcg(p.part_ml + (it * 16 + m) * 2);
-            lc[c] = __ldcg(p.part_ml + (it * 16 + m) * 2 + 1);
-            oc[c] = __ldcg(p.part_o + (it * 16 + m) * HD + d);
-          }
-        }
+        const float* ml = p.part_ml + ((long)h * NCH * 16 + m) * 2;
+        const float* oc = p.part_o + ((long)h * NCH * 16 + m) * HD + d;
         float mx = -3.4e38f;
-#pragma unroll
-        for (int c = 0; c < 17; ++c)
-          if (c < NCH) mx = fmaxf(mx, mc[c]);
+#pragma unroll 4
+        for (int c = 0; c < NCH; ++c) mx = fmaxf(mx, __ldcg(ml + (long)c * 32));
         float den = 0.f, num = 0.f;
-#pragma unroll
-        for (int c = 0; c < 17; ++c) {
-          if (c < NCH) {
-            const float w = __expf(mc[c] - mx);
-            den += w * lc[c];
-            num += w * oc[c];
-          }
+#pragma unroll 4
+        for (int c = 0; c < NCH; ++c) {
+          const float w = __expf(__ldcg(ml + (long)c * 32) - mx);
+          den += w * __ldcg(ml + (long)c * 32 + 1);
+          num += w * __ldcg(oc + (long)c * 16 * HD);
         }
         Obuf[(long)m * OD + h * HD + d] = __float2bfloat16_rn(num / den);
       }
-      // P3's weights (one n8 tile of Wo per CTA): in flight across the barrier
-      uint4 w3[8][1];
-      const bf16* wt3[1] = {o_te > o_tb ? Wo + (long)o_tb * 8 * OD : nullptr};
-      dn_load_w<1, 8>(w3, wt3, OD, OD >> 5, warp);
-      if (f_pe > f_pb) {
-        dn_prefetch_l2(Wgu + (long)f_pb * 8 * D1, (long)(f_pe - f_pb) * 8 * D1 * 2);
-        dn_prefetch_l2(Wgu + ((long)F1 + (long)f_pb * 8) * D1, (long)(f_pe - f_pb) * 8 * D1 * 2);
-      }
+      tick(21);
+      // P3's weights (one n8 tile of Wo per CTA, K split over all 32 warps): in flight across the barrier
+      uint4 w3[2];
+      const bf16* wt3 = o_te > o_tb ? Wo + (long)o_tb * 8 * OD : nullptr;
+      dn_load_w<2>(w3, wt3, OD, ngo, warp, DN_WARPS);
+      tick(22);
       tick(6);
       bar.sync();
       tick(7);
 
       // ---------------- P3: XE1 = XE + gate_a * (O Wo^T) ----------------
-      uint4 w4[4][4];
-      const bf16* wt4[4];
-      gu_tiles(Wgu, f_pb, wt4);
+      uint4 w4[4];
+      const bf16* wt4 = gu_tile(Wgu, f_pb);
       if (o_te > o_tb) {
         dn_stage(Obuf, OD, h_s, ldo, A, OD);
         dn_cp_wait_all();
         __syncthreads();
         for (int t0 = o_tb; t0 < o_te; ++t0) {
-          dn_mma_pass<1, 8>(h_s, ldo, A, OD, wt3, OD, w3, red);
+          dn_mma_warp<2>(h_s, ldo, A, ngo, warp, DN_WARPS, w3, wt3, OD, red);
+          __syncthreads();
           if (t0 + 1 < o_te) {
-            wt3[0] = Wo + (long)(t0 + 1) * 8 * OD;
-            dn_load_w<1, 8>(w3, wt3, OD, OD >> 5, warp);
+            wt3 = Wo + (long)(t0 + 1) * 8 * OD;
+            dn_load_w<2>(w3, wt3, OD, ngo, warp, DN_WARPS);
           } else {
-            dn_load_w<4, 4>(w4, wt4, D1, D1 >> 5, warp);  // P4's first pass
+            dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);  // P4's first pass
           }
           if (threadIdx.x < 16 * 8) {
             const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
             if (m < A) {
               const int n = t0 * 8 + cc;
-              const float y = bf16r(dn_tile_val<1>(red, 0, m, cc));
+              const float y = bf16r(dn_tile_val(red, 0, m, cc, true));
               const float gt = __bfloat162float(mod_a[2 * D1 + n]);
               const float r = __bfloat162float(xe_s[m * D1 + n]);
               XE1[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
@@ -688,9 +680,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           __syncthreads();
         }
       } else {
-        dn_load_w<4, 4>(w4, wt4, D1, D1 >> 5, warp);
+        dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);
       }
-      if (o_te > o_tb) dn_prefetch_l2(Wd + (long)o_tb * 8 * F1, (long)(o_te - o_tb) * 8 * F1 * 2);
       tick(8);
       bar.sync();
       tick(9);
@@ -699,31 +690,31 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       dn_stage(XE1, D1, xe_s, D1, A, D1);
       dn_cp_wait_all();
       __syncthreads();
+      tick(28);
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_f);
       __syncthreads();
-      uint4 w5[16][1];
-      const bf16* wt5[1] = {o_te > o_tb ? Wd + (long)o_tb * 8 * F1 : nullptr};
+      tick(29);
       for (int p0 = f_pb; p0 < f_pe; p0 += 2) {
-        dn_mma_pass<4, 4>(h_s, ldh, A, D1, wt4, D1, w4, red);
-        const bf16* wn[4];
-        gu_tiles(Wgu, p0 + 2, wn);
-        if (p0 + 2 < f_pe) dn_load_w<4, 4>(w4, wn, D1, D1 >> 5, warp);
-        {
+        dn_mma_warp<4>(h_s, ldh, A, ng1, kpart, 8, w4, wt4, D1, red);
+        __syncthreads();
+        wt4 = gu_tile(Wgu, p0 + 2);
+        if (p0 + 2 < f_pe) dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);
+        if (threadIdx.x < 256) {
           const int e = threadIdx.x;  // 16 rows x 2 pairs x 8 columns = 256 outputs
           const int m = e >> 4, pi = (e >> 3) & 1, cc = e & 7;
           if (m < A && p0 + pi < f_pe) {
-            const float gv = bf16r(dn_tile_val<4>(red, 2 * pi, m, cc));
-            const float uv = bf16r(dn_tile_val<4>(red, 2 * pi + 1, m, cc));
+            const float gv = bf16r(dn_tile_val(red, 2 * pi, m, cc, false));
+            const float uv = bf16r(dn_tile_val(red, 2 * pi + 1, m, cc, false));
             act[(long)m * F1 + (p0 + pi) * 8 + cc] = __float2bfloat16_rn(bf16r(gelu_tanh(gv)) * uv);
           }
         }
         __syncthreads();
-#pragma unroll
-        for (int i = 0; i < 4; ++i) wt4[i] = wn[i];
       }
-      dn_load_w<1, 16>(w5, wt5, F1, F1 >> 5, warp);  // P5's tile of Wd: in flight across the barrier
-      if (l + 1 < L && q_te > q_tb)
-        dn_prefetch_l2(Wqkv + p.qkv_ls + (long)q_tb * 8 * D1, (long)(q_te - q_tb) * 8 * D1 * 2);
+      tick(30);
+      // P5's tile of Wd (K split over all 32 warps): in flight across the barrier
+      uint4 w5[4];
+      const bf16* wt5 = o_te > o_tb ? Wd + (long)o_tb * 8 * F1 : nullptr;
+      dn_load_w<4>(w5, wt5, F1, ngf, warp, DN_WARPS);
       tick(10);
       bar.sync();
       tick(11);
@@ -734,16 +725,17 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
         dn_cp_wait_all();
         __syncthreads();
         for (int t0 = o_tb; t0 < o_te; ++t0) {
-          dn_mma_pass<1, 16>(h_s, ldf, A, F1, wt5, F1, w5, red);
+          dn_mma_warp<4>(h_s, ldf, A, ngf, warp, DN_WARPS, w5, wt5, F1, red);
+          __syncthreads();
           if (t0 + 1 < o_te) {
-            wt5[0] = Wd + (long)(t0 + 1) * 8 * F1;
-            dn_load_w<1, 16>(w5, wt5, F1, F1 >> 5, warp);
+            wt5 = Wd + (long)(t0 + 1) * 8 * F1;
+            dn_load_w<4>(w5, wt5, F1, ngf, warp, DN_WARPS);
           }
           if (threadIdx.x < 16 * 8) {
             const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
             if (m < A) {
               const int n = t0 * 8 + cc;
-              const float y = bf16r(dn_tile_val<1>(red, 0, m, cc));
+              const float y = bf16r(dn_tile_val(red, 0, m, cc, true));
               const float gt = __bfloat162float(mod_f[2 * D1 + n]);
               const float r = __bfloat162float(xe_s[m * D1 + n]);
               XE[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
@@ -754,8 +746,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       }
       // next layer's qkv tiles: in flight across the barrier (the next step's layer 0 is loaded in the final phase)
       if (l + 1 < L) {
-        qkv_tiles(Wqkv + p.qkv_ls, q_tb, wt1);
-        dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
+        wt1 = qkv_tile(Wqkv + p.qkv_ls, q_tb);
+        dn_load_w<4>(w1, wt1, D1, ng1, kpart, 8);
       }
       tick(12);
       bar.sync();
@@ -764,8 +756,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
 
     // ---------------- final: v = action_out_proj(adaRMS(XE)); x += dt * v (lap.py:665-667) ----------------
     if (step + 1 < S) {
-      qkv_tiles(reinterpret_cast<const bf16*>(p.qkv_w), q_tb, wt1);
-      dn_load_w<4, 4>(w1, wt1, D1, D1 >> 5, warp);
+      wt1 = qkv_tile(reinterpret_cast<const bf16*>(p.qkv_w), q_tb);
+      dn_load_w<4>(w1, wt1, D1, ng1, kpart, 8);
     }
     dn_stage(XE, D1, xe_s, D1, A, D1);
     dn_stage(mod_s + (long)(p.nm - 1) * 3 * D1, 0, mod_sm, 0, 1, 2 * D1);
@@ -773,7 +765,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
     __syncthreads();
     dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_sm);
     __syncthreads();
-    for (int o = warp; o < A * ad; o += 8) {
+    for (int o = warp; o < A * ad; o += DN_WARPS) {
       const int m = o / ad, j = o % ad;
       float acc = 0.f;
 #pragma unroll 8

@@ -36,5 +36,9 @@ names = ["prologue", "action_in", "P1 work", "P1 barrier", "P2 work", "P2 barrie
          "P3 barrier", "P4 work", "P4 barrier", "P5 work", "P5 barrier", "final"]
 out["phase_us_total_10_steps"] = {n: v / 1e3 for n, v in zip(names, prof)}
 out["phase_us_per_layer_step"] = {n: v / 1e3 / (10 * cfg.gemma.depth) for n, v in zip(names[2:14], prof[2:14])}
+sub = {16: "P1 stage+wait", 17: "P1 norm", 18: "P1 mma", 19: "P1 epilogue", 20: "P1 kv preload", 2: "P1 prefetch",
+       21: "P2b loop", 22: "P2b load_w", 6: "P2b prefetch", 24: "P2 stage+wait", 25: "P2 rope", 26: "P2 S mma", 27: "P2 softmax",
+       4: "P2 PV+store", 28: "P4 stage+wait", 29: "P4 norm", 30: "P4 passes", 10: "P4 w5+prefetch"}
+out["sub_us_per_layer_step"] = {n: prof[i] / 1e3 / (10 * cfg.gemma.depth) for i, n in sub.items()}
 out["error_flag"] = model.denoise_error_flag()
 print(json.dumps(out, indent=1))
