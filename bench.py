@@ -335,6 +335,9 @@ def run_train(args) -> None:
 
 
 def run_infer(args) -> None:
+    """Second headline metric: wall time of Policy-level `sample_actions` at batch 1 (host observation in, host actions
+    out, 10 Euler steps), p50/p90 over >= 100 timed calls after >= 10 warm-up calls.  After warm-up the call
+    is ONE CUDA graph: prefix pass (SigLIP + Gemma-2B, ~400 kernels) + the persistent denoise-loop kernel (K10)."""
     import numpy as np
     import torch
 
@@ -344,24 +347,67 @@ def run_infer(args) -> None:
     from lap_b200.model import LAP
     from lap_b200.observation import Observation
 
+    steps = args.steps if args.steps_given else 100
+    warmup = args.warmup if args.warmup_given else 10
     tc = get_config("lap_libero")
-    model = LAP(tc.model, seed=0)
-    b = synthetic_batch(tc.model, 1, step=0, with_langact=False)
+    cfg = tc.model
+    model = LAP(cfg, seed=0)
+    b = synthetic_batch(cfg, 1, step=0, with_langact=False)
     obs = Observation.from_dict(b)
     times = []
-    for i in range(args.warmup + args.steps):
+    for i in range(warmup + steps):
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         a = model.sample_actions(0, obs, num_steps=10, noise=b["noise"])
         a_host = a.cpu()
         dt = time.perf_counter() - t0
-        if i >= args.warmup:
+        if i >= warmup:
             times.append(dt * 1e3)
     times.sort()
+    # device-side split: the whole graph, and the denoise loop alone (K10 + the V transpose), CUDA events
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    g = model._infer_graphs.get((1, 10))
+    graph_ms = None
+    if g is not None:
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            g.replay()
+        e1.record(); torch.cuda.synchronize()
+        graph_ms = e0.elapsed_time(e1) / 20
+    denoise_ms, n0 = None, ops.launch_count
+    bufs = model._bufs
+    fused = model.use_denoise_megakernel and "dn.sync" in bufs
+    if fused:
+        x, Kc, Vc = bufs["inf.x"], bufs["inf.Kc"], bufs["inf.Vc"]
+        for _ in range(3):
+            model._denoise_loop_fused(x, Kc, Vc, bufs["inf.bits_s"], bufs["inf.pos_s"], 10, -0.1)
+        torch.cuda.synchronize(); e0.record()
+        for _ in range(20):
+            model._denoise_loop_fused(x, Kc, Vc, bufs["inf.bits_s"], bufs["inf.pos_s"], 10, -0.1)
+        e1.record(); torch.cuda.synchronize()
+        denoise_ms = e0.elapsed_time(e1) / 20
+    # algorithmic HBM bytes of the denoise loop: expert weights once per step, the adaRMS modulation weights once,
+    # the K / V^T cache once per (step, layer)   ("each step streams the expert weights")
+    e, L, nm = cfg.expert, cfg.gemma.depth, 2 * cfg.gemma.depth + 1
+    per_layer = 2 * ((e.num_heads + 2) * e.head_dim * e.width + e.width * e.num_heads * e.head_dim + 3 * e.width * e.mlp_dim)
+    kv = 2 * 2 * cfg.prefix_len * e.head_dim
+    dn_bytes = 10 * L * (per_layer + kv) + 2 * nm * 3 * e.width * e.width
+    peaks, _ = _peaks()
     line = {"metric": "action-chunk infer p50 ms", "value": times[len(times) // 2], "unit": "ms",
-            "p90": times[int(len(times) * 0.9)], "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+            "p90": times[int(len(times) * 0.9)], "n_gpus": 1, "steps": steps, "warmup": warmup,
             "higher_is_better": False, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "lap_libero sample_actions, batch 1, 2x224px cameras, 180-token prompt, 10 Euler steps"}}
+            "config": {"workload": "lap_libero sample_actions, batch 1, 2x224px cameras, 180-token prompt, 10 Euler steps",
+                       "cuda_graph": g is not None, "fused_denoise_loop": bool(fused)},
+            "device_ms": {"graph_replay": graph_ms, "denoise_loop": denoise_ms,
+                          "prefix_pass": (graph_ms - denoise_ms) if (graph_ms and denoise_ms) else None},
+            "e2e": {"value": times[len(times) // 2], "unit": "ms", "h2d_bytes_per_step": int(model.last_h2d_bytes),
+                    "d2h_bytes_per_step": int(a_host.numel() * 4)},
+            "roofline": None if not denoise_ms else {
+                "bound": "hbm", "kernel": "denoise_loop_kernel (K10: 10 Euler steps x 18 expert layers, one launch)",
+                "achieved": dn_bytes / (denoise_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                "frac": dn_bytes / (denoise_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                "algorithmic_bytes_per_launch": dn_bytes, "avg_launch_ms": denoise_ms,
+                "note": "latency/barrier-bound: 1083 grid barriers per launch; see profiles/r01_denoise_loop.md"}}
     print(json.dumps(line), flush=True)
 
 
@@ -374,6 +420,8 @@ def main():
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    args.steps_given = any(a == "--steps" or a.startswith("--steps=") for a in sys.argv[1:])
+    args.warmup_given = any(a == "--warmup" or a.startswith("--warmup=") for a in sys.argv[1:])
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":
         run_reference(args)

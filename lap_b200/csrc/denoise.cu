@@ -30,6 +30,7 @@
 #include "../../include/lapb200.h"
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace lapb {
 
@@ -843,7 +844,14 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
   LAPB_REQUIRE(per_sm >= 1, "denoise_loop: kernel does not fit on an SM (smem %zu)", smem);
   LAPB_CUDA_OK(cudaMemsetAsync(p.sync, 0, 2 * sizeof(uint32_t), STREAM(s)));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3((unsigned)num_sms());
+  // Grid: one CTA per SM by default.  128 CTAs balance LAP-3B's phases exactly (128 o/down tiles, 512 gate/up pairs);
+  // LAPB_DENOISE_CTAS overrides for experiments.
+  int ctas = num_sms();
+  if (const char* e = getenv("LAPB_DENOISE_CTAS")) {
+    const int v = atoi(e);
+    if (v >= 1 && v <= num_sms()) ctas = v;
+  }
+  cfg.gridDim = dim3((unsigned)ctas);
   cfg.blockDim = dim3(DN_THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = STREAM(s);
