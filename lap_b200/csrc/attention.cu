@@ -22,11 +22,49 @@ typedef __nv_bfloat16 bf16;
 //   positions: prefix cumsum(pm)-1 ; suffix sum(pma) + cumsum(sm) - 1
 // bits[b, i - row_begin, w] bit k  <->  key j = 32w + k
 // ------------------------------------------------------------------------------------------------
+// block-wide inclusive scan of v[0..n) (n <= 4 * 256) in shared memory: 4 consecutive elements per thread, warp shuffles
+__device__ __forceinline__ void block_scan_inclusive(int* v, int n, int* warp_tot /*[8]*/) {
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  for (int base = 0; base < n; base += 1024) {  // chunks of 1024, carried through warp_tot[8]
+    int x[4], sum = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = base + 4 * t + k;
+      x[k] = (j < n) ? v[j] : 0;
+      sum += x[k];
+    }
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += y;
+    }
+    __syncthreads();
+    if (lane == 31) warp_tot[w] = incl;
+    __syncthreads();
+    int off = (base > 0) ? warp_tot[8] : 0;
+    for (int k = 0; k < w; ++k) off += warp_tot[k];
+    int run = off + incl - sum;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int j = base + 4 * t + k;
+      run += x[k];
+      if (j < n) v[j] = run;
+    }
+    __syncthreads();
+    if (t == 255) warp_tot[8] = run;  // carry into the next chunk
+    __syncthreads();
+  }
+}
+
+// grid = (B, row chunks): every CTA rebuilds the (cheap) scans of its sample and writes the mask words of its rows.
 __global__ void __launch_bounds__(256)
 mask_build_kernel(const uint8_t* __restrict__ pm, const uint8_t* __restrict__ par, const uint8_t* __restrict__ pma,
                   const uint8_t* __restrict__ sm, const uint8_t* __restrict__ sar, uint32_t* __restrict__ bits,
                   int* __restrict__ positions, int P, int A, int W32, int row_begin, int infer_rows) {
   extern __shared__ int sh[];
+  __shared__ int warp_tot[9];
+  __shared__ int na_s;
   int T = P + A;
   int* cum = sh;            // [T]  cumsum of ar for prefix rows' view (prefix part) / suffix view (suffix part)
   int* valid_p = sh + T;    // [T]  pm (prefix view); suffix part = 0
@@ -36,17 +74,31 @@ mask_build_kernel(const uint8_t* __restrict__ pm, const uint8_t* __restrict__ pa
   const uint8_t* pmb = pm + (long)b * P;
   const uint8_t* parb = par + (long)b * P;
   const uint8_t* pmab = pma ? pma + (long)b * P : pmb;
-  if (threadIdx.x == 0) {
-    int c = 0, pc = 0, na = 0;
-    for (int j = 0; j < P; ++j) {
-      c += parb[j] ? 1 : 0;
-      cum[j] = c;
-      valid_p[j] = pmb[j] ? 1 : 0;
-      valid_a[j] = pmab[j] ? 1 : 0;
-      pc += valid_p[j];
-      pos[j] = pc - 1;
-      na += valid_a[j];
+  for (int j = threadIdx.x; j < P; j += 256) {
+    cum[j] = parb[j] ? 1 : 0;
+    valid_p[j] = pmb[j] ? 1 : 0;
+    valid_a[j] = pmab[j] ? 1 : 0;
+    pos[j] = valid_p[j];
+  }
+  __syncthreads();
+  block_scan_inclusive(cum, P, warp_tot);   // cumsum(ar) over the prefix
+  block_scan_inclusive(pos, P, warp_tot);   // cumsum(pm)
+  {  // na = sum(pma): block reduction
+    int part = 0;
+    for (int j = threadIdx.x; j < P; j += 256) part += valid_a[j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if ((threadIdx.x & 31) == 0) warp_tot[threadIdx.x >> 5] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int na = 0;
+      for (int k = 0; k < 8; ++k) na += warp_tot[k];
+      na_s = na;
     }
+    __syncthreads();
+  }
+  for (int j = threadIdx.x; j < P; j += 256) pos[j] -= 1;
+  if (threadIdx.x == 0) {  // the suffix is a handful of tokens
     int cs = 0, sc = 0;
     for (int j = 0; j < A; ++j) {
       cs += sar[(long)b * A + j] ? 1 : 0;
@@ -54,15 +106,19 @@ mask_build_kernel(const uint8_t* __restrict__ pm, const uint8_t* __restrict__ pa
       valid_p[P + j] = 0;
       valid_a[P + j] = sm[(long)b * A + j] ? 1 : 0;
       sc += valid_a[P + j];
-      pos[P + j] = na + sc - 1;
+      pos[P + j] = na_s + sc - 1;
     }
   }
   __syncthreads();
   int nrows = T - row_begin;
-  for (int i = row_begin + threadIdx.x; i < T; i += 256) positions[(long)b * nrows + (i - row_begin)] = pos[i];
-  long total = (long)nrows * W32;
+  if (blockIdx.y == 0)
+    for (int i = row_begin + threadIdx.x; i < T; i += 256) positions[(long)b * nrows + (i - row_begin)] = pos[i];
+  // rows of this CTA: a contiguous slice; one thread per 32-key word
+  const int rows_per = (nrows + gridDim.y - 1) / gridDim.y;
+  const int r0 = blockIdx.y * rows_per, r1 = min(nrows, r0 + rows_per);
+  long total = (long)max(0, r1 - r0) * W32;
   for (long idx = threadIdx.x; idx < total; idx += 256) {
-    int i = row_begin + (int)(idx / W32), w = (int)(idx % W32);
+    int i = row_begin + r0 + (int)(idx / W32), w = (int)(idx % W32);
     uint32_t word = 0;
     for (int k = 0; k < 32; ++k) {
       int j = w * 32 + k;
@@ -256,8 +312,13 @@ int lapb200_mask_build(const uint8_t* pm, const uint8_t* par, const uint8_t* pma
   LAPB_REQUIRE(A == 0 || (sm && sar), "mask_build: suffix masks missing");
   size_t smem = 4 * (size_t)(P + A) * sizeof(int);
   LAPB_REQUIRE(smem <= 48 * 1024, "mask_build: sequence too long (%ld tokens)", (long)(P + A));
-  mask_build_kernel<<<(unsigned)B, 256, smem, STREAM(s)>>>(pm, par, pma, sm, sar, bits, positions, (int)P, (int)A,
-                                                          (int)W32, (int)row_begin, (int)infer_rows);
+  // enough row chunks to fill the GPU at small batch (inference: B = 1), one chunk per sample at training batch sizes
+  long nrows = P + A - row_begin;
+  long chunks = (2L * num_sms() + B - 1) / B;
+  if (chunks > (nrows + 7) / 8) chunks = (nrows + 7) / 8;
+  if (chunks < 1) chunks = 1;
+  mask_build_kernel<<<dim3((unsigned)B, (unsigned)chunks), 256, smem, STREAM(s)>>>(
+      pm, par, pma, sm, sar, bits, positions, (int)P, (int)A, (int)W32, (int)row_begin, (int)infer_rows);
   LAPB_LAUNCH_OK("mask_build");
   return 0;
 }
