@@ -791,11 +791,20 @@ class LAP:
             Pm, Q, Kc, Vc = sv("P"), sv("Q"), sv("Kc"), sv("Vc")
             bsR, bsT, bsP = (Rq * hd, 0), (Tpad * hd, 0), (Rq * Tpad, 0)
             ops.gemm(dOc, Vc, dP, M=Rq, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=bsR, b_bs=bsT, c_bs=bsP)
-            ops.gemm(Pm, dOc, dVc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
-                     a_bs=bsP, b_bs=bsR, c_bs=bsT)
+            if not cfg.stop_action_to_vlm_grad:
+                ops.gemm(Pm, dOc, dVc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                         a_bs=bsP, b_bs=bsR, c_bs=bsT)
             ops.softmax_bwd(Pm, dP, dP, B * Rq, Tpad)
             ops.gemm(dP, Kc, dQ, M=Rq, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B, a_bs=bsP,
                      b_bs=bsT, c_bs=bsR)
+            if cfg.stop_action_to_vlm_grad:
+                # gemma.py:206-213,242-269: action-expert queries read expert 0's K and V through stop_gradient, so the
+                # [action rows x prefix keys] block of P and dS must not reach dV / dK (dQ above used the full dS).
+                # Both tensors are dead after this layer's two products: the block is cleared in place.
+                Pm.view(B, Rq, Tpad)[:, Pn * NH:, :Pn].zero_()
+                dP.view(B, Rq, Tpad)[:, Pn * NH:, :Pn].zero_()
+                ops.gemm(Pm, dOc, dVc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
+                         a_bs=bsP, b_bs=bsR, c_bs=bsT)
             ops.gemm(dP, Q, dKc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
                      a_bs=bsP, b_bs=bsR, c_bs=bsT)
             ops.rope_bwd(dQ, dKc, dVc, positions, self.timescale, dqkv0, dqkv1, B, Pn, A, Tpad, NH, hd, qscale)

@@ -209,9 +209,11 @@ def gated_residual(x, y, gate, bf16):
     return _r(x + _r(y * gate, bf16), bf16)
 
 
-def gemma_attention(p, cfgs, layer, xs, positions, attn_mask, kv_cache, bf16, pre="PaliGemma/llm/layers/attn/"):
-    """gemma.py:167-290 (stop_action_to_vlm_grad=False: forward identical either way).
-    xs: list per expert of [B,T_i,D_i] or None; attn_mask [B,T,S] bool; kv_cache (k,v) or None."""
+def gemma_attention(p, cfgs, layer, xs, positions, attn_mask, kv_cache, bf16, pre="PaliGemma/llm/layers/attn/",
+                    stop_action_to_vlm_grad=False):
+    """gemma.py:167-290.  xs: list per expert of [B,T_i,D_i] or None; attn_mask [B,T,S] bool; kv_cache (k,v) or None.
+    stop_action_to_vlm_grad (gemma.py:206-213,242-269): queries of experts > 0 see expert 0's K and V through
+    stop_gradient — the forward value is the same function, evaluated as two value products that are rounded separately."""
     qs, ks, vs = [], [], []
     for i, (x, c) in enumerate(zip(xs, cfgs)):
         if x is None:
@@ -236,9 +238,22 @@ def gemma_attention(p, cfgs, layer, xs, positions, attn_mask, kv_cache, bf16, pr
     qg = q.reshape(B, T, K, Nh // K, hd)
     logits = torch.einsum("btkgh,bskh->bkgts", qg, k)  # fp32
     assert attn_mask.shape == (B, T, k.shape[1]), (attn_mask.shape, q.shape, k.shape)
+    stop = stop_action_to_vlm_grad and xs[0] is not None and any(x is not None for x in xs[1:])
+    if stop:
+        P0 = xs[0].shape[1]  # expert-0 tokens come first (gemma.py:204)
+        logits0_i = torch.einsum("btkgh,bskh->bkgts", qg[:, P0:], k[:, :P0].detach())  # gemma.py:248-253
+        logits = torch.cat([logits[:, :, :, :P0], torch.cat([logits0_i, logits[:, :, :, P0:, P0:]], -1)], 3)
     masked = torch.where(attn_mask[:, None, None, :, :], logits, torch.tensor(BIG_NEG))
     probs = _r(torch.softmax(masked, dim=-1), bf16)
-    enc = _r(torch.einsum("bkgts,bskh->btkgh", probs, v), bf16).reshape(B, T, Nh, hd)
+    if stop:
+        cross = torch.zeros(T, k.shape[1], dtype=torch.bool)
+        cross[P0:, :P0] = True
+        probs_cross = probs * cross.to(probs.dtype)
+        probs_self = probs - probs_cross
+        enc = _r(_r(torch.einsum("bkgts,bskh->btkgh", probs_self, v), bf16)
+                 + _r(torch.einsum("bkgts,bskh->btkgh", probs_cross, v.detach()), bf16), bf16).reshape(B, T, Nh, hd)
+    else:
+        enc = _r(torch.einsum("bkgts,bskh->btkgh", probs, v), bf16).reshape(B, T, Nh, hd)
     out, start = [], 0
     for i, (x, c) in enumerate(zip(xs, cfgs)):
         if x is None:
@@ -261,7 +276,7 @@ def feed_forward(p, key, layer, x, bf16):
 
 
 def gemma_forward(p, cfgs, embedded, positions, mask, adarms_cond, bf16, kv_cache=None,
-                  pre="PaliGemma/llm/"):
+                  pre="PaliGemma/llm/", stop_action_to_vlm_grad=False):
     """gemma.Module.__call__ (gemma.py:455-531). Returns (outputs per expert, per-layer kv list)."""
     xs = [None if e is None else _r(e, bf16) for e in embedded]  # astype(embed_dtype), gemma.py:494
     depth = cfgs[0].depth
@@ -278,7 +293,7 @@ def gemma_forward(p, cfgs, embedded, positions, mask, adarms_cond, bf16, kv_cach
             pre_attn.append(h)
             gates.append(g)
         post, kv = gemma_attention(p, cfgs, l, pre_attn, positions, mask, None if kv_cache is None else kv_cache[l],
-                                   bf16, pre=lay + "attn/")
+                                   bf16, pre=lay + "attn/", stop_action_to_vlm_grad=stop_action_to_vlm_grad)
         new_cache.append(kv)
         xs = [None if x is None else gated_residual(x, y, g, bf16) for x, y, g in zip(xs, post, gates)]
         outs, gates = [], []
@@ -376,7 +391,8 @@ def compute_loss(p, cfg, obs, actions, noise, time, *, bf16: bool, softmax_dtype
     mask = build_combined_attention_mask(pre_mask, pre_ar, pre_mask_action, suf_mask, suf_ar)
     positions = build_combined_positions(pre_mask, pre_mask_action, suf_mask)
     (pre_out, suf_out), _ = gemma_forward(p, [cfg.gemma, cfg.expert], [pre_tok, suf_tok], positions, mask,
-                                          [None, cond], bf16)
+                                          [None, cond], bf16,
+                                          stop_action_to_vlm_grad=getattr(cfg, "stop_action_to_vlm_grad", False))
     metrics = {}
     # language loss (lap.py:209-289)
     tp = obs["tokenized_prompt"].long()

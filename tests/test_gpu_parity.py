@@ -263,6 +263,34 @@ def _grad_check(tc, ref, model, b, tol=TOL_GRAD):
             assert rel_err(g_eng[k], g_o[k]) < tol, (k, rel_err(g_eng[k], g_o[k]))
 
 
+@pytest.mark.parametrize("name", ["debug_tiny", "debug_small"])
+def test_stop_action_to_vlm_grad_gradients_match_oracle(name):
+    """The `lap` pre-training variant (config.py:616, gemma.py:206-213,242-269): the engine clears the
+    [action rows x prefix keys] block of P and dS before the dV / dK products; gradients vs the oracle's autograd with
+    stop_gradient, and vs the flag-off gradients (must differ on the VLM, agree on the action expert's MLPs)."""
+    import dataclasses
+    from lap_b200.model import LAP
+    from lap_b200.train import batch_from_dict, init_train_state
+    tc = get_config(name)
+    tc_stop = dataclasses.replace(tc, model=dataclasses.replace(tc.model, stop_action_to_vlm_grad=True))
+    ref = P.init_reference_params(tc.model, 5, reference_zero_init=False)
+    b = synthetic_batch(tc.model, 2, step=2)
+    model = LAP(tc_stop.model, init=False)
+    model.load_params(ref)
+    _grad_check(tc_stop, ref, model, b)
+    g_stop = {k: v.clone() for k, v in model.params_reference(model.G).items()}
+    model2 = LAP(tc.model, init=False)
+    model2.load_params(ref)
+    obs, actions, extra = batch_from_dict(b)
+    init_train_state(tc, model=model2)
+    model2.forward_backward(model2._stage(obs, actions, extra["noise"], extra["time"], with_loss=True))
+    g_plain = model2.params_reference(model2.G)
+    kv = "PaliGemma/llm/layers/attn/kv_einsum/w"
+    assert rel_err(g_stop[kv], g_plain[kv]) > 1e-3  # the action loss no longer reaches the VLM's K/V projection
+    mlp1 = "PaliGemma/llm/layers/mlp_1/linear"
+    assert rel_err(g_stop[mlp1], g_plain[mlp1]) < 2e-2  # same forward, same cotangents inside the action expert
+
+
 def test_edge_cases_empty_langact_dropped_camera_masked_samples():
     """Ragged inputs: a sample without lang-action tokens, a sample_mask=False sample, a dropped wrist camera."""
     tc, ref, model, b = _setup("debug_small", 3, seed=3, step=4)

@@ -166,6 +166,45 @@ def test_bf16_and_fp32_oracle_agree(tiny):
     assert abs(l32.item() - l16.item()) < 5e-3 * abs(l32.item())
 
 
+def test_stop_action_to_vlm_grad_blocks_exactly_the_action_loss_into_the_vlm(tiny):
+    """gemma.py:206-213,242-269 (`lap` config, config.py:616): action-expert queries read expert 0's K/V through
+    stop_gradient.  Consequences checked on the oracle: the forward value is unchanged; the action loss has ZERO gradient
+    w.r.t. every VLM parameter (SigLIP, Gemma-2B, embedding); the action expert's own gradients and the language-loss
+    gradients are what they were."""
+    import dataclasses
+    tc, ref, b = tiny
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    args = (obs_for_oracle(b), t(b["actions"]), t(b["noise"]), t(b["time"]))
+
+    def grads(cfg):
+        p = {k: v.detach().clone().requires_grad_(True) for k, v in ref.items()}
+        loss, _ = O.compute_loss(p, cfg, *args, bf16=False)
+        loss.backward()
+        return loss.detach(), {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in p.items()}
+
+    base = dataclasses.replace(tc.model, language_loss_weight=0.0)  # action loss only
+    l0, g0 = grads(base)
+    l1, g1 = grads(dataclasses.replace(base, stop_action_to_vlm_grad=True))
+    assert abs(l0.item() - l1.item()) < 1e-6 * abs(l0.item())
+    expert = lambda k: (k.startswith("PaliGemma/llm/") and any(s in k for s in ("einsum_1", "mlp_1", "norm_1"))) or \
+        k.split("/")[0] in ("action_in_proj", "action_out_proj", "time_mlp_in", "time_mlp_out")
+    n_vlm = 0
+    for k in ref:
+        if expert(k):
+            assert rel_err(g1[k], g0[k]) < 1e-5, k
+        else:
+            n_vlm += 1
+            assert g1[k].abs().max() == 0, k  # nothing of the action loss reaches the VLM
+    assert n_vlm > 10 and any(g0[k].abs().max() > 0 for k in ref if not expert(k))
+    # language loss only: the flag changes nothing
+    lang = dataclasses.replace(tc.model, action_loss_weight=0.0)
+    _, ga = grads(lang)
+    _, gb = grads(dataclasses.replace(lang, stop_action_to_vlm_grad=True))
+    for k in ref:
+        if ga[k].abs().max() > 0:
+            assert rel_err(gb[k], ga[k]) < 1e-5, k
+
+
 def test_training_path_equals_cached_inference_path(tiny):
     """Reference-implied invariant (SURVEY §8c ii): with no lang-action tokens, the suffix outputs of the joint
     [prefix,suffix] pass equal those of prefix-KV-cache + suffix-only pass."""
