@@ -741,12 +741,10 @@ class LAP:
         dact = self.buf("bwd.dact", (Mg, F))
         dh = self.buf("bwd.dh", (Mg, D))
         dqkv0 = self.buf("bwd.dqkv0", (Mg, QKV))
-        dO0 = self.buf("bwd.dO0", (Mg, NH * hd))
         dyE = self.buf("bwd.dyE", (Me, D1))
         dactE = self.buf("bwd.dactE", (Me, F1))
         dhE = self.buf("bwd.dhE", (Me, D1))
         dqkv1 = self.buf("bwd.dqkv1", (Me, QKV))
-        dO1 = self.buf("bwd.dO1", (Me, NH * hd))
         dOc = self.buf("bwd.dOc", (B, Rq, hd))
         dP = self.buf("bwd.dP", (B, Rq, Tpad))
         dQ = self.buf("bwd.dQ", (B, Rq, hd))
@@ -780,13 +778,14 @@ class LAP:
             # ===== attention output projections =====
             O0, O1 = sv("O0"), sv("O1")
             self._wgrad(dX, O0, self.g("g.o_w", l), Mg, D, NH * hd)
-            self._dgrad(dX, self.w("g.o_w", l), dO0, Mg, D, NH * hd)
+            # d(attention output), written by the two dgrad GEMMs straight into the stacked [B, (P+A)*NH, hd] layout
+            # (one batch entry per sample: rows [0, P) from the prefix expert, [P, P+A) from the action expert)
+            self._dgrad(dX, self.w("g.o_w", l), dOc, Pn, D, NH * hd, batch_i=B, a_bs=(Pn * D, 0), c_bs=(Rq * hd, 0))
             ops.gated_bwd(dXE, sv("yEa"), mod.view(-1)[(2 * l) * 3 * D1 + 2 * D1:], nm3, dyE,
                           dmod.view(-1)[(2 * l) * 3 * D1 + 2 * D1:], nm3, B, A, D1)
             self._wgrad(dyE, O1, self.g("e.o_w", l), Me, D1, NH * hd)
-            self._dgrad(dyE, self.w("e.o_w", l), dO1, Me, D1, NH * hd)
-            dOc.view(B, Rq * hd)[:, : Pn * NH * hd].copy_(dO0.view(B, Pn * NH * hd))
-            dOc.view(B, Rq * hd)[:, Pn * NH * hd:].copy_(dO1.view(B, A * NH * hd))
+            self._dgrad(dyE, self.w("e.o_w", l), dOc.view(-1)[Pn * NH * hd:], A, D1, NH * hd, batch_i=B,
+                        a_bs=(A * D1, 0), c_bs=(Rq * hd, 0))
             # ===== shared attention =====
             Pm, Q, Kc, Vc = sv("P"), sv("Q"), sv("Kc"), sv("Vc")
             bsR, bsT, bsP = (Rq * hd, 0), (Tpad * hd, 0), (Rq * Tpad, 0)
@@ -995,6 +994,10 @@ class LAP:
             ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
             Q = self.buf("inf.Qp", (B, Pn, NH, hd))
             ops.rope_fwd(qkv0, None, positions, self.timescale, Q, Kc, Vc, B, Pn, 0, Tpad, NH, hd, 0, qscale)
+            if l == g.depth - 1:
+                # sample_actions consumes only the KV cache of the prefix pass (lap.py:627 discards the outputs): the
+                # last layer's attention, output projection and MLP feed nothing
+                return None
             O0 = self.buf("inf.O0", (Mg, NH * hd))
             if hd == 256 and self.use_fused_attention:
                 ops.fa_gemma_fwd(Q, Kc, Vc, bits, None, O0, O0, B, R, NH, Pn, Pn, Tpad, W32, R, hd)
