@@ -4,16 +4,24 @@
 //   O = P V   (tcgen05, P staged in shared memory as the A operand, V read MN-major straight from the cache layout)
 //
 // The 8 query heads of a token share the KV head, so they are stacked into the MMA M dimension: a CTA owns 128
-// query rows (16 tokens x 8 heads) of one sample and walks the keys in tiles of 64, K/V tiles double-buffered in
-// shared memory by TMA.  The softmax is TWO-PASS: pass 1 only accumulates the row max / sum (online), pass 2
-// recomputes S and forms p = exp(s - max) / sum rounded to bf16 — exactly the reference's rounding point — so the
-// result is bit-compatible with the unfused (GEMM + softmax + GEMM) path, and P can be written out for the backward
-// pass with a TMA store straight from the swizzled A-operand tile.  Attention is 2 % of the model FLOPs, so spending
-// a second QK^T to avoid rescaling the 256-column O accumulator in TMEM is the cheap choice.
+// query rows (16 tokens x 8 heads) of one sample.  The softmax is TWO-PASS: pass 1 only accumulates the row max / sum
+// (online), pass 2 recomputes S and forms p = exp(s - max) / sum rounded to bf16 — exactly the reference's rounding
+// point — so the result is bit-compatible with the unfused (GEMM + softmax + GEMM) path, and P can be written out for
+// the backward pass with a TMA store straight from the swizzled A-operand tile.
 //
-// Warp roles (384 threads): warps 0-7 softmax/epilogue — two warpgroups, thread == query row == TMEM lane, warpgroup g
-// owns key columns [32g, 32g+32) of every 64-key tile so two warps share each scheduler and hide each other's
-// MUFU/ALU latency; warp 8 TMA producer, warp 9 MMA issuer, warp 10 TMEM allocator.
+// Shape of the MMAs (v2).  A tcgen05.mma with M = 128 occupies the issue/operand path for ~128 cycles whatever its N
+// (measured: the 64-key S tiles of v1 took the same time with N = 16, 32, 64 or 128), so v1's 16 N = 64 instructions per
+// 64 keys left the tensor pipe 70 % idle.  Here S is produced 256 KEYS at a time: K is streamed through shared memory in
+// 64-dim slices of 256 keys ([256 keys x 128 B] = 32 KB per stage, the K loop of a GEMM), 16 instructions of N = 256 per
+// chunk; P V keeps its 64-key steps (4 instructions of N = 256 dims).  One ring of four 32 KB stages carries the K slices
+// and the V tiles in the order the MMA warp consumes them.
+//   TMEM (512 columns): pass 1 double-buffers S (2 x 256); pass 2 uses [0,256) for S and [256,512) for O.
+//   softmax: four warpgroups, thread == query row == TMEM lane, warpgroup w owns keys [64w, 64w+64) of every 256-key chunk
+//   — i.e. exactly one P sub-tile, which it writes (one 128-byte swizzled row per thread) when the single P buffer is free;
+//   the S slices of the NEXT chunk are issued between P V (j,0) and P V (j,1) so the tensor pipe has work during the P
+//   hand-offs.
+// Warp roles (608 threads): warps 0-15 softmax/epilogue, warp 16 TMA producer, warp 17 MMA issuer (whole warp, elected
+// lane issues), warp 18 TMEM allocator.
 #include "../../include/lapb200.h"
 #include "common.cuh"
 #include "host_util.h"
@@ -23,16 +31,21 @@ namespace lapb {
 typedef __nv_bfloat16 bf16;
 #define BIG_NEG (-2.3819763e38f)
 
-constexpr int FA_QT = 128;  // query rows per CTA
-constexpr int FA_KT = 64;   // keys per tile
-constexpr int FA_HD = 256;  // head dim
-constexpr int FA_Q_BYTES = FA_QT * FA_HD * 2;      // 64 KB: 4 k-chunks of [128 rows x 128 B]
-constexpr int FA_KV_BYTES = FA_KT * FA_HD * 2;     // 32 KB per stage
+constexpr int FA_QT = 128;   // query rows per CTA
+constexpr int FA_KT = 64;    // keys per P V step (= keys per softmax warpgroup and chunk)
+constexpr int FA_KC = 256;   // keys per S chunk
+constexpr int FA_HD = 256;   // head dim
+constexpr int FA_WG = 4;     // softmax warpgroups
+constexpr int FA_SOFT = 128 * FA_WG;
+constexpr int FA_THREADS = FA_SOFT + 96;
+constexpr int FA_NST = 4;                          // ring stages
+constexpr int FA_Q_BYTES = FA_QT * FA_HD * 2;      // 64 KB: 4 dim-chunks of [128 rows x 128 B]
+constexpr int FA_ST_BYTES = 32 * 1024;             // a K slice [256 keys x 64 dims] or a V tile [64 keys x 256 dims]
 constexpr int FA_P_BYTES = FA_QT * FA_KT * 2;      // 16 KB
-constexpr int FA_SMEM = FA_Q_BYTES + 4 * FA_KV_BYTES + FA_P_BYTES + 1024 + 256 + 2048;  // + (m,l) exchange
+constexpr int FA_SMEM = FA_Q_BYTES + FA_NST * FA_ST_BYTES + FA_P_BYTES + 1024 + 512 + FA_WG * 1024;
 
 struct FaArgs {
-  int B, R, G, Tq, S_len, Tpad, W32, NT;
+  int B, R, G, Tq, S_len, Tpad, W32, NCH;
   const uint32_t* bits;
   bf16* O0;
   bf16* O1;
@@ -49,57 +62,60 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FA_SOFT) : "memory"); }
+__device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory"); }
 
-__global__ void __launch_bounds__(384, 1)
+__global__ void __launch_bounds__(FA_THREADS, 1)
 fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const FaArgs a) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
-  uint8_t* Ks = smem + FA_Q_BYTES;
-  uint8_t* Vs = Ks + 2 * FA_KV_BYTES;
-  uint8_t* Ps = Vs + 2 * FA_KV_BYTES;
+  uint8_t* Ring = smem + FA_Q_BYTES;
+  uint8_t* Ps = Ring + FA_NST * FA_ST_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + FA_P_BYTES);
   uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;    // [2]
-  uint64_t* k_empty = bars + 3;   // [2]
-  uint64_t* v_full = bars + 5;    // [2]
-  uint64_t* v_empty = bars + 7;   // [2]
-  uint64_t* s_full = bars + 9;    // [2]
-  uint64_t* s_empty = bars + 11;  // [2]
-  uint64_t* p_full = bars + 13;
-  uint64_t* p_empty = bars + 14;
-  uint64_t* o_full = bars + 15;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  uint64_t* r_full = bars + 1;     // [4] ring stage filled by TMA
+  uint64_t* r_empty = bars + 5;    // [4] ring stage consumed by the MMAs
+  uint64_t* s_full = bars + 9;     // [2] S slot written
+  uint64_t* s_empty = bars + 11;   // [2] S slot read by every softmax thread
+  uint64_t* p_full = bars + 13;    // [4] P sub-tile w written
+  uint64_t* pv_done = bars + 17;   // [4] P V of sub-tile w retired (P buffer free again)
+  uint64_t* st_done = bars + 21;   // [4] TMA store of sub-tile w has read the P buffer
+  uint64_t* o_full = bars + 25;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
+  float* stat = reinterpret_cast<float*>(bars + 64);  // [FA_WG][128][2] (m, l) exchange between the warpgroups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int q0 = blockIdx.x * FA_QT;
-  const int NT = a.NT;
+  const int NCH = a.NCH;
+  constexpr int W_TMA = 4 * FA_WG, W_MMA = W_TMA + 1, W_ALLOC = W_TMA + 2;
+  const int U0 = (NCH + 1) / 2;  // uses of S slot 0 in pass 1
 
-  if (warp == 8 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmK);
     tma_prefetch_desc(&tmV);
   }
-  if (warp == 9 && lane == 0) {
+  if (warp == W_MMA && lane == 0) {
     mbar_init(q_full, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&k_full[i], 1);
-      mbar_init(&k_empty[i], 1);
-      mbar_init(&v_full[i], 1);
-      mbar_init(&v_empty[i], 1);
-      mbar_init(&s_full[i], 1);
-      mbar_init(&s_empty[i], 256);
+    for (int i = 0; i < FA_NST; ++i) {
+      mbar_init(&r_full[i], 1);
+      mbar_init(&r_empty[i], 1);
+      mbar_init(&p_full[i], 1);
+      mbar_init(&pv_done[i], 1);
+      mbar_init(&st_done[i], 1);
     }
-    mbar_init(p_full, 1);
-    mbar_init(p_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1);
+      mbar_init(&s_empty[i], FA_SOFT);
+    }
     mbar_init(o_full, 1);
     fence_barrier_init();
     fence_proxy_async();
   }
-  if (warp == 10) {
+  if (warp == W_ALLOC) {
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
@@ -107,85 +123,97 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tmem_O = tmem_base + 128;  // S buffers: columns [0,64) and [64,128); O: [128, 384)
+  const uint32_t tmem_O = tmem_base + 256;  // pass 2: S in columns [0,256), O in [256,512)
+  auto chunk_keys = [&](int j) { return min(FA_KC, a.Tpad - j * FA_KC); };  // multiple of 64
 
-  if (warp == 8) {
-    // ===================== TMA producer =====================
+  if (warp == W_TMA) {
+    // ===================== TMA producer: one ring, loads in the order the MMA warp consumes them =====================
     if (lane == 0) {
       mbar_expect_tx(q_full, FA_Q_BYTES);
 #pragma unroll
       for (int c = 0; c < 4; ++c) tma_load_4d(Qs + c * (FA_QT * 128), &tmQ, q_full, c * 64, q0, b, 0);
       int it = 0;
-      for (int pass = 0; pass < 2; ++pass) {
-        for (int i = 0; i < NT; ++i, ++it) {
-          const int st = it & 1;
-          const uint32_t ph = (it >> 1) & 1;
-          mbar_wait(&k_empty[st], ph ^ 1);
-          mbar_expect_tx(&k_full[st], FA_KV_BYTES);
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            tma_load_4d(Ks + st * FA_KV_BYTES + c * (FA_KT * 128), &tmK, &k_full[st], c * 64, i * FA_KT, b, 0);
-          if (pass == 1) {
-            const int vst = i & 1;
-            const uint32_t vph = (i >> 1) & 1;
-            mbar_wait(&v_empty[vst], vph ^ 1);
-            mbar_expect_tx(&v_full[vst], FA_KV_BYTES);
-#pragma unroll
-            for (int c = 0; c < 4; ++c)  // 64-dim atoms of the MN-major B operand: [64 keys x 128 B] each
-              tma_load_4d(Vs + vst * FA_KV_BYTES + c * (FA_KT * 128), &tmV, &v_full[vst], c * 64, i * FA_KT, b, 0);
-          }
+      auto load_k_chunk = [&](int j) {  // four 64-dim slices of 256 keys
+        for (int c = 0; c < 4; ++c, ++it) {
+          const int st = it & (FA_NST - 1);
+          mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
+          mbar_expect_tx(&r_full[st], FA_ST_BYTES);
+          tma_load_4d(Ring + st * FA_ST_BYTES, &tmK, &r_full[st], c * 64, j * FA_KC, b, 0);
         }
+      };
+      auto load_v_tile = [&](int key0) {  // [64 keys x 256 dims]: 4 atoms of 64 dims ([64 keys x 128 B] each)
+        const int st = it & (FA_NST - 1);
+        mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
+        mbar_expect_tx(&r_full[st], FA_ST_BYTES);
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+          tma_load_4d(Ring + st * FA_ST_BYTES + c * (FA_KT * 128), &tmV, &r_full[st], c * 64, key0, b, 0);
+        ++it;
+      };
+      for (int j = 0; j < NCH; ++j) load_k_chunk(j);  // pass 1
+      load_k_chunk(0);                                // pass 2
+      for (int j = 0; j < NCH; ++j) {
+        const int ns = chunk_keys(j) / FA_KT;
+        load_v_tile(j * FA_KC);
+        if (j + 1 < NCH) load_k_chunk(j + 1);
+        for (int s = 1; s < ns; ++s) load_v_tile(j * FA_KC + s * FA_KT);
       }
     }
-  } else if (warp == 9) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idescS = make_idesc_bf16(FA_QT, FA_KT, 0, 0);
-      constexpr uint32_t idescPV = make_idesc_bf16(FA_QT, FA_HD, 0, 1);
-      const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), p_addr = smem_u32(Ps);
-      mbar_wait(q_full, 0);
-      auto issue_S = [&](int it) {
-        const int st = it & 1;
-        const uint32_t ph = (it >> 1) & 1;
-        mbar_wait(&k_full[st], ph);
-        mbar_wait(&s_empty[st], ph ^ 1);
-        tc_fence_after();
-        const uint32_t d = tmem_base + st * FA_KT;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-#pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            uint64_t da = make_smem_desc_sw128(q_addr + c * (FA_QT * 128) + kk * 32, 16, 1024);
-            uint64_t db = make_smem_desc_sw128(k_addr + st * FA_KV_BYTES + c * (FA_KT * 128) + kk * 32, 16, 1024);
-            umma_bf16(d, da, db, idescS, (c | kk) != 0 ? 1u : 0u);
-          }
-        }
-        umma_commit(&k_empty[st]);
-        umma_commit(&s_full[st]);
-      };
-      for (int it = 0; it < NT; ++it) issue_S(it);  // pass 1: logits only
-      issue_S(NT);                                   // pass 2, software-pipelined: S(i+1) is issued before PV(i)
-      for (int i = 0; i < NT; ++i) {
-        if (i + 1 < NT) issue_S(NT + i + 1);
-        const int vst = i & 1;
-        mbar_wait(p_full, i & 1);
-        mbar_wait(&v_full[vst], (i >> 1) & 1);
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer (whole warp; an elected lane issues) =====================
+    const uint32_t q_addr = smem_u32(Qs), ring_addr = smem_u32(Ring), p_addr = smem_u32(Ps);
+    constexpr uint32_t idescPV = make_idesc_bf16(FA_QT, FA_HD, 0, 1);
+    mbar_wait(q_full, 0);
+    int it = 0;
+    auto issue_S = [&](int j, int slot, int use) {
+      const uint32_t idescS = make_idesc_bf16(FA_QT, chunk_keys(j), 0, 0);
+      mbar_wait(&s_empty[slot], (use & 1) ^ 1);
+      const uint32_t d = tmem_base + slot * FA_KC;
+      for (int c = 0; c < 4; ++c, ++it) {
+        const int st = it & (FA_NST - 1);
+        mbar_wait(&r_full[st], (it / FA_NST) & 1);
         tc_fence_after();
 #pragma unroll
         for (int kk = 0; kk < 4; ++kk) {
-          uint64_t da = make_smem_desc_sw128(p_addr + kk * 32, 16, 1024);
-          // V tile: MN-major, 4 atoms of 64 dims ([64 keys x 128 B] = 8 KB apart), 16 keys per step = 2 KB
-          uint64_t db = make_smem_desc_sw128(v_addr + vst * FA_KV_BYTES + kk * (16 * 128), FA_KT * 128, 1024);
-          umma_bf16(tmem_O, da, db, idescPV, (i | kk) != 0 ? 1u : 0u);
+          uint64_t da = make_smem_desc_sw128(q_addr + c * (FA_QT * 128) + kk * 32, 16, 1024);
+          uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * 32, 16, 1024);
+          umma_bf16_elect(d, da, db, idescS, (c | kk) != 0 ? 1u : 0u);
         }
-        umma_commit(p_empty);
-        umma_commit(&v_empty[vst]);
+        umma_commit_elect(&r_empty[st]);
       }
-      umma_commit(o_full);
+      umma_commit_elect(&s_full[slot]);
+    };
+    auto issue_PV = [&](int j, int s, uint32_t accumulate) {
+      const int st = it & (FA_NST - 1);
+      mbar_wait(&p_full[s], j & 1);
+      mbar_wait(&r_full[st], (it / FA_NST) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        uint64_t da = make_smem_desc_sw128(p_addr + kk * 32, 16, 1024);
+        // V tile: MN-major, 4 atoms of 64 dims ([64 keys x 128 B] = 8 KB apart), 16 keys per step = 2 KB
+        uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * (16 * 128), FA_KT * 128, 1024);
+        umma_bf16_elect(tmem_O, da, db, idescPV, (accumulate | (uint32_t)kk) != 0 ? 1u : 0u);
+      }
+      umma_commit_elect(&r_empty[st]);
+      umma_commit_elect(&pv_done[s]);
+      ++it;
+    };
+    for (int j = 0; j < NCH; ++j) issue_S(j, j & 1, j >> 1);  // pass 1: logits only, S double-buffered
+    issue_S(0, 0, U0);                                         // pass 2
+    if (NCH / 2 > 0) mbar_wait(&s_empty[1], ((NCH / 2) - 1) & 1);  // O reuses the columns of S slot 1
+    uint32_t acc = 0;
+    for (int j = 0; j < NCH; ++j) {
+      const int ns = chunk_keys(j) / FA_KT;
+      issue_PV(j, 0, acc);
+      acc = 1;
+      if (j + 1 < NCH) issue_S(j + 1, 0, U0 + j + 1);  // keeps the tensor pipe busy during the P hand-offs below
+      for (int s = 1; s < ns; ++s) issue_PV(j, s, 1);
     }
-  } else if (warp < 8) {
-    // ===================== softmax + epilogue: thread == (query row, 32-key column half) =====================
-    const int wg = warp >> 2;                 // column half of every key tile / dim half of the output
+    umma_commit_elect(o_full);
+  } else if (warp < W_TMA) {
+    // ===================== softmax + epilogue: thread == (query row, 64-key slice of every chunk) =====================
+    const int wg = warp >> 2;
     const int r = (warp & 3) * 32 + lane;     // query row of the tile == TMEM lane
     const long grow = (long)q0 + r;
     const bool valid_row = grow < a.R;
@@ -194,112 +222,134 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t* mrow = a.bits + ((long)b * a.Tq + tok) * a.W32;
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float LOG2E = 1.4426950408889634f;
-    float* stat = reinterpret_cast<float*>(tmem_slot + 4);  // [2][128][2] (m, l) exchange between the warpgroups
     float m = -3.4e38f, l = 0.f;
-    // ---- pass 1: running max / sum over this warpgroup's columns ----
-    for (int it = 0; it < NT; ++it) {
-      const int sb = it & 1;
-      mbar_wait(&s_full[sb], (it >> 1) & 1);
+    // ---- pass 1: running max / sum over this warpgroup's keys ----
+    for (int j = 0; j < NCH; ++j) {
+      const int slot = j & 1;
+      const bool active = wg * FA_KT < chunk_keys(j);
+      mbar_wait(&s_full[slot], (j >> 1) & 1);
       tc_fence_after();
-      uint32_t sv[32];
-      tmem_ld_32x32(tmem_base + lane_base + sb * FA_KT + wg * 32, sv);
-      tmem_ld_wait();
+#pragma unroll
+      for (int hf = 0; hf < 2; ++hf) {
+        if (active) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_base + lane_base + slot * FA_KC + wg * FA_KT + hf * 32, sv);
+          tmem_ld_wait();
+          const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
+          const uint32_t w = mrow[key0 >> 5];
+          const int nvalid = a.S_len - key0;  // columns [0, nvalid) are real keys
+          if (w != 0xFFFFFFFFu) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (!((w >> c) & 1u)) sv[c] = __float_as_uint(BIG_NEG);
+          }
+          float tmax = -3.4e38f;
+          if (nvalid >= 32) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) tmax = fmaxf(tmax, __uint_as_float(sv[c]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < nvalid) tmax = fmaxf(tmax, __uint_as_float(sv[c]));
+          }
+          const float m_new = fmaxf(m, tmax);
+          float sum = 0.f;
+          // (x - m) is formed BEFORE scaling by log2(e): for a fully masked row m = -2.38e38 and m*log2(e) would overflow
+          if (nvalid >= 32) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) sum += exp2f((__uint_as_float(sv[c]) - m_new) * LOG2E);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c)
+              if (c < nvalid) sum += exp2f((__uint_as_float(sv[c]) - m_new) * LOG2E);
+          }
+          l = l * exp2f((m - m_new) * LOG2E) + sum;
+          m = m_new;
+        }
+      }
       tc_fence_before();
-      mbar_arrive_relaxed(&s_empty[sb]);
-      const int key0 = it * FA_KT + wg * 32;
-      const uint32_t w = mrow[2 * it + wg];
-      const int nvalid = a.S_len - key0;  // columns [0, nvalid) of this half are real keys
-      float tmax = -3.4e38f;
-      if (w != 0xFFFFFFFFu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (!((w >> j) & 1u)) sv[j] = __float_as_uint(BIG_NEG);
-      }
-      if (nvalid >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) tmax = fmaxf(tmax, __uint_as_float(sv[j]));
-      }
-      const float m_new = fmaxf(m, tmax);
-      float sum = 0.f;
-      // (x - m) is formed BEFORE scaling by log2(e): for a fully masked row m = -2.38e38 and m*log2(e) would overflow
-      if (nvalid >= 32) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sum += exp2f((__uint_as_float(sv[j]) - m_new) * LOG2E);
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (j < nvalid) sum += exp2f((__uint_as_float(sv[j]) - m_new) * LOG2E);
-      }
-      l = l * exp2f((m - m_new) * LOG2E) + sum;
-      m = m_new;
+      mbar_arrive_relaxed(&s_empty[slot]);
     }
-    // combine the two column halves
+    // combine the key slices of the warpgroups
     stat[(wg * 128 + r) * 2 + 0] = m;
     stat[(wg * 128 + r) * 2 + 1] = l;
     softmax_bar();
     {
-      const float mo = stat[((wg ^ 1) * 128 + r) * 2 + 0], lo = stat[((wg ^ 1) * 128 + r) * 2 + 1];
-      const float mf = fmaxf(m, mo);
-      l = l * exp2f((m - mf) * LOG2E) + lo * exp2f((mo - mf) * LOG2E);
+      float mf = m;
+#pragma unroll
+      for (int o = 0; o < FA_WG; ++o) mf = fmaxf(mf, stat[(o * 128 + r) * 2 + 0]);
+      float lf = 0.f;
+#pragma unroll
+      for (int o = 0; o < FA_WG; ++o) lf += stat[(o * 128 + r) * 2 + 1] * exp2f((stat[(o * 128 + r) * 2 + 0] - mf) * LOG2E);
+      l = lf;
       m = mf;
     }
-    // ---- pass 2: p = exp(s - max) / sum -> bf16 -> smem (A operand of P V) [+ TMA store for the backward] ----
+    // ---- pass 2: p = exp(s - max) / sum -> bf16 -> this warpgroup's P sub-tile [+ TMA store for the backward] ----
     const float inv = 1.0f / l;
-    for (int i = 0; i < NT; ++i) {
-      const int it = NT + i;
-      const int sb = it & 1;
-      mbar_wait(&s_full[sb], (it >> 1) & 1);
+    const bool leader = (warp & 3) == 0 && lane == 0;
+    for (int j = 0; j < NCH; ++j) {
+      const int nkeys = chunk_keys(j);
+      const bool active = wg * FA_KT < nkeys;
+      mbar_wait(&s_full[0], (U0 + j) & 1);
       tc_fence_after();
-      uint32_t sv[32];
-      tmem_ld_32x32(tmem_base + lane_base + sb * FA_KT + wg * 32, sv);
-      tmem_ld_wait();
-      tc_fence_before();
-      mbar_arrive_relaxed(&s_empty[sb]);
-      const int key0 = i * FA_KT + wg * 32;
-      const uint32_t w = mrow[2 * i + wg];
-      const int nvalid = a.S_len - key0;
-      if (w != 0xFFFFFFFFu) {
+      uint32_t pk[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (!((w >> j) & 1u)) sv[j] = __float_as_uint(BIG_NEG);
-      }
-      uint32_t pk[16];
+      for (int hf = 0; hf < 2; ++hf) {
+        if (active) {
+          uint32_t sv[32];
+          tmem_ld_32x32(tmem_base + lane_base + wg * FA_KT + hf * 32, sv);
+          tmem_ld_wait();
+          const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
+          const uint32_t w = mrow[key0 >> 5];
+          const int nvalid = a.S_len - key0;
+          if (w != 0xFFFFFFFFu) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 2) {
-        float p0 = exp2f((__uint_as_float(sv[j]) - m) * LOG2E) * inv;
-        float p1 = exp2f((__uint_as_float(sv[j + 1]) - m) * LOG2E) * inv;
-        if (j >= nvalid) p0 = 0.f;
-        if (j + 1 >= nvalid) p1 = 0.f;
-        pk[j >> 1] = pack_bf16x2(p0, p1);
-      }
-      // the P tile may be overwritten once the previous P V MMAs and the previous TMA store have read it
-      if (threadIdx.x == 0) {
-        mbar_wait(p_empty, (i & 1) ^ 1);
-        if (a.write_p) tma_store_wait_read();
-      }
-      softmax_bar();
-      // K-major, 128B-swizzled A tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
-      uint8_t* prow = Ps + r * 128;
+            for (int c = 0; c < 32; ++c)
+              if (!((w >> c) & 1u)) sv[c] = __float_as_uint(BIG_NEG);
+          }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int cc = wg * 4 + c;
-        *reinterpret_cast<uint4*>(prow + ((cc ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      }
-      fence_proxy_async();
-      softmax_bar();
-      if (threadIdx.x == 0) {
-        if (a.write_p) {
-          tma_store_4d(&tmP, Ps, i * FA_KT, q0, b, 0);
-          tma_store_commit();
+          for (int c = 0; c < 32; c += 2) {
+            float p0 = exp2f((__uint_as_float(sv[c]) - m) * LOG2E) * inv;
+            float p1 = exp2f((__uint_as_float(sv[c + 1]) - m) * LOG2E) * inv;
+            if (c >= nvalid) p0 = 0.f;
+            if (c + 1 >= nvalid) p1 = 0.f;
+            pk[hf * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
+          }
         }
-        mbar_arrive(p_full);
+      }
+      tc_fence_before();
+      mbar_arrive_relaxed(&s_empty[0]);  // S(j) is in registers: the next chunk's S may overwrite the slot
+      if (active) {
+        // the single P buffer is free once the previous sub-tile's P V has retired (and its TMA store has read it)
+        if (wg > 0) {
+          mbar_wait(&pv_done[wg - 1], j & 1);
+          if (a.write_p) mbar_wait(&st_done[wg - 1], j & 1);
+        } else if (j > 0) {
+          const int last = chunk_keys(j - 1) / FA_KT - 1;
+          mbar_wait(&pv_done[last], (j - 1) & 1);
+          if (a.write_p) mbar_wait(&st_done[last], (j - 1) & 1);
+        }
+        // K-major, 128B-swizzled A tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
+        uint8_t* prow = Ps + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async();
+        wg_bar(wg);
+        if (leader) {
+          if (a.write_p) {
+            tma_store_4d(&tmP, Ps, j * FA_KC + wg * FA_KT, q0, b, 0);
+            tma_store_commit();
+          }
+          mbar_arrive(&p_full[wg]);
+          if (a.write_p) {
+            tma_store_wait_read();
+            mbar_arrive(&st_done[wg]);
+          }
+        }
       }
     }
-    // ---- epilogue: O (fp32, TMEM) -> bf16 rows; warpgroup g stores dims [128g, 128g + 128) ----
+    // ---- epilogue: O (fp32, TMEM) -> bf16 rows; warpgroup g stores dims [64g, 64g + 64) ----
     mbar_wait(o_full, 0);
     tc_fence_after();
     bf16* orow = nullptr;
@@ -308,8 +358,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       else orow = a.O1 + ((long)b * (a.R - a.split_row) + (grow - a.split_row)) * FA_HD;
     }
 #pragma unroll 1
-    for (int c4 = 0; c4 < FA_HD / 64; ++c4) {
-      const int c = wg * (FA_HD / 64) + c4;
+    for (int c4 = 0; c4 < FA_HD / 32 / FA_WG; ++c4) {
+      const int c = wg * (FA_HD / 32 / FA_WG) + c4;
       uint32_t o[32];
       tmem_ld_32x32(tmem_O + lane_base + c * 32, o);
       tmem_ld_wait();
@@ -325,12 +375,11 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
     }
-    if (threadIdx.x == 0 && a.write_p) tma_store_wait_all();
+    if (leader && a.write_p) tma_store_wait_all();
   }
-
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) {
+  if (warp == W_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
   }
@@ -354,7 +403,7 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   CUtensorMap tmQ, tmK, tmV, tmP;
   int rc;
   if ((rc = make_tmap_bf16_4d(&tmQ, Q, FA_HD, R, B, 1, FA_HD, R * FA_HD, 0, 64, FA_QT))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tmK, Kc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KT))) return rc;
+  if ((rc = make_tmap_bf16_4d(&tmK, Kc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KC))) return rc;  // K slice
   if ((rc = make_tmap_bf16_4d(&tmV, Vc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KT))) return rc;
   if (P) {
     if ((rc = make_tmap_bf16_4d(&tmP, P, Tpad, R, B, 1, Tpad, R * Tpad, 0, 64, FA_QT))) return rc;
@@ -363,7 +412,7 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   }
   FaArgs a;
   a.B = (int)B; a.R = (int)R; a.G = (int)G; a.Tq = (int)Tq; a.S_len = (int)S_len; a.Tpad = (int)Tpad;
-  a.W32 = (int)W32; a.NT = (int)(Tpad / FA_KT);
+  a.W32 = (int)W32; a.NCH = (int)((Tpad + FA_KC - 1) / FA_KC);
   a.bits = bits; a.O0 = (bf16*)O0; a.O1 = (bf16*)O1; a.split_row = (int)split_row; a.write_p = P ? 1 : 0;
   static bool configured = false;
   if (!configured) {
@@ -371,7 +420,7 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
     configured = true;
   }
   dim3 grid(cdiv(R, FA_QT), (unsigned)B);
-  fa_gemma_fwd_kernel<<<grid, 384, FA_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
+  fa_gemma_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
   LAPB_LAUNCH_OK("fa_gemma_fwd");
   return 0;
 }
