@@ -122,6 +122,17 @@ __device__ __forceinline__ void tma_load_4d(void* smem_dst, const CUtensorMap* m
       : "memory");
 }
 
+// multicast variant: the box lands at the same shared-memory offset of every CTA in `cta_mask` of the cluster and
+// credits the mbarrier at the same offset in each of them
+__device__ __forceinline__ void tma_load_4d_mc(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
+                                               int c2, int c3, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], %7;" ::"r"(smem_u32(smem_dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "h"(cta_mask)
+      : "memory");
+}
+
 // 2-CTA variant: executed by both CTAs of a pair; the transaction bytes are credited to the barrier of the
 // LEADER CTA (peer bit 24 of the shared::cluster address cleared), data lands in the executing CTA's smem.
 __device__ __forceinline__ void tma_load_4d_2sm(void* smem_dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1,
@@ -228,6 +239,15 @@ __device__ __forceinline__ void umma_commit_elect(uint64_t* bar) {
       "{\n\t.reg .pred e;\n\t"
       "elect.sync _|e, 0xffffffff;\n\t"
       "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc_elect(uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t}" ::"r"(
+          smem_u32(bar)),
+      "h"(cta_mask)
       : "memory");
 }
 // arrive on an mbarrier once all previously issued tcgen05 ops of this thread retire

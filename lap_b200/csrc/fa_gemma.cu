@@ -25,6 +25,7 @@
 #include "../../include/lapb200.h"
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace lapb {
 
@@ -65,6 +66,12 @@ __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bu
 __device__ __forceinline__ void softmax_bar() { asm volatile("bar.sync 1, %0;" ::"n"(FA_SOFT) : "memory"); }
 __device__ __forceinline__ void wg_bar(int wg) { asm volatile("bar.sync %0, 128;" ::"r"(2 + wg) : "memory"); }
 
+// CL = CTAs per cluster (1, 2 or 4): neighbouring query tiles of one sample.  Every CTA loads 1/CL of each ring stage (a key
+// range of a K slice, whole 64-dim atoms of a V tile) and multicasts it into the shared memory of all CL CTAs: the kernel
+// cuts the L2 -> SM traffic (each 128-row query tile re-reads the sample's whole K twice and V once: 1.6 GB per launch at the
+// training shape) by CL.  Measured: the kernel is NOT L2-bound (CL = 2 / 4 are 4 % / 14 % slower than CL = 1 because the
+// CTAs of a cluster then advance in lock-step), so the launcher defaults to CL = 1; LAPB_FA_CLUSTER selects 2 or 4.
+template <int CL>
 __global__ void __launch_bounds__(FA_THREADS, 1)
 fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const FaArgs a) {
@@ -102,7 +109,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_full, 1);
     for (int i = 0; i < FA_NST; ++i) {
       mbar_init(&r_full[i], 1);
-      mbar_init(&r_empty[i], 1);
+      mbar_init(&r_empty[i], CL);  // released by the MMA warp of every CTA that received the multicast stage
       mbar_init(&p_full[i], 1);
       mbar_init(&pv_done[i], 1);
       mbar_init(&st_done[i], 1);
@@ -121,7 +128,10 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // the peers' barriers must exist before anything is multicast into them
   tc_fence_after();
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0;
+  constexpr uint16_t CMASK = (uint16_t)((1u << CL) - 1u);
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tmem_O = tmem_base + 256;  // pass 2: S in columns [0,256), O in [256,512)
   auto chunk_keys = [&](int j) { return min(FA_KC, a.Tpad - j * FA_KC); };  // multiple of 64
@@ -138,7 +148,11 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int st = it & (FA_NST - 1);
           mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
           mbar_expect_tx(&r_full[st], FA_ST_BYTES);
-          tma_load_4d(Ring + st * FA_ST_BYTES, &tmK, &r_full[st], c * 64, j * FA_KC, b, 0);
+          if (CL > 1)  // this CTA's key range of the slice, to every CTA of the cluster
+            tma_load_4d_mc(Ring + st * FA_ST_BYTES + crank * (FA_KC / CL) * 128, &tmK, &r_full[st], c * 64,
+                           j * FA_KC + crank * (FA_KC / CL), b, 0, CMASK);
+          else
+            tma_load_4d(Ring + st * FA_ST_BYTES, &tmK, &r_full[st], c * 64, j * FA_KC, b, 0);
         }
       };
       auto load_v_tile = [&](int key0) {  // [64 keys x 256 dims]: 4 atoms of 64 dims ([64 keys x 128 B] each)
@@ -146,8 +160,14 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
         mbar_expect_tx(&r_full[st], FA_ST_BYTES);
 #pragma unroll
-        for (int c = 0; c < 4; ++c)
-          tma_load_4d(Ring + st * FA_ST_BYTES + c * (FA_KT * 128), &tmV, &r_full[st], c * 64, key0, b, 0);
+        for (int c = 0; c < 4; ++c) {
+          if (CL > 1) {  // atoms c = crank, crank + CL, ... to every CTA of the cluster
+            if ((c % CL) == (int)crank)
+              tma_load_4d_mc(Ring + st * FA_ST_BYTES + c * (FA_KT * 128), &tmV, &r_full[st], c * 64, key0, b, 0, CMASK);
+          } else {
+            tma_load_4d(Ring + st * FA_ST_BYTES + c * (FA_KT * 128), &tmV, &r_full[st], c * 64, key0, b, 0);
+          }
+        }
         ++it;
       };
       for (int j = 0; j < NCH; ++j) load_k_chunk(j);  // pass 1
@@ -179,7 +199,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * 32, 16, 1024);
           umma_bf16_elect(d, da, db, idescS, (c | kk) != 0 ? 1u : 0u);
         }
-        umma_commit_elect(&r_empty[st]);
+        if (CL > 1) umma_commit_mc_elect(&r_empty[st], CMASK);
+        else umma_commit_elect(&r_empty[st]);
       }
       umma_commit_elect(&s_full[slot]);
     };
@@ -195,7 +216,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * (16 * 128), FA_KT * 128, 1024);
         umma_bf16_elect(tmem_O, da, db, idescPV, (accumulate | (uint32_t)kk) != 0 ? 1u : 0u);
       }
-      umma_commit_elect(&r_empty[st]);
+      if (CL > 1) umma_commit_mc_elect(&r_empty[st], CMASK);
+      else umma_commit_elect(&r_empty[st]);
       umma_commit_elect(&pv_done[s]);
       ++it;
     };
@@ -379,6 +401,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer can still arrive on its barriers
   if (warp == W_ALLOC) {
     tc_fence_after();
     tmem_dealloc(tmem_base, 512);
@@ -403,7 +426,14 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   CUtensorMap tmQ, tmK, tmV, tmP;
   int rc;
   if ((rc = make_tmap_bf16_4d(&tmQ, Q, FA_HD, R, B, 1, FA_HD, R * FA_HD, 0, 64, FA_QT))) return rc;
-  if ((rc = make_tmap_bf16_4d(&tmK, Kc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KC))) return rc;  // K slice
+  dim3 grid(cdiv(R, FA_QT), (unsigned)B);
+  static int cl_env = -1;
+  if (cl_env < 0) {
+    const char* e = getenv("LAPB_FA_CLUSTER");
+    cl_env = e ? atoi(e) : 1;  // measured at the training shape: CL = 1 282 us, CL = 2 292 us, CL = 4 321 us
+  }
+  const int CLN = (cl_env >= 4 && grid.x % 4 == 0) ? 4 : (cl_env >= 2 && grid.x % 2 == 0) ? 2 : 1;
+  if ((rc = make_tmap_bf16_4d(&tmK, Kc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KC / CLN))) return rc;  // K slice
   if ((rc = make_tmap_bf16_4d(&tmV, Vc, FA_HD, Tpad, B, 1, FA_HD, Tpad * FA_HD, 0, 64, FA_KT))) return rc;
   if (P) {
     if ((rc = make_tmap_bf16_4d(&tmP, P, Tpad, R, B, 1, Tpad, R * Tpad, 0, 64, FA_QT))) return rc;
@@ -416,11 +446,29 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   a.bits = bits; a.O0 = (bf16*)O0; a.O1 = (bf16*)O1; a.split_row = (int)split_row; a.write_p = P ? 1 : 0;
   static bool configured = false;
   if (!configured) {
-    LAPB_CUDA_OK(cudaFuncSetAttribute(fa_gemma_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    LAPB_CUDA_OK(cudaFuncSetAttribute(fa_gemma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    LAPB_CUDA_OK(cudaFuncSetAttribute(fa_gemma_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
+    LAPB_CUDA_OK(cudaFuncSetAttribute(fa_gemma_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
     configured = true;
   }
-  dim3 grid(cdiv(R, FA_QT), (unsigned)B);
-  fa_gemma_fwd_kernel<<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
+  if (CLN > 1) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(FA_THREADS);
+    cfg.dynamicSmemBytes = FA_SMEM;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CLN;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (CLN == 4) LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, fa_gemma_fwd_kernel<4>, tmQ, tmK, tmV, tmP, a));
+    else LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, fa_gemma_fwd_kernel<2>, tmQ, tmK, tmV, tmP, a));
+  } else {
+    fa_gemma_fwd_kernel<1><<<grid, FA_THREADS, FA_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
+  }
   LAPB_LAUNCH_OK("fa_gemma_fwd");
   return 0;
 }
