@@ -166,6 +166,27 @@ def test_rmsnorm_plain_and_adaptive():
     assert rel_err(dmod[:, : 2 * D], mr.grad[:, : 2 * D]) < 6e-3
 
 
+@pytest.mark.parametrize("M,D", [(4099, 2048), (2048, 1152), (1500, 72)])
+def test_forward_norms_warp_per_row_path(M, D):
+    """M >= 1024 contiguous rows take the warp-per-row kernels (rows kept in registers); same arithmetic as the
+    CTA-per-row kernels used for small M / gathered rows."""
+    x = (torch.randn(M, D, device=DEV) * 1.5 + 0.25).bfloat16()
+    sc, bi = torch.randn(D, device=DEV) * 0.3, torch.randn(D, device=DEV)
+    y, mean, rstd = torch.empty_like(x), torch.empty(M, device=DEV), torch.empty(M, device=DEV)
+    ops.rmsnorm_fwd(x, y, rstd, M, D, scale=sc)
+    xf = x.float()
+    r = torch.rsqrt((xf * xf).mean(-1, keepdim=True) + 1e-6)
+    assert rel_err(y, xf * r * (1 + sc)) < 3e-3 and rel_err(rstd, r[:, 0]) < 1e-5
+    ops.layernorm_fwd(x, sc, bi, y, mean, rstd, M, D)
+    assert rel_err(y, torch.nn.functional.layer_norm(xf, (D,), sc, bi, eps=1e-6)) < 3e-3
+    assert rel_err(mean, xf.mean(-1)) < 1e-4
+    # small-M path gives the same values on the same rows
+    y2, rstd2 = torch.empty(512, D, device=DEV, dtype=torch.bfloat16), torch.empty(512, device=DEV)
+    ops.rmsnorm_fwd(x[:512].contiguous(), y2, rstd2, 512, D, scale=sc)
+    ops.rmsnorm_fwd(x, y, rstd, M, D, scale=sc)
+    assert rel_err(y[:512], y2) < 1e-3 and rel_err(rstd[:512], rstd2) < 1e-6
+
+
 def test_rope_roundtrip_and_reference():
     from oracle.lap_oracle import apply_rope
 

@@ -12,7 +12,7 @@ peaks = {}
 p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
 if os.path.exists(p):
     peaks = json.load(open(p))
-HBM = float(peaks.get("hbm_gbps_burst", peaks.get("hbm_gbps", 6540.8)))
+HBM = float(peaks.get("hbm_gbs", peaks.get("hbm_gbps", 6540.8)))
 
 rows = list(csv.reader(sys.stdin))
 hdr, units = rows[0], rows[1]
