@@ -68,6 +68,7 @@ OP_SRC = os.path.join(REF, "third_party/openpi/src")
 TR = os.path.join(OP_SRC, "openpi/models_pytorch/transformers_replace/models")
 CONVERTER = os.path.join(REF, "third_party/openpi/examples/convert_jax_model_to_pytorch.py")
 
+from reference_cases import grad_fingerprint  # noqa: E402
 from reference_cases import (ACTION_DIM, CASES, VIS_DEPTH, VIS_HEADS, VIS_MLP, VIS_WIDTH, VOCAB, lap_config, pack_rows,  # noqa: E402
                              params_digest, seeded_inputs, seeded_reference_params)
 
@@ -270,6 +271,49 @@ def build_reference_model(pp, cfg, params: dict[str, np.ndarray]):
     return model
 
 
+def torch_index_of_jax_layout(cfg, params: dict[str, np.ndarray]) -> dict[str, tuple[str, np.ndarray]]:
+    """Which JAX-tree element every PyTorch-port parameter element comes from, WITHOUT hand-writing the inverse of the
+    reference's converter: the converter (pure transposes / reshapes / slices) is applied to a tree of element ids."""
+    slice_paligemma, slice_gemma = load_reference_converter()
+    ids, offs, off = {}, {}, 0
+    for k, v in params.items():
+        ids[k] = (off + np.arange(v.size, dtype=np.float64)).reshape(v.shape)
+        offs[k] = off
+        off += v.size
+    pg = {k[len("PaliGemma/"):]: v.copy() for k, v in ids.items() if k.startswith("PaliGemma/")}
+    hf = types.SimpleNamespace(
+        vision_config=types.SimpleNamespace(hidden_size=VIS_WIDTH, num_hidden_layers=VIS_DEPTH),
+        text_config=types.SimpleNamespace(hidden_size=cfg.gemma.width, num_hidden_layers=cfg.gemma.depth,
+                                          num_attention_heads=cfg.gemma.num_heads, head_dim=cfg.gemma.head_dim))
+    pal, exp = slice_paligemma(pg, hf)
+    gem = slice_gemma(exp, types.SimpleNamespace(**dataclasses.asdict(cfg.expert)), num_expert=1, checkpoint_dir="pi05",
+                      pi05=True)
+    out = {**{k: v.numpy() for k, v in pal.items()}, **{k: v.numpy() for k, v in gem.items()}}
+    for key in ("action_in_proj", "action_out_proj", "time_mlp_in", "time_mlp_out"):
+        out[key + ".weight"] = ids[key + "/kernel"].T
+        out[key + ".bias"] = ids[key + "/bias"]
+    return out, offs, off
+
+
+def reference_grad_summary(pp, cfg, params, model, obs, actions, noise, time) -> dict[str, np.ndarray]:
+    for p_ in model.parameters():
+        p_.grad = None
+    with torch.enable_grad():
+        loss = model.forward(obs, actions, noise=noise, time=time).mean()
+        loss.backward()
+    idx, offs, total = torch_index_of_jax_layout(cfg, params)
+    flat = np.zeros(total, dtype=np.float64)
+    named = dict(model.named_parameters())
+    for k, id_arr in idx.items():
+        if k in named and named[k].grad is not None:
+            np.add.at(flat, id_arr.astype(np.int64).reshape(-1), named[k].grad.detach().double().numpy().reshape(-1))
+    out = {"grad_loss": np.float32(loss.item())}
+    for k, v in params.items():
+        g = flat[offs[k]: offs[k] + v.size]
+        out["grad/" + k] = grad_fingerprint(g)
+    return out
+
+
 def run_case(pp, case: str) -> dict[str, np.ndarray]:
     pv, ev, batch, horizon, L, seed = CASES[case]
     cfg = lap_config(case)
@@ -313,6 +357,8 @@ def run_case(pp, case: str) -> dict[str, np.ndarray]:
                                                                            num_steps=10).numpy()  # S6
         out["sampled_actions_3"] = pp.PI0Pytorch.sample_actions.__wrapped__(model, torch.device("cpu"), obs, noise=noise,
                                                                              num_steps=3).numpy()
+    # backward: d mean(mse) / d params through the reference's autograd, scattered back to the JAX layout and summarised
+    out.update(reference_grad_summary(pp, cfg, params, model, obs, actions, noise, time))
     # module-level helpers
     out["posemb_t"] = np.linspace(0.001, 1.0, 7, dtype=np.float32)
     out["posemb"] = pp.create_sinusoidal_pos_embedding(t(out["posemb_t"]), 32, 4e-3, 4.0, device=torch.device("cpu")).numpy()

@@ -97,6 +97,14 @@ def params_digest(params: dict[str, np.ndarray]) -> str:
     return h.hexdigest()
 
 
+def grad_fingerprint(g: np.ndarray) -> np.ndarray:
+    """Three numbers per gradient tensor (sum, L2 norm, dot with a fixed +-1 pattern) — what the fixtures keep of the
+    reference's autograd gradients."""
+    g = np.asarray(g, dtype=np.float64).reshape(-1)
+    sign = np.where((np.arange(g.size, dtype=np.int64) * 2654435761 % 4294967296) & 0x10000, 1.0, -1.0)
+    return np.array([g.sum(), np.sqrt((g * g).sum()), (g * sign).sum()], dtype=np.float64)
+
+
 def pack_rows(x: np.ndarray, stride: int) -> np.ndarray:
     """Fixtures keep every `stride`-th token row of the big [B, tokens, width] activations (plus always the last 32 rows)."""
     return x[:, row_index(x.shape[1], stride)]

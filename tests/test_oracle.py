@@ -259,3 +259,30 @@ def test_adamw_ema_closed_form():
     exp = ref[k] - tc.lr_schedule.lr(0) * upd
     assert torch.allclose(ns["params"][k], exp, rtol=1e-5, atol=1e-8)
     assert torch.allclose(ns["ema"][k], 0.999 * ref[k] + 0.001 * exp, rtol=1e-6, atol=1e-8)
+
+
+def test_train_step_matches_an_independent_adamw(tiny):
+    """a3 pin against an independent implementation (optax itself is not installable): two oracle train steps vs
+    torch.optim.AdamW (decoupled weight decay, the same update optax.adamw applies: p - lr*(m_hat/(sqrt(v_hat)+eps) + wd*p))
+    fed with the same clipped gradients, learning rate from the warm-up schedule."""
+    tc, ref, b = tiny
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    args = (obs_for_oracle(b), t(b["actions"]), t(b["noise"]), t(b["time"]))
+    z = {k: torch.zeros_like(v) for k, v in ref.items()}
+    state = dict(step=0, params={k: v.clone() for k, v in ref.items()}, mu=z, nu={k: v.clone() for k, v in z.items()}, ema=None)
+    tp = {k: v.clone().requires_grad_(True) for k, v in ref.items()}
+    o = tc.optimizer
+    opt = torch.optim.AdamW(list(tp.values()), lr=1.0, betas=(o.b1, o.b2), eps=o.eps, weight_decay=o.weight_decay)
+    for step in range(2):
+        state, info, grads = O.train_step(tc, state, *args, bf16=False)
+        gn = float(info["grad_norm"])
+        scale = 1.0 if gn < o.clip_gradient_norm else o.clip_gradient_norm / gn  # optax.clip_by_global_norm
+        for k, v in tp.items():
+            v.grad = grads[k] * scale
+        for grp in opt.param_groups:
+            grp["lr"] = tc.lr_schedule.lr(step)
+        opt.step()
+        for k in ref:
+            d_o, d_t = state["params"][k] - ref[k], tp[k].detach() - ref[k]
+            # (the difference p_new - p cancels ~4 digits of fp32 for parameters of magnitude 1)
+            assert rel_err(d_o, d_t) < 1e-3, (step, k, rel_err(d_o, d_t))

@@ -95,6 +95,31 @@ def test_oracle_matches_reference_pytorch_port(case):
     assert rel_err(O.posemb_sincos(_t(g["posemb_t"]), 32, 4e-3, 4.0), g["posemb"]) < TOL_F32
 
 
+@pytest.mark.parametrize("case", list(RC.CASES))
+def test_oracle_gradients_match_reference_autograd(case):
+    """Backward pin: d mean((v - u)^2) / d params from the reference PyTorch port's autograd (scattered back to the JAX
+    layout through the reference's own converter applied to an index tree) vs torch autograd through the oracle."""
+    cfg, p, inp, g = _load("pi05", case)
+    ps = {k: v.detach().clone().requires_grad_(True) for k, v in p.items()}
+    loss, _ = O.compute_loss(ps, cfg, _oracle_obs(cfg, inp), _t(inp["actions"]), _t(inp["noise"]), _t(inp["time"]),
+                             bf16=False)
+    assert abs(loss.item() - float(g["grad_loss"])) < TOL_F32 * abs(float(g["grad_loss"]))
+    loss.backward()
+    gtot = np.sqrt(sum(float(g["grad/" + k][1]) ** 2 for k in p))
+    n_checked = 0
+    for k, v in ps.items():
+        ref_fp = g["grad/" + k].astype(np.float64)
+        fp = RC.grad_fingerprint((v.grad if v.grad is not None else torch.zeros_like(v)).numpy())
+        if ref_fp[1] < 1e-6 * gtot:  # structurally zero (e.g. SigLIP key bias: softmax shift invariance)
+            assert fp[1] < 1e-4 * gtot, k
+            continue
+        n_checked += 1
+        assert abs(fp[1] - ref_fp[1]) < 1e-3 * ref_fp[1], (k, fp, ref_fp)          # norm
+        assert abs(fp[0] - ref_fp[0]) < 2e-3 * ref_fp[1] * np.sqrt(v.numel()) / 10 + 1e-3 * abs(ref_fp[0]), (k, fp, ref_fp)
+        assert abs(fp[2] - ref_fp[2]) < 2e-3 * ref_fp[1] * np.sqrt(v.numel()) / 10 + 1e-3 * abs(ref_fp[2]), (k, fp, ref_fp)
+    assert n_checked > 30
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # oracle vs LAP.compute_loss / sample_actions executed from the reference's source (LAP-specific rows a5, a10, a13, a19)
 # ----------------------------------------------------------------------------------------------------------------
