@@ -8,7 +8,9 @@ PARITY PIN (what the restatement has been checked against, tests/test_reference_
     gemma_pytorch.py, transformers_replace/**), run UNMODIFIED in the build container on seeded weights mapped by the
     reference's JAX->PyTorch converter: SigLIP tower, token embedding, suffix embedding / adaRMS condition,
     make_attn_mask + positions (bit-exact), the joint two-expert Gemma stack, the flow-matching squared error and
-    sample_actions (KV cache + Euler loop) agree with the fp32 mode of this file to <= 3e-5 normwise
+    sample_actions (KV cache + Euler loop) agree with the fp32 mode of this file to <= 3e-5 normwise, and the
+    gradients of the flow-matching loss from the port's autograd (scattered back to the JAX layout by applying the
+    converter to an index tree) agree with autograd through this file to <= 1e-3 per tensor
     (fixtures tests/golden/reference_pi05_*.npz, generator tests/golden/make_reference_golden.py);
   * LAP.compute_loss / embed_prefix / prepare_suffix / the lang-action mask builders / the language CE and loss
     weighting / sample_actions, executed from src/lap/models/lap.py's own source with numpy standing in for
@@ -19,7 +21,7 @@ PARITY PIN (what the restatement has been checked against, tests/test_reference_
 STILL UNPINNED (the JAX/Flax program itself cannot run here: no jax/flax/optax wheels, no network; the reference's
 tests hold no numeric vector): WHERE the JAX program rounds to bfloat16 (the bf16=True mode follows SURVEY.md
 Appendix A by reading the source), and the optax/EMA train-step arithmetic (third-party optax, restated from its
-published definitions; closed-form one-step checks only).  Every function cites the file:line it follows
+published definitions; checked against closed forms and against torch.optim.AdamW as an independent implementation).  Every function cites the file:line it follows
 (`OP/` = third_party/openpi/src/openpi/).
 
 Two precision modes:
