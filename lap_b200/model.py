@@ -969,13 +969,111 @@ class LAP:
         b = self._bufs.get("dn.sync")
         return int(b[1].item()) if b is not None else 0
 
+    # ------------------------------------------------------------------------------------------
+    # autoregressive decoding of lang-action tokens (lap.py:678-766), greedy
+    # ------------------------------------------------------------------------------------------
+    def sample_tokens(self, rng, observation: Observation, *, max_decoding_steps: int = 390,
+                      temperature: float = 0.0) -> torch.Tensor:
+        """LAP.sample_tokens: prefix prefill -> KV cache -> one token per step through expert 0 alone, until every
+        sample has emitted EOS or `max_decoding_steps`.  Returns int32 [B, max_decoding_steps] (zeros after the stop).
+
+        The reference right-aligns the prefix (pi0_fast.left_to_right_align) and masks decode steps by slot RANGE
+        (slot >= prefix_start, lap.py:737-741).  Attention does not depend on where a key is stored, so the engine keeps
+        its left-aligned cache and translates the range into key positions: rolled slot i holds token (i + seqlen) mod P."""
+        if temperature > 0.0:
+            raise NotImplementedError("temperature > 0 draws from jax.random.categorical (lap.py:727-729); greedy only")
+        cfg, g = self.cfg, self.cfg.gemma
+        st = self._stage(observation, with_loss=False)
+        B, Pn, L, S = st.B, cfg.prefix_len, cfg.max_token_len, int(max_decoding_steps)
+        if B > 16:
+            raise NotImplementedError("sample_tokens uses the weight-streaming kernels: batch <= 16")
+        C, Np, D, hd, NH, F = len(cfg.image_keys), cfg.num_patches, g.width, g.head_dim, g.num_heads, g.mlp_dim
+        QKV = (NH + 2) * hd
+        V = cfg.vocab_size
+        # ---- prefill (same kernels as sample_actions' prefix pass, but the last layer's output is needed) ----
+        Tpad = _round_up(Pn + cfg.action_horizon, 64)
+        W32 = Tpad // 32
+        X0 = self.buf("inf.X0", (B * Pn, D))
+        self._siglip_fwd(st, X0, Pn)
+        ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
+        bits_p = self.buf("inf.bits_p", (B, Pn, W32), torch.int32)
+        pos_p = self.buf("inf.pos_p", (B, Pn), torch.int32)
+        ops.mask_build(st.pm, st.par, None, None, None, bits_p, pos_p, B, Pn, 0, W32)
+        Kp = self.buf("inf.Kc", (g.depth, B, Tpad, hd), zero=True)
+        Vp = self.buf("inf.Vc", (g.depth, B, Tpad, hd), zero=True)
+        X = self._gemma_fwd_prefix(B, X0, bits_p, pos_p, (Kp, Vp), need_output=True)
+        # ---- decode cache: prefix keys + one slot per step ----
+        Tcap = _round_up(Pn + S, 64)
+        W32c = Tcap // 32
+        Kc = self.buf("ar.Kc", (g.depth, B, Tcap, hd), zero=True)
+        Vc = self.buf("ar.Vc", (g.depth, B, Tcap, hd), zero=True)
+        Kc[:, :, :Pn].copy_(Kp[:, :, :Pn])
+        Vc[:, :, :Pn].copy_(Vp[:, :, :Pn])
+        pm = st.pm.cpu().numpy().astype(bool)  # [B, Pn] validity of the prefix tokens (tiny, host side)
+        idx = np.arange(Pn)
+        seqlen = (pm * idx[None, :]).max(-1) + 1                      # pi0_fast.py:60
+        prefill_len = pm.sum(-1)
+        prefix_start = Pn - prefill_len
+        rolled_slot = (idx[None, :] - seqlen[:, None]) % Pn            # slot of token j after the roll by -seqlen
+        allowed = np.zeros((B, Tcap), dtype=bool)
+        allowed[:, :Pn] = rolled_slot >= prefix_start[:, None]
+        allowed[:, Pn:] = True                                         # decode slots; S_len cuts off the future ones
+        bits_np = np.packbits(allowed.reshape(B, W32c, 32), axis=-1, bitorder="little").view(np.uint32).reshape(B, 1, W32c)
+        bits_ar = torch.from_numpy(bits_np.view(np.int32).copy()).to(self.device)
+        pos0 = torch.from_numpy(prefill_len.astype(np.int32)).to(self.device)
+        last_row = torch.from_numpy((np.arange(B) * Pn + seqlen - 1).astype(np.int64)).to(self.device)
+        # ---- first logits: final norm + LM head on the last valid prefix token ----
+        pre2 = self.buf("ar.pre2", (B, 2 * D))
+        rstd = self.buf("ar.rstd", (B,), F32)
+        logits = self.buf("ar.logits", (B, V), F32)
+        ops.rmsnorm_fwd(X, pre2, rstd, B, D, scale=self.p("g.final_norm_s"), row_idx=last_row, ldy=2 * D, dup=True)
+        ops.skinny_gemm(pre2, self.E_split, logits, M=B, N=V, K=2 * D)
+        out = torch.zeros((B, S), dtype=torch.int32, device=self.device)
+        eos = torch.zeros((B,), dtype=torch.bool, device=self.device)
+        x = self.buf("ar.x", (B, D))
+        x1 = self.buf("ar.x1", (B, D))
+        h = self.buf("ar.h", (B, D))
+        qkv = self.buf("ar.qkv", (B, QKV))
+        Q = self.buf("ar.Q", (B, 1, NH, hd))
+        O = self.buf("ar.O", (B, NH * hd))
+        act = self.buf("ar.act", (B, F))
+        pos = self.buf("ar.pos", (B,), torch.int32)
+        qscale = hd ** -0.5
+        step = 0
+        while step < S:
+            token = torch.argmax(logits, dim=-1).to(torch.int32)       # lap.py:730 (temperature = 0)
+            out[:, step] = token
+            eos |= token == self.EOS_TOKEN
+            all_eos = bool(eos.all().item())
+            # decode one step with expert 0 (the reference also runs it after the last token; its result is unused)
+            if all_eos or step + 1 >= S:
+                break
+            ops.embed_fwd(token, self.p("g.embed"), x, B, 1, 0, 1, D, math.sqrt(D))
+            torch.add(pos0, step, out=pos)
+            xin = x
+            for l in range(g.depth):
+                ops.rmsnorm_fwd(xin, h, rstd, B, D, scale=self.p("g.attn_norm_s", l))
+                ops.skinny_gemm(h, self.w("g.qkv_w", l), qkv, M=B, N=QKV, K=D)
+                ops.rope_fwd(None, qkv, pos, self.timescale, Q, Kc[l], Vc[l], B, Pn + step, 1, Tcap, NH, hd, Pn + step,
+                             qscale)
+                ops.decode_attn(Q, Kc[l], Vc[l], bits_ar, O, B, 1, NH, hd, Pn + step + 1, Tcap, W32c)
+                ops.skinny_gemm(O, self.w("g.o_w", l), x1, M=B, N=D, K=NH * hd, epi=ops.EPI_RESID, resid=xin)
+                ops.rmsnorm_fwd(x1, h, rstd, B, D, scale=self.p("g.ffn_norm_s", l))
+                ops.skinny_gemm(h, self.w("g.gu_w", l), act, M=B, N=F, K=D, epi=ops.EPI_GEGLU)
+                ops.skinny_gemm(act, self.w("g.down_w", l), x, M=B, N=D, K=F, epi=ops.EPI_RESID, resid=x1)
+                xin = x
+            ops.rmsnorm_fwd(x, pre2, rstd, B, D, scale=self.p("g.final_norm_s"), ldy=2 * D, dup=True)
+            ops.skinny_gemm(pre2, self.E_split, logits, M=B, N=V, K=2 * D)
+            step += 1
+        return out
+
     def _gemma_prefix_only(self, B, X0, bits, positions, cache):
         """Prefix-only pass (lap.py:627): expert 0 alone, K/V (post-RoPE) written into the cache."""
         cfg = self.cfg
         # reuse the generic layer loop with A = 0 by temporarily viewing the sequence as prefix-only
         self._gemma_fwd_prefix(B, X0, bits, positions, cache)
 
-    def _gemma_fwd_prefix(self, B, X, bits, positions, cache):
+    def _gemma_fwd_prefix(self, B, X, bits, positions, cache, need_output: bool = False):
         cfg, g = self.cfg, self.cfg.gemma
         Pn = cfg.prefix_len
         Tpad = _round_up(cfg.prefix_len + cfg.action_horizon, 64)
@@ -994,7 +1092,7 @@ class LAP:
             ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
             Q = self.buf("inf.Qp", (B, Pn, NH, hd))
             ops.rope_fwd(qkv0, None, positions, self.timescale, Q, Kc, Vc, B, Pn, 0, Tpad, NH, hd, 0, qscale)
-            if l == g.depth - 1:
+            if l == g.depth - 1 and not need_output:
                 # sample_actions consumes only the KV cache of the prefix pass (lap.py:627 discards the outputs): the
                 # last layer's attention, output projection and MLP feed nothing
                 return None

@@ -463,6 +463,51 @@ def sample_actions(p, cfg, obs, noise, *, num_steps=10, bf16: bool, softmax_dtyp
     return x_t
 
 
+def left_to_right_align(x, input_mask, attn_mask):
+    """OP/models/pi0_fast.py:52-64, per example: roll so that the last valid token sits in the last slot."""
+    n = input_mask.shape[0]
+    seqlen = int((input_mask.to(torch.int64) * torch.arange(n)).max()) + 1
+    return (torch.roll(x, -seqlen, 0), torch.roll(input_mask, -seqlen, 0), torch.roll(attn_mask, (-seqlen, -seqlen), (0, 1)))
+
+
+def sample_tokens(p, cfg, obs, *, max_decoding_steps=390, bf16: bool, softmax_dtype="bf16", return_logits=False):
+    """LAP.sample_tokens (lap.py:678-766), greedy (temperature = 0): right-aligned prefix prefill -> KV cache -> one token
+    per step through expert 0 alone.  The decode-step mask is the reference's RANGE mask
+    (slot >= prefix_start and slot <= current), not a validity mask (lap.py:737-741)."""
+    pre_tok, pre_mask, pre_ar = embed_prefix(p, cfg, obs, bf16, softmax_dtype)
+    attn = make_attn_mask(pre_mask, pre_ar)
+    B, P, _ = pre_tok.shape
+    al = [left_to_right_align(pre_tok[b], pre_mask[b], attn[b]) for b in range(B)]
+    pre_tok, pre_mask, attn = (torch.stack([a[i] for a in al]) for i in range(3))
+    prefill_len = pre_mask.sum(-1)
+    prefix_start = P - prefill_len
+    S = max_decoding_steps
+    attn = torch.cat([attn, torch.zeros(B, P, S, dtype=torch.bool)], -1)
+    positions = torch.cumsum(pre_mask.to(torch.int64), -1) - 1
+    cfgs = [cfg.gemma, cfg.expert]
+    # prefill: the cache holds P slots now, S more are appended one per step (keys beyond the current slot are masked)
+    (pre_out, _), cache = gemma_forward(p, cfgs, [pre_tok, None], positions, attn[:, :, :P], [None, None], bf16)
+    last_logit = decode_logits(p, pre_out[:, -1:], bf16)
+    out = torch.zeros(B, S, dtype=torch.int64)
+    eos = torch.zeros(B, dtype=torch.bool)
+    logits_log = []
+    step = 0
+    while (not bool(eos.all())) and step < S:
+        token = last_logit.argmax(-1)  # [B, 1]
+        logits_log.append(last_logit[:, 0])
+        out[:, step] = token[:, 0]
+        eos = eos | (token[:, 0] == 1)  # EOS_TOKEN (lap.py:32)
+        emb = embed_tokens(p, cfg, token, bf16)
+        pos = prefill_len[:, None] + step
+        slots = torch.arange(P + step + 1)[None, None, :]
+        mask = (slots >= prefix_start[:, None, None]) & (slots < P + step + 1)
+        (o, _), new = gemma_forward(p, cfgs, [emb, None], pos, mask, [None, None], bf16, kv_cache=cache)
+        cache = new  # gemma_attention returns (cache ++ new token)
+        last_logit = decode_logits(p, o, bf16)
+        step += 1
+    return (out, torch.stack(logits_log, 1)) if return_logits else out
+
+
 # ---------------------------------------------------------------------------------------------
 # train step  (scripts/train.py:329-419; optax semantics restated, Appendix A.9)
 # ---------------------------------------------------------------------------------------------

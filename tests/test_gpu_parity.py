@@ -293,6 +293,42 @@ def test_stop_action_to_vlm_grad_gradients_match_oracle(name):
     assert rel_err(g_stop[mlp1], g_plain[mlp1]) < 2e-2  # same forward, same cotangents inside the action expert
 
 
+@pytest.mark.parametrize("name", ["debug_tiny", "debug_small"])
+def test_sample_tokens_matches_oracle(name):
+    """LAP.sample_tokens (lap.py:678-766), greedy: engine vs the bf16-emulating oracle.  Tokens must agree wherever the
+    oracle's top-2 logit margin is not within bf16 noise; includes a dropped camera (a hole inside the reference's
+    right-aligned slot range) and ragged prompt lengths."""
+    from lap_b200.observation import Observation
+    tc, ref, model, b = _setup(name, 3, seed=9, step=6)
+    cfg = tc.model
+    b = {k: (dict(v) if isinstance(v, dict) else v.copy()) for k, v in b.items() if k != "tokenized_langact_mask"}
+    L = cfg.max_token_len
+    n_p = np.array([L // 3, L // 2, L - 9])
+    b["tokenized_prompt_mask"] = np.arange(L)[None, :] < n_p[:, None]
+    b["image_mask"] = {k: np.ones_like(v) for k, v in b["image_mask"].items()}
+    b["image_mask"]["left_wrist_0_rgb"][2] = False
+    S = 8
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    toks_o, logits_o = O.sample_tokens(ref, cfg, obs_for_oracle(b, langact=False), max_decoding_steps=S, bf16=True,
+                                       return_logits=True)
+    toks_e = model.sample_tokens(0, Observation.from_dict(b), max_decoding_steps=S).cpu()
+    assert toks_e.shape == (3, S) and toks_e.dtype == torch.int32
+    top2 = logits_o.topk(2, dim=-1).values
+    margin = (top2[..., 0] - top2[..., 1])
+    scale = logits_o.abs().amax(-1)
+    n_cmp = 0
+    for i in range(3):
+        for s_ in range(toks_o.shape[1]):
+            if s_ < logits_o.shape[1] and margin[i, s_] > 2e-2 * scale[i, s_]:
+                assert int(toks_e[i, s_]) == int(toks_o[i, s_]), (i, s_, toks_e[i], toks_o[i])
+                n_cmp += 1
+            else:
+                break  # after a near-tie the two decodes may legitimately diverge
+    assert n_cmp >= 3
+    with pytest.raises(NotImplementedError):
+        model.sample_tokens(0, Observation.from_dict(b), max_decoding_steps=4, temperature=0.7)
+
+
 def test_edge_cases_empty_langact_dropped_camera_masked_samples():
     """Ragged inputs: a sample without lang-action tokens, a sample_mask=False sample, a dropped wrist camera."""
     tc, ref, model, b = _setup("debug_small", 3, seed=3, step=4)

@@ -286,3 +286,38 @@ def test_train_step_matches_an_independent_adamw(tiny):
             d_o, d_t = state["params"][k] - ref[k], tp[k].detach() - ref[k]
             # (the difference p_new - p cancels ~4 digits of fp32 for parameters of magnitude 1)
             assert rel_err(d_o, d_t) < 1e-3, (step, k, rel_err(d_o, d_t))
+
+
+def test_sample_tokens_equals_teacher_forced_forward(tiny):
+    """AR decode (lap.py:678-766) invariant: the logits of greedy decode step s equal the training-style forward of the same
+    prompt with the generated tokens appended as causal lang-action tokens (prefix-LM mask, positions cumsum-1) — checks
+    the right-aligned prefill, the KV cache growth, the range mask and the positions of the decode loop."""
+    tc, ref, _ = tiny
+    cfg = tc.model
+    b = synthetic_batch(cfg, 3, step=5, with_langact=False)
+    L = cfg.max_token_len
+    n_p = np.array([7, 10, 12])
+    b["tokenized_prompt_mask"] = np.arange(L)[None, :] < n_p[:, None]
+    b["image_mask"] = {k: np.ones_like(v) for k, v in b["image_mask"].items()}  # no holes: range mask == validity mask
+    t = lambda x: torch.from_numpy(np.asarray(x))
+    K = 6
+    obs = obs_for_oracle(b, langact=False)
+    toks, logits = O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False, return_logits=True)
+    assert toks.shape == (3, K) and logits.shape[:2] == (3, K)
+    # teacher forcing
+    prompt = b["tokenized_prompt"].copy()
+    pm, la = b["tokenized_prompt_mask"].copy(), np.zeros((3, L), dtype=bool)
+    for i in range(3):
+        prompt[i, n_p[i]: n_p[i] + K] = toks[i].numpy()
+        pm[i, n_p[i]: n_p[i] + K] = True
+        la[i, n_p[i]: n_p[i] + K] = True
+    b2 = dict(b, tokenized_prompt=prompt, tokenized_prompt_mask=pm, tokenized_langact_mask=la)
+    _, _, aux = O.compute_loss(ref, cfg, obs_for_oracle(b2), t(b["actions"]), t(b["noise"]), t(b["time"]), bf16=False,
+                               return_aux=True)
+    for i in range(3):
+        for s_ in range(K):
+            assert rel_err(logits[i, s_], aux["logits"][i, n_p[i] + s_ - 1]) < 1e-4, (i, s_)
+    # a dropped camera leaves a hole inside the right-aligned range: the decode still runs and returns tokens
+    b["image_mask"]["left_wrist_0_rgb"][1] = False
+    toks2 = O.sample_tokens(ref, cfg, obs_for_oracle(b, langact=False), max_decoding_steps=3, bf16=True)
+    assert toks2.shape == (3, 3)
