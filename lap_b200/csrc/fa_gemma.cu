@@ -174,9 +174,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       load_k_chunk(0);                                // pass 2
       for (int j = 0; j < NCH; ++j) {
         const int ns = chunk_keys(j) / FA_KT;
-        load_v_tile(j * FA_KC);
         if (j + 1 < NCH) load_k_chunk(j + 1);
-        for (int s = 1; s < ns; ++s) load_v_tile(j * FA_KC + s * FA_KT);
+        for (int s = 0; s < ns; ++s) load_v_tile(j * FA_KC + s * FA_KT);
       }
     }
   } else if (warp == W_MMA) {
@@ -227,10 +226,13 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t acc = 0;
     for (int j = 0; j < NCH; ++j) {
       const int ns = chunk_keys(j) / FA_KT;
-      issue_PV(j, 0, acc);
-      acc = 1;
-      if (j + 1 < NCH) issue_S(j + 1, 0, U0 + j + 1);  // keeps the tensor pipe busy during the P hand-offs below
-      for (int s = 1; s < ns; ++s) issue_PV(j, s, 1);
+      // S(j+1) goes first: it runs on the tensor pipe while the softmax warps spend their ~2 K MUFU cycles on chunk j
+      // (its slot is free as soon as every softmax thread has pulled S(j) into registers)
+      if (j + 1 < NCH) issue_S(j + 1, 0, U0 + j + 1);
+      for (int s = 0; s < ns; ++s) {
+        issue_PV(j, s, acc);
+        acc = 1;
+      }
     }
     umma_commit_elect(o_full);
   } else if (warp < W_TMA) {
@@ -317,10 +319,16 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       uint32_t pk[32];
 #pragma unroll
       for (int hf = 0; hf < 2; ++hf) {
+        uint32_t sv[32];
         if (active) {
-          uint32_t sv[32];
           tmem_ld_32x32(tmem_base + lane_base + wg * FA_KT + hf * 32, sv);
           tmem_ld_wait();
+        }
+        if (hf == 1) {  // S(j) is out of TMEM: the next chunk's S may overwrite the slot while the exps below run
+          tc_fence_before();
+          mbar_arrive_relaxed(&s_empty[0]);
+        }
+        if (active) {
           const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
           const uint32_t w = mrow[key0 >> 5];
           const int nvalid = a.S_len - key0;
@@ -339,8 +347,6 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive_relaxed(&s_empty[0]);  // S(j) is in registers: the next chunk's S may overwrite the slot
       if (active) {
         // the single P buffer is free once the previous sub-tile's P V has retired (and its TMA store has read it)
         if (wg > 0) {
