@@ -781,6 +781,444 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
     for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) p.x[i] = x_s[i];
 }
 
+// ======================================================================================================================
+// K10c — the same Euler loop as ONE THREAD-BLOCK CLUSTER of 16 CTAs (16 SMs), synchronised by the hardware cluster barrier.
+//
+// Why: `profiles/r01_denoise_loop.md` — in the 148-CTA kernel above 53 % of every warp's time is spent at the six grid
+// barriers per layer (~2 us each plus the imbalance in front of them), while the memory system idles.  A microbenchmark
+// (`tools/micro/sm_bw.cu`) shows that 16 SMs alone stream 2.5 TB/s (157 GB/s per SM; 148 SMs share 6.4 TB/s = 43 GB/s each),
+// so 16 CTAs are enough to read a layer's 34.6 MB in ~14 us, and `barrier.cluster` costs a few hundred cycles instead of
+// ~2 us.  Five phases per layer (the chunk combine is folded into the staging of the o-projection):
+//   P1 adaRMS + qkv            : a warp owns whole n8 tiles (full K: no cross-warp reduction, no block barrier)
+//   P2 attention               : CTA = (head, half of the prefix keys [+ the suffix keys]); S over up to 512 keys in shared
+//                                memory, one softmax over the CTA's keys, P V with one head-dim tile per warp
+//   P3 combine halves + o-proj : 8 tiles per CTA x 4 K-quarters (one 16 KB reduction through shared memory)
+//   P4 adaRMS + gate/up + GeGLU: a warp owns one (gate, up) tile pair, GeGLU on the accumulator fragments
+//   P5 down                    : 8 tiles x 4 K-quarters
+// Arithmetic, rounding points and scratch buffers are those of the grid kernel; only the partitioning differs.
+//
+// STATUS (round 1): correct (same tests as the grid kernel) but NOT yet faster — 27.9 ms per 10 steps against 13.0 ms
+// (`LAPB_DENOISE_MODE=cluster` selects it; the default stays the grid kernel).  Per layer-step: P1 16 us, P2 17 us,
+// combine 15 us, o-proj 12 us, gate/up 43 us, down 23 us, cluster barriers ~1.2 us each.  The register-fed warp-per-tile
+// loops keep only 40-64 KB in flight per SM with 64-byte row segments (20-25 GB/s per SM instead of the 157 GB/s of
+// contiguous streaming): the weight slices have to go through a TMA-fed shared-memory ring (contiguous 2-8 KB rows, deep
+// prefetch) and the combine needs vector loads before this partitioning can win.
+// ======================================================================================================================
+constexpr int DNC_CTAS = 16;
+constexpr int DNC_MAXK = 512;  // prefix keys per attention CTA (Tpad <= 1024)
+
+__host__ __device__ inline size_t dnc_attn_bytes(int HD) {
+  return (size_t)16 * (HD + 8) * 2                 /* q_s   */ + (size_t)16 * (DNC_MAXK + 16) * 4 /* s_s */ +
+         (size_t)16 * (DNC_MAXK + 8) * 2           /* p_s   */ + (size_t)16 * HD * 4              /* ks_s */ +
+         (size_t)3 * 16 * HD * 2                   /* raw q, k, v */ + (size_t)16 * 16 * 4          /* p of the suffix keys */;
+}
+__host__ __device__ inline size_t dnc_big_bytes(int D1, int HD, int OD, int F1) {
+  size_t b = dn_big_bytes(D1, HD, OD, F1);
+  const size_t a = dn_align16(dnc_attn_bytes(HD));
+  return b > a ? b : a;
+}
+__host__ __device__ inline size_t dnc_smem_bytes(int D1, int HD, int OD, int F1) {
+  return (size_t)16 * D1 * 2 + dnc_big_bytes(D1, HD, OD, F1) + (size_t)4 * 8 * 32 * 4 * 4 + (size_t)16 * 32 * 4 +
+         (size_t)16 * (HD / 2) * 8 + (size_t)6 * D1 * 2 + (size_t)16 * 32 * 4 + 64 + 16;
+}
+
+// one n8 weight tile x K groups [kg_begin, kg_end) against the staged rows As: accumulator fragment of this warp
+// (lane (g, t): rows g and g + 8, columns 2t and 2t + 1)
+__device__ __forceinline__ void dnc_warp_tile(const bf16* As, int lda, int M, const bf16* wtile, long ldw, int kg_begin,
+                                              int kg_end, float (&acc)[4]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const bf16* xlo = As + (long)g * lda + 8 * t;
+  const bf16* xhi = As + (long)(g + 8) * lda + 8 * t;
+  const bf16* wr = wtile + (long)g * ldw + 8 * t;
+  const bool vlo = g < M, vhi = (g + 8) < M;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int kg0 = kg_begin; kg0 < kg_end; kg0 += 4) {
+    uint4 b[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) b[u] = (kg0 + u < kg_end) ? dn_ld_stream(wr + (kg0 + u) * 32) : zero;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (kg0 + u < kg_end) {
+        const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(xlo + (kg0 + u) * 32) : zero;
+        const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(xhi + (kg0 + u) * 32) : zero;
+        dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, b[u].x, b[u].y);
+        dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, b[u].z, b[u].w);
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const lapb_denoise_params_t p) {
+  extern __shared__ __align__(16) unsigned char dn_smem[];
+  const int A = p.A, ad = p.ad, D1 = p.D1, NH = p.NH, HD = p.HD, F1 = p.F1, L = p.L, Pn = p.Pn, W32 = p.W32;
+  const int QKV = (NH + 2) * HD, OD = NH * HD, nm3 = p.nm * 3 * D1, S = p.num_steps;
+  const int ldh = D1 + 8, ldo = OD + 8, ldf = F1 + 8, ldq = HD + 8, half = HD / 2;
+  constexpr int LDS = DNC_MAXK + 16, LDP = DNC_MAXK + 8;
+  // ---- shared memory ----
+  bf16* xe_s = reinterpret_cast<bf16*>(dn_smem);
+  unsigned char* big = dn_smem + (size_t)16 * D1 * 2;
+  bf16* h_s = reinterpret_cast<bf16*>(big);
+  float* red = reinterpret_cast<float*>(big + dnc_big_bytes(D1, HD, OD, F1));          // [4 K-quarters][8 tiles][32][4]
+  float* x_s = red + 4 * 8 * 32 * 4;
+  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);
+  bf16* mod_sm = reinterpret_cast<bf16*>(rope_s + 16 * half);
+  uint32_t* bits_s = reinterpret_cast<uint32_t*>(mod_sm + 6 * D1);
+  float* te_s = reinterpret_cast<float*>(dn_smem);
+  // attention scratch (inside `big`)
+  bf16* q_s = reinterpret_cast<bf16*>(big);                                            // [16][HD+8]
+  float* s_s = reinterpret_cast<float*>(q_s + 16 * ldq);                               // [16][DNC_MAXK+16]
+  bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * LDS);                                 // [16][DNC_MAXK+8]
+  float* ks_s = reinterpret_cast<float*>(p_s + 16 * LDP);                              // [16][HD]
+  bf16* qraw = reinterpret_cast<bf16*>(ks_s + 16 * HD);
+  bf16* kraw = qraw + 16 * HD;
+  bf16* vraw = kraw + 16 * HD;
+  float* psuf = reinterpret_cast<float*>(vraw + 16 * HD);                              // [16][16] p of the suffix keys
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t4 = lane & 3;
+  const int rank = blockIdx.x;  // one cluster: rank == cluster_ctarank
+  const bf16* mod = reinterpret_cast<const bf16*>(p.mod);
+  bf16* XE = reinterpret_cast<bf16*>(p.XE);
+  bf16* XE1 = reinterpret_cast<bf16*>(p.XE1);
+  bf16* qkv = reinterpret_cast<bf16*>(p.qkv);
+  bf16* act = reinterpret_cast<bf16*>(p.act);
+  const int NCHP = (Pn + DN_CK - 1) / DN_CK;
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int ng1 = D1 >> 5, ngo = OD >> 5, ngf = F1 >> 5;
+  int q_tb, q_te, o_tb, o_te, f_pb, f_pe;
+  dn_range(QKV / 8, q_tb, q_te);
+  dn_range(D1 / 8, o_tb, o_te);
+  dn_range(F1 / 8, f_pb, f_pe);
+  unsigned long long prof_last = 0;
+  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  auto tick = [&](int slot) {
+    if (prof_on) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (slot >= 0) p.prof[slot] += now - prof_last;
+      prof_last = now;
+    }
+  };
+  tick(-1);
+
+  // =========================== prologue: time conditioning of every step ===========================
+  {
+    const int halfw = D1 / 2;
+    for (int i = threadIdx.x; i < S * halfw; i += DN_THREADS) {
+      const int r = i / halfw, c = i % halfw;
+      const float fraction = (halfw > 1) ? (float)c / (float)(halfw - 1) : 0.f;
+      const float period = 4e-3f * powf(4.0f / 4e-3f, fraction);
+      const float inp = p.times[r] * (1.0f / period * 2.0f * 3.14159265358979323846f);
+      float sn, cs;
+      sincosf(inp, &sn, &cs);
+      te_s[r * D1 + c] = sn;
+      te_s[r * D1 + halfw + c] = cs;
+    }
+    __syncthreads();
+    dn_time_mlp(te_s, S, D1, p.tin_w, p.tin_b, p.s1, nullptr);
+    cluster_sync_all();
+    for (int i = threadIdx.x; i < S * D1; i += DN_THREADS) te_s[i] = __ldcg(p.s1 + i);
+    __syncthreads();
+    dn_time_mlp(te_s, S, D1, p.tout_w, p.tout_b, nullptr, reinterpret_cast<bf16*>(p.cond16));
+    cluster_sync_all();
+    // mod = cond16 @ mod_w^T + mod_b (rows = steps): a warp owns whole tiles
+    dn_stage(reinterpret_cast<const bf16*>(p.cond16), D1, h_s, ldh, S, D1);
+    dn_cp_wait_all();
+    __syncthreads();
+    int tb, te;
+    dn_range(nm3 / 8, tb, te);
+    const bf16* mw = reinterpret_cast<const bf16*>(p.mod_w);
+    for (int tile = tb + warp; tile < te; tile += DN_WARPS) {
+      float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      dnc_warp_tile(h_s, ldh, S, mw + (long)tile * 8 * D1, D1, 0, ng1, acc);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int m = g + (j >> 1) * 8, n = tile * 8 + 2 * t4 + (j & 1);
+        if (m < S) reinterpret_cast<bf16*>(p.mod)[(long)m * nm3 + n] = __float2bfloat16_rn(bf16r(acc[j]) + bf16r(p.mod_b[n]));
+      }
+    }
+    for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) x_s[i] = p.x[i];
+    for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+      const int m = i / half, d = i % half;
+      float sn, cs;
+      sincosf((float)p.pos[m] / p.timescale[d], &sn, &cs);
+      rope_s[i] = make_float2(cs, sn);
+    }
+    for (int i = threadIdx.x; i < A * W32; i += DN_THREADS) bits_s[(i / W32) * 32 + (i % W32)] = p.bits[i];
+    cluster_sync_all();
+    tick(0);
+  }
+
+  // attention role of this CTA: (head, half of the prefix chunks); the second half also owns the suffix keys
+  const int at_h = rank >> 1, at_half = rank & 1;
+  const int c_first = (NCHP + 1) / 2;
+  const int c_begin = at_half ? c_first : 0, c_end = at_half ? NCHP : c_first;
+  const int key0 = c_begin * DN_CK, nk = (c_end - c_begin) * DN_CK;  // nk <= DNC_MAXK
+  const bool at_active = at_h < NH;
+
+  for (int step = 0; step < S; ++step) {
+    const bf16* mod_s = mod + (long)step * nm3;
+    for (int i = threadIdx.x; i < A * D1; i += DN_THREADS) {
+      const int m = i / D1, n = i % D1;
+      float v = 0.f;
+      for (int j = 0; j < ad; ++j) v += x_s[m * ad + j] * __ldg(p.ain_w + (long)n * ad + j);
+      xe_s[i] = __float2bfloat16_rn(v + __ldg(p.ain_b + n));
+    }
+    __syncthreads();
+    tick(1);
+
+    for (int l = 0; l < L; ++l) {
+      const bf16* Wqkv = reinterpret_cast<const bf16*>(p.qkv_w) + (long)l * p.qkv_ls;
+      const bf16* Wo = reinterpret_cast<const bf16*>(p.o_w) + (long)l * p.o_ls;
+      const bf16* Wgu = reinterpret_cast<const bf16*>(p.gu_w) + (long)l * p.gu_ls;
+      const bf16* Wd = reinterpret_cast<const bf16*>(p.down_w) + (long)l * p.down_ls;
+      const bf16* Kc = reinterpret_cast<const bf16*>(p.Kc) + (long)l * p.kc_ls;
+      const bf16* VcT = reinterpret_cast<const bf16*>(p.VcT) + (long)l * p.vct_ls;
+      const bf16* mod_a = mod_sm;
+      const bf16* mod_f = mod_sm + 3 * D1;
+
+      // ---------------- P1: h = adaRMS(XE); qkv = h Wqkv^T (warp = tile) ----------------
+      if (l > 0) dn_stage(XE, D1, xe_s, D1, A, D1);
+      dn_stage(mod_s + (long)(2 * l) * 3 * D1, 0, mod_sm, 0, 1, 6 * D1);
+      dn_cp_wait_all();
+      __syncthreads();
+      dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_a);
+      __syncthreads();
+      for (int tile = q_tb + warp; tile < q_te; tile += DN_WARPS) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        dnc_warp_tile(h_s, ldh, A, Wqkv + (long)tile * 8 * D1, D1, 0, ng1, acc);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const int m = g + (j >> 1) * 8;
+          if (m < A)
+            *reinterpret_cast<uint32_t*>(qkv + (long)m * QKV + tile * 8 + 2 * t4) = pack_bf16x2(acc[j], acc[j + 1]);
+        }
+      }
+      tick(2);
+      cluster_sync_all();
+      tick(3);
+
+      // ---------------- P2: attention partial of (head, key half) ----------------
+      if (at_active) {
+        dn_stage(qkv + at_h * HD, QKV, qraw, HD, A, HD);
+        if (at_half) {
+          dn_stage(qkv + NH * HD, QKV, kraw, HD, A, HD);
+          dn_stage(qkv + (NH + 1) * HD, QKV, vraw, HD, A, HD);
+        }
+        dn_cp_wait_all();
+        __syncthreads();
+        for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+          const int m = i / half, d = i % half;
+          const float cs = rope_s[i].x, sn = rope_s[i].y;
+          const float x1 = __bfloat162float(qraw[m * HD + d]), x2 = __bfloat162float(qraw[m * HD + half + d]);
+          q_s[m * ldq + d] = __float2bfloat16_rn(bf16r(x1 * cs - x2 * sn) * p.qscale);
+          q_s[m * ldq + half + d] = __float2bfloat16_rn(bf16r(x2 * cs + x1 * sn) * p.qscale);
+          if (at_half) {
+            const float k1 = __bfloat162float(kraw[m * HD + d]), k2 = __bfloat162float(kraw[m * HD + half + d]);
+            ks_s[m * HD + d] = bf16r(k1 * cs - k2 * sn);
+            ks_s[m * HD + half + d] = bf16r(k2 * cs + k1 * sn);
+          }
+        }
+        __syncthreads();
+        // S = Q_h K^T over this CTA's prefix keys: a warp owns 8-key tiles (full K = HD)
+        for (int tl = warp; tl < nk / 8; tl += DN_WARPS) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          dnc_warp_tile(q_s, ldq, A, Kc + (long)(key0 + 8 * tl) * HD, HD, 0, HD / 32, acc);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = g + (j >> 1) * 8, kk = 8 * tl + 2 * t4 + (j & 1), key = key0 + kk;
+            bool ok = false;
+            if (m < A && key < Pn) ok = (bits_s[m * 32 + (key >> 5)] >> (key & 31)) & 1u;
+            s_s[m * LDS + kk] = ok ? acc[j] : DN_BIG_NEG;
+          }
+        }
+        if (at_half) {  // logits of the suffix keys: warp per (query a, key a2)
+          for (int pr = warp; pr < A * A; pr += DN_WARPS) {
+            const int a = pr / A, a2 = pr % A;
+            float sacc = 0.f;
+            for (int d = lane; d < HD; d += 32) sacc += __bfloat162float(q_s[a * ldq + d]) * ks_s[a2 * HD + d];
+            sacc = warp_sum(sacc);
+            if (lane == 0) {
+              const int key = Pn + a2;
+              const bool ok = (bits_s[a * 32 + (key >> 5)] >> (key & 31)) & 1u;
+              s_s[a * LDS + nk + a2] = ok ? sacc : DN_BIG_NEG;
+            }
+          }
+        }
+        __syncthreads();
+        // softmax over the CTA's keys: warp m -> row m
+        float* pml = p.part_ml + (long)rank * 16 * 2;
+        if (warp < A) {
+          const int m = warp, ncol = nk + (at_half ? A : 0);
+          float mx = -3.4e38f;
+          for (int c = lane; c < ncol; c += 32) mx = fmaxf(mx, s_s[m * LDS + c]);
+          mx = warp_max(mx);
+          float sum = 0.f;
+          for (int c = lane; c < ncol; c += 32) {
+            const float e = __expf(s_s[m * LDS + c] - mx);
+            sum += e;
+            if (c < nk) p_s[m * LDP + c] = __float2bfloat16_rn(e);
+            else psuf[m * 16 + (c - nk)] = bf16r(e);
+          }
+          sum = warp_sum(sum);
+          if (lane == 0) {
+            pml[m * 2] = mx;
+            pml[m * 2 + 1] = sum;
+          }
+        }
+        __syncthreads();
+        // O_partial = P V: warp w -> head-dim tile w; prefix keys by MMA from V^T, suffix keys on the CUDA cores
+        float* po = p.part_o + (long)rank * 16 * HD;
+        if (warp < HD / 8) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          dnc_warp_tile(p_s, LDP, A, VcT + (long)(warp * 8) * p.TpadK + key0, p.TpadK, 0, nk / 32, acc);
+          if (at_half) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = g + (j >> 1) * 8, d = warp * 8 + 2 * t4 + (j & 1);
+              if (m < A) {
+                float o = 0.f;
+                for (int a2 = 0; a2 < A; ++a2) o += psuf[m * 16 + a2] * __bfloat162float(vraw[a2 * HD + d]);
+                acc[j] += o;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int m = g + (j >> 1) * 8, d = warp * 8 + 2 * t4 + (j & 1);
+            if (m < A) po[m * HD + d] = acc[j];
+          }
+        }
+      }
+      tick(4);
+      cluster_sync_all();
+      tick(5);
+
+      // ---------------- P3: combine the two halves of every head -> O (staged), XE1 = XE + gate_a * (O Wo^T) ----------------
+      for (int i = threadIdx.x; i < A * OD; i += DN_THREADS) {
+        const int m = i / OD, c = i - m * OD, h = c / HD, d = c - h * HD;
+        const float* ml0 = p.part_ml + ((long)(2 * h) * 16 + m) * 2;
+        const float* ml1 = p.part_ml + ((long)(2 * h + 1) * 16 + m) * 2;
+        const float m0 = __ldcg(ml0), l0 = __ldcg(ml0 + 1), m1 = __ldcg(ml1), l1 = __ldcg(ml1 + 1);
+        const float o0 = __ldcg(p.part_o + ((long)(2 * h) * 16 + m) * HD + d);
+        const float o1 = __ldcg(p.part_o + ((long)(2 * h + 1) * 16 + m) * HD + d);
+        const float mx = fmaxf(m0, m1);
+        const float w0 = __expf(m0 - mx), w1 = __expf(m1 - mx);
+        h_s[m * ldo + c] = __float2bfloat16_rn((w0 * o0 + w1 * o1) / (w0 * l0 + w1 * l1));
+      }
+      __syncthreads();
+      tick(6);
+      {
+        const int tl = warp & 7, kq = warp >> 3;  // 8 tiles x 4 K-quarters
+        for (int t0 = o_tb; t0 < o_te; t0 += 8) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int gq = (ngo + 3) / 4;
+          if (t0 + tl < o_te)
+            dnc_warp_tile(h_s, ldo, A, Wo + (long)(t0 + tl) * 8 * OD, OD, kq * gq, min(ngo, (kq + 1) * gq), acc);
+          *reinterpret_cast<float4*>(red + (((kq * 8 + tl) * 32 + lane) << 2)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          __syncthreads();
+          {
+            const int e = threadIdx.x, et = e >> 7, m = (e >> 3) & 15, cc = e & 7;
+            if (m < A && t0 + et < o_te) {
+              const int src_lane = (m & 7) * 4 + (cc >> 1), idx = (m >> 3) * 2 + (cc & 1);
+              float v = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v += red[((q * 8 + et) * 32 + src_lane) * 4 + idx];
+              const int n = (t0 + et) * 8 + cc;
+              const float y = bf16r(v);
+              const float gt = __bfloat162float(mod_a[2 * D1 + n]);
+              const float r = __bfloat162float(xe_s[m * D1 + n]);
+              XE1[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
+            }
+          }
+          __syncthreads();
+        }
+      }
+      tick(8);
+      cluster_sync_all();
+      tick(9);
+
+      // ---------------- P4: h = adaRMS(XE1); act = gelu(h Wg^T) * (h Wu^T) (warp = gate/up tile pair) ----------------
+      dn_stage(XE1, D1, xe_s, D1, A, D1);
+      dn_cp_wait_all();
+      __syncthreads();
+      dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_f);
+      __syncthreads();
+      for (int pr = f_pb + warp; pr < f_pe; pr += DN_WARPS) {
+        float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
+        dnc_warp_tile(h_s, ldh, A, Wgu + (long)pr * 8 * D1, D1, 0, ng1, ag);
+        dnc_warp_tile(h_s, ldh, A, Wgu + ((long)F1 + (long)pr * 8) * D1, D1, 0, ng1, au);
+#pragma unroll
+        for (int j = 0; j < 4; j += 2) {
+          const int m = g + (j >> 1) * 8;
+          if (m < A) {
+            const float a0 = bf16r(gelu_tanh(bf16r(ag[j]))) * bf16r(au[j]);
+            const float a1 = bf16r(gelu_tanh(bf16r(ag[j + 1]))) * bf16r(au[j + 1]);
+            *reinterpret_cast<uint32_t*>(act + (long)m * F1 + pr * 8 + 2 * t4) = pack_bf16x2(a0, a1);
+          }
+        }
+      }
+      tick(10);
+      cluster_sync_all();
+      tick(11);
+
+      // ---------------- P5: XE = XE1 + gate_f * (act Wd^T) ----------------
+      dn_stage(act, F1, h_s, ldf, A, F1);
+      dn_cp_wait_all();
+      __syncthreads();
+      {
+        const int tl = warp & 7, kq = warp >> 3;
+        for (int t0 = o_tb; t0 < o_te; t0 += 8) {
+          float acc[4] = {0.f, 0.f, 0.f, 0.f};
+          const int gq = (ngf + 3) / 4;
+          if (t0 + tl < o_te)
+            dnc_warp_tile(h_s, ldf, A, Wd + (long)(t0 + tl) * 8 * F1, F1, kq * gq, min(ngf, (kq + 1) * gq), acc);
+          *reinterpret_cast<float4*>(red + (((kq * 8 + tl) * 32 + lane) << 2)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+          __syncthreads();
+          {
+            const int e = threadIdx.x, et = e >> 7, m = (e >> 3) & 15, cc = e & 7;
+            if (m < A && t0 + et < o_te) {
+              const int src_lane = (m & 7) * 4 + (cc >> 1), idx = (m >> 3) * 2 + (cc & 1);
+              float v = 0.f;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) v += red[((q * 8 + et) * 32 + src_lane) * 4 + idx];
+              const int n = (t0 + et) * 8 + cc;
+              const float y = bf16r(v);
+              const float gt = __bfloat162float(mod_f[2 * D1 + n]);
+              const float r = __bfloat162float(xe_s[m * D1 + n]);
+              XE[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
+            }
+          }
+          __syncthreads();
+        }
+      }
+      tick(12);
+      cluster_sync_all();
+      tick(13);
+    }
+
+    // ---------------- final: v = action_out_proj(adaRMS(XE)); x += dt * v ----------------
+    dn_stage(XE, D1, xe_s, D1, A, D1);
+    dn_stage(mod_s + (long)(p.nm - 1) * 3 * D1, 0, mod_sm, 0, 1, 2 * D1);
+    dn_cp_wait_all();
+    __syncthreads();
+    dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_sm);
+    __syncthreads();
+    for (int o = warp; o < A * ad; o += DN_WARPS) {
+      const int m = o / ad, j = o % ad;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = lane; k < D1; k += 32) acc += __ldg(p.aout_w + (long)j * D1 + k) * __bfloat162float(h_s[m * ldh + k]);
+      acc = warp_sum(acc);
+      if (lane == 0) x_s[o] += p.dt * (acc + __ldg(p.aout_b + j));
+    }
+    __syncthreads();
+    tick(14);
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) p.x[i] = x_s[i];
+}
+
 // V^T of the prefix part of the KV cache: VcT[l][d][j] = Vc[l][j][d], j < TpadK (zero beyond Pn) — written once per
 // inference after the prefix pass so that P V in the denoise loop reads keys contiguously (mma.sync B operand).
 __global__ void transpose_v_kernel(const bf16* __restrict__ Vc, bf16* __restrict__ VcT, int Tpad, int TpadK, int HD, int Pn) {
@@ -832,6 +1270,38 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
                "denoise_loop: unsupported shape (A=%d ad=%d D1=%d NH=%d HD=%d F1=%d Pn=%d Tpad=%d steps=%d)", p.A, p.ad,
                p.D1, p.NH, p.HD, p.F1, p.Pn, p.Tpad, p.num_steps);
   LAPB_REQUIRE(p.TpadK == ((p.Pn + DN_CK - 1) / DN_CK) * DN_CK, "denoise_loop: TpadK must be round_up(Pn, 64)");
+  // Two partitionings of the same loop: "cluster" = one 16-CTA thread-block cluster (hardware cluster barriers; needs
+  // 8 query heads so that (head, key half) maps onto the 16 CTAs), "grid" = one CTA per SM with grid barriers.
+  static int mode = -1;  // 0 grid, 1 cluster
+  if (mode < 0) {
+    const char* e = getenv("LAPB_DENOISE_MODE");
+    mode = (e && e[0] == 'c') ? 1 : 0;  // default: grid (measured faster, see the K10c header)
+  }
+  const size_t csmem = dnc_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
+  if (mode == 1 && p.NH * 2 <= DNC_CTAS && p.TpadK <= 2 * DNC_MAXK && csmem <= (size_t)227 * 1024) {
+    static size_t cconf = 0;
+    if (csmem > cconf) {
+      LAPB_CUDA_OK(cudaFuncSetAttribute(denoise_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
+      LAPB_CUDA_OK(cudaFuncSetAttribute(denoise_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+      cconf = csmem;
+    }
+    cudaLaunchConfig_t ccfg = {};
+    ccfg.gridDim = dim3(DNC_CTAS);
+    ccfg.blockDim = dim3(DN_THREADS);
+    ccfg.dynamicSmemBytes = csmem;
+    ccfg.stream = STREAM(s);
+    cudaLaunchAttribute cattr[1];
+    cattr[0].id = cudaLaunchAttributeClusterDimension;
+    cattr[0].val.clusterDim.x = DNC_CTAS;
+    cattr[0].val.clusterDim.y = 1;
+    cattr[0].val.clusterDim.z = 1;
+    ccfg.attrs = cattr;
+    ccfg.numAttrs = 1;
+    const cudaError_t ce = cudaLaunchKernelEx(&ccfg, denoise_cluster_kernel, p);
+    if (ce == cudaSuccess) return 0;
+    (void)cudaGetLastError();  // e.g. no GPC with 16 free SMs for the cluster: use the grid kernel from now on
+    mode = 0;
+  }
   const size_t smem = dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
   LAPB_REQUIRE(smem <= 227 * 1024, "denoise_loop: needs %zu bytes of shared memory (> 227 KB)", smem);
   static size_t configured = 0;
