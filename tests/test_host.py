@@ -119,3 +119,32 @@ def test_config_registry():
     assert c.optimizer.weight_decay == 1e-4 and c.ema_schedule_choice.kind == "constant"
     with pytest.raises(ValueError):
         get_config("nope")
+
+
+def test_transforms_match_reference_source():
+    """lap_b200.transforms (Normalize / Unnormalize / PadStates) against the reference classes executed from
+    src/lap/transforms.py (fixture: tests/golden/reference_transforms.npz, make_reference_transforms_golden.py)."""
+    import os
+    from lap_b200 import transforms as T
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "reference_transforms.npz"))
+    stats = T.NormStats(**{k: g[f"stats/{k}"] for k in ("mean", "std", "q01", "q99", "min", "max")})
+    ns = {k: stats for k in ("state", "actions", "wide")}
+    data = {k: g[f"data/{k}"] for k in ("state", "actions", "wide", "untouched")}
+    for kind in ("normal", "bounds", "bounds_q99"):
+        out = T.Normalize({k: v for k, v in ns.items() if k != "wide"}, kind)({k: v.copy() for k, v in data.items()})
+        for k in data:
+            np.testing.assert_array_equal(np.asarray(out[k]), g[f"normalize/{kind}/{k}"])
+        out = T.Unnormalize(ns, T.NormalizationType(kind))({k: v.copy() for k, v in data.items()})
+        for k in data:
+            np.testing.assert_array_equal(np.asarray(out[k]), g[f"unnormalize/{kind}/{k}"])
+    np.testing.assert_array_equal(T.PadStates(32)({"state": data["state"].copy()})["state"], g["padstates/short"])
+    np.testing.assert_array_equal(T.PadStates(4)({"state": data["state"].copy()})["state"], g["padstates/long"])
+    # round trip and error behaviour
+    x = T.Unnormalize(ns, "bounds_q99")(T.Normalize(ns, "bounds_q99")({"actions": data["actions"].copy()}))["actions"]
+    keep = stats.q01 != stats.q99
+    np.testing.assert_allclose(x[:, keep], data["actions"][:, keep], rtol=1e-9, atol=1e-9)
+    with pytest.raises(ValueError):
+        T.Normalize({"state": T.NormStats(mean=stats.mean, std=stats.std)}, "bounds_q99")
+    with pytest.raises(ValueError):
+        T.Normalize(ns, "normal", strict=True)({"state": data["state"]})
+    assert T.Normalize(None)({"a": 1}) == {"a": 1}
