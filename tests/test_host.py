@@ -1,5 +1,6 @@
 """CPU tests of the host side: parameter tree mapping, layout, C-ABI library loading and symbol export, error paths."""
 import ctypes
+import os
 import math
 
 import numpy as np
@@ -148,3 +149,50 @@ def test_transforms_match_reference_source():
     with pytest.raises(ValueError):
         T.Normalize(ns, "normal", strict=True)({"state": data["state"]})
     assert T.Normalize(None)({"a": 1}) == {"a": 1}
+
+
+def test_tokenizer_masks_match_reference_source():
+    """N2 second slice: `CoTTokenizer.tokenize` against `PaligemmaTokenizer.tokenize` of the reference executed from source
+    with its real "lap" prompt format (tests/golden/make_reference_tokenizer_golden.py).  Bit-exact: tokens and all five masks,
+    incl. truncation inside the prompt / inside the reasoning and the seeded reasoning dropout."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    from lap_b200 import tokenizer as tk
+    from tests.golden.make_reference_tokenizer_golden import CASES
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, "reference_tokenizer.npz"))
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(gold, "tiny_sp.model"))
+    assert int(z["n_cases"]) == len(CASES)
+
+    class StoredFormat:  # the prompt STRING is the injected part; everything after it is under test
+        def __init__(self, text):
+            self.text = text
+        def format_prompt(self, prompt, state, state_type, **kw):
+            return self.text
+        direction_token_checker = staticmethod(tk.is_direction_natural)
+
+    seen_number = seen_direction = seen_drop = 0
+    for i, c in enumerate(CASES):
+        fmt = StoredFormat(bytes(z[f"{i}/formatted"]).decode())
+        t = tk.CoTTokenizer(sp, max_len=c["max_len"], prompt_format=fmt, reasoning_mask_prob=c.get("reasoning_mask_prob", 0.0))
+        if "seed" in c:
+            np.random.seed(c["seed"])
+        res = t.tokenize(c["prompt"], c["reasoning"], state=c.get("state"), state_type=c.get("state_type"))
+        for name, v in zip(("tokens", "attn", "reasoning", "number", "direction", "loss"), res):
+            key = f"{i}/{name}"
+            if v is None:
+                assert key not in z, key
+                continue
+            assert v.dtype == z[key].dtype and v.shape == z[key].shape, key
+            np.testing.assert_array_equal(v, z[key], err_msg=key)
+        assert res[0].dtype == np.int32 and len(res[0]) == c["max_len"]
+        if res[3] is not None:
+            seen_number += int(res[3].sum()); seen_direction += int(res[4].sum())
+            seen_drop += int((~res[5]).sum())
+        expect = [p for p in ("right", "-", "+3", "back", "7", "cm") if tk.is_direction_natural(p)]
+        assert "\x00".join(expect).encode() == bytes(z[f"{i}/direction_pieces"])
+    assert seen_number > 0 and seen_direction > 0 and seen_drop > 0   # the fixture exercises every mask
+    # decode() drops out-of-vocabulary ids (tokenizer.py:317-326)
+    t = tk.CoTTokenizer(sp, max_len=16, prompt_format=StoredFormat("x"))
+    ids = sp.encode("move left 2 cm")
+    assert t.decode(np.asarray(ids + [10_000, -1])) == "move left 2 cm"
