@@ -4,43 +4,39 @@
 (src/lap/models/prompt_utils/checkers.py:4-6).
 
 What is injected instead of restated: the SentencePiece processor (the reference downloads
-gs://big_vision/paligemma_tokenizer.model; any `sentencepiece.SentencePieceProcessor` works) and the prompt FORMAT — an object
-with `format_prompt(prompt, state, state_type, *, time_horizon_seconds, frame_description, state_dropout) -> str` and
-`direction_token_checker(piece) -> bool`, e.g. the reference's own `PROMPT_FORMAT_REGISTRY["lap"]`
-(src/lap/models/prompt_utils/prompt.py is plain Python).  Everything downstream of the formatted string — BOS/EOS
+gs://big_vision/paligemma_tokenizer.model; any `sentencepiece.SentencePieceProcessor` works).  The prompt format is a
+registry name or an object with `format_prompt(...) -> str` and `direction_token_checker(piece) -> bool`
+(`lap_b200.prompt_format`, or the reference's own `PromptFormat`).  Everything downstream of the formatted string — BOS/EOS
 placement, truncation, `tokenized_prompt_mask`, `tokenized_langact_mask`, `token_loss_mask`, number / direction masks,
 right padding — is bit-exact against the reference method executed from source
 (tests/golden/make_reference_tokenizer_golden.py -> tests/golden/reference_tokenizer.npz).
 """
 from __future__ import annotations
 
-import re
-
 import numpy as np
 
-
-def is_number(piece: str) -> bool:
-    """checkers.py:4-6."""
-    return bool(re.search(r"[0-9]", piece))
+from .prompt_format import (DEFAULT_VQA_PROMPT_FORMAT, PREDICTION_PROMPT_FORMAT_REGISTRY, PROMPT_FORMAT_REGISTRY,
+                            is_direction_natural, is_number)  # noqa: F401  (re-exported)
 
 
-_DIRECTION_WORDS = ("right", "left", "forward", "up", "down", "back", "clockwise", "counterclockwise")
-
-
-def is_direction_natural(piece: str) -> bool:
-    """checkers.py:9-13 - the `direction_token_checker` of the "lap" prompt format."""
-    low = piece.lower()
-    return any(w in low for w in _DIRECTION_WORDS)
+def _resolve(fmt, registry, what):
+    """tokenizer.py:51-71: a registry name or a format object."""
+    if isinstance(fmt, str):
+        if fmt not in registry:
+            raise ValueError(f"Unknown {what}: {fmt}. Available formats: {list(registry.keys())}")
+        return registry[fmt]
+    return fmt
 
 
 class CoTTokenizer:
-    def __init__(self, sp_processor, max_len: int = 48, prompt_format=None, vqa_format=None, prediction_format=None,
+    def __init__(self, sp_processor, max_len: int = 48, prompt_format="lap", prediction_format="default",
                  reasoning_mask_prob: float = 0.0):
+        """tokenizer.py:221-235 with the processor passed in (`sentencepiece.SentencePieceProcessor(model_file=...)`)."""
         self._tokenizer = sp_processor
         self._max_len = int(max_len)
-        self._prompt_format = prompt_format
-        self._vqa_format = vqa_format if vqa_format is not None else prompt_format
-        self._prediction_format = prediction_format if prediction_format is not None else prompt_format
+        self._prompt_format = _resolve(prompt_format, PROMPT_FORMAT_REGISTRY, "prompt format")
+        self._prediction_format = _resolve(prediction_format, PREDICTION_PROMPT_FORMAT_REGISTRY, "prediction format")
+        self._vqa_format = DEFAULT_VQA_PROMPT_FORMAT
         self.reasoning_mask_prob = float(reasoning_mask_prob)
 
     # tokenizer.py:93-103

@@ -178,6 +178,12 @@ def test_tokenizer_masks_match_reference_source():
         if "seed" in c:
             np.random.seed(c["seed"])
         res = t.tokenize(c["prompt"], c["reasoning"], state=c.get("state"), state_type=c.get("state_type"))
+        # ... and the whole chain with this repo's own "lap" format instead of the stored string
+        t2 = tk.CoTTokenizer(sp, max_len=c["max_len"], prompt_format="lap", reasoning_mask_prob=c.get("reasoning_mask_prob", 0.0))
+        if "seed" in c:
+            np.random.seed(c["seed"])
+        res2 = t2.tokenize(c["prompt"], c["reasoning"], state=c.get("state"), state_type=c.get("state_type"))
+        assert all((a is None and b is None) or np.array_equal(a, b) for a, b in zip(res, res2))
         for name, v in zip(("tokens", "attn", "reasoning", "number", "direction", "loss"), res):
             key = f"{i}/{name}"
             if v is None:
@@ -196,3 +202,38 @@ def test_tokenizer_masks_match_reference_source():
     t = tk.CoTTokenizer(sp, max_len=16, prompt_format=StoredFormat("x"))
     ids = sp.encode("move left 2 cm")
     assert t.decode(np.asarray(ids + [10_000, -1])) == "move left 2 cm"
+    with pytest.raises(ValueError, match="Unknown prompt format"):
+        tk.CoTTokenizer(sp, prompt_format="nope")
+
+
+def test_prompt_formats_match_reference_source():
+    """N2 third slice: every registered prompt format, the state discretisation and the token-piece checkers against the
+    reference modules executed from source (tests/golden/make_reference_prompt_golden.py).  Strings compare byte for byte."""
+    import gzip, json, random
+    from lap_b200 import prompt_format as pf
+    from tests.golden.make_reference_prompt_golden import PIECES, PROMPTS, states
+
+    z = json.load(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "reference_prompts.json.gz"), "rt", encoding="utf-8"))
+    assert z["prompts"] == PROMPTS and z["pieces"] == PIECES
+    formats = {**{f"train/{k}": v for k, v in pf.PROMPT_FORMAT_REGISTRY.items()},
+               **{f"pred/{k}": v for k, v in pf.PREDICTION_PROMPT_FORMAT_REGISTRY.items()},
+               "vqa/default_vqa": pf.DEFAULT_VQA_PROMPT_FORMAT}
+    assert set(formats) == {r["format"] for r in z["rows"]} == set(z["include_state"])
+    st = states()
+    for r in z["rows"]:
+        got = formats[r["format"]].format_prompt(PROMPTS[r["prompt"]], st[r["state"]], r["state_type"],
+                                                  time_horizon_seconds=1.3, frame_description=r["frame"])
+        assert got == r["text"], (r, got)
+    random.seed(11)
+    drops = [pf.LAP_PROMPT_FORMAT.format_prompt("pick", st[2] if k % 3 else None, "eef_pose", state_dropout=0.5) for k in range(12)]
+    assert drops == z["drops"] and len(set(drops)) == 2
+    disc = [pf.discretize_state(s, bins=b, min_dim=m) for b, m in ((256, 10), (1000, 0), (16, 3)) for s in st[1:]]
+    assert disc == z["disc"]
+    for fname, fmt in formats.items():
+        assert fmt.include_state == z["include_state"][fname]
+        for kind in ("critical_token_checker", "direction_token_checker"):
+            fn = getattr(fmt, kind)
+            assert [bool(fn(p)) if fn is not None else None for p in PIECES] == z["checks"][f"{fname}/{kind}"], (fname, kind)
+    # the horizon template's unfilled {frame_description} raises like the reference (prompt.py:59)
+    with pytest.raises(KeyError):
+        pf.PromptFormat(name="h", include_time_horizon=True).format_prompt("x", time_horizon_seconds=1.0)
