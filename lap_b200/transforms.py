@@ -5,8 +5,8 @@ third_party/openpi/src/openpi/transforms.py:340-347,404-420,455-460 (`flatten_di
 `_assert_quantile_stats`); third_party/openpi/src/openpi/shared/normalize.py:10-14 (`NormStats`);
 src/lap/datasets/utils/helpers.py:32-37 (`NormalizationType`).  Same class names, fields, defaults and error behaviour, so a
 `Policy(model, transforms=[..., Normalize(stats, "bounds_q99")], output_transforms=[Unnormalize(stats, "bounds_q99"), ...])`
-reads like the reference's `policy_config` wiring.  Tokenisation / prompt formats need the PaliGemma SentencePiece model
-and are not part of this slice.  Checked against the reference classes executed from source
+reads like the reference's `policy_config` wiring.  `TokenizePromptAndReasoning` / `DetokenizeReasoning` /
+`SafeRepackTransform` (src/lap/transforms.py:26-147) wrap `lap_b200.tokenizer.CoTTokenizer`.  Checked against the reference classes executed from source
 (tests/golden/make_reference_transforms_golden.py -> tests/golden/reference_transforms.npz).
 """
 from __future__ import annotations
@@ -181,3 +181,81 @@ class PadStates:
     def __call__(self, data: dict) -> dict:
         data["state"] = pad_to_dim(data["state"], self.model_action_dim, axis=-1)
         return data
+
+
+@dataclasses.dataclass(frozen=True)
+class TokenizePromptAndReasoning:
+    """src/lap/transforms.py:26-110: pops `prompt` / `language_actions` / `dataset_name` / `frame_description` /
+    `time_horizon_seconds` from the sample and adds the token / mask fields `CoTObservation.from_dict` reads.
+    `language_actions` absent (inference) -> `tokenized_langact_mask` is None."""
+    tokenizer: Any
+    discrete_state_input: bool = False
+    dataset_name_pad_len: int = 100
+    verbose_mode: bool = False
+    state_dropout: float = 0.0
+
+    def __call__(self, data: dict) -> dict:
+        prompt = data.pop("prompt", None)
+        if prompt is None:
+            raise ValueError("Prompt is required")
+        if not isinstance(prompt, str):
+            prompt = prompt.item()
+        state = None
+        if self.discrete_state_input:
+            state = data.get("state", None)
+            if state is None:
+                raise ValueError("State is required.")
+        language_actions = data.pop("language_actions", None)
+        dataset_name = data.pop("dataset_name", None)
+        frame_description = data.pop("frame_description", "robot base frame")
+        sp = self.tokenizer._tokenizer
+        name_ids = sp.encode(dataset_name) if dataset_name is not None else []
+        # left padded; a name longer than the pad length is kept whole, as in the reference ([pad] * negative == [])
+        name_ids = [sp.pad_id()] * (self.dataset_name_pad_len - len(name_ids)) + name_ids
+        is_vqa_sample, is_prediction_sample = data["is_vqa_sample"], data["is_prediction_sample"]
+        time_horizon_seconds = data.pop("time_horizon_seconds", None)
+        tokens, pad_mask, reasoning_mask, number_mask, direction_mask, token_loss_mask = self.tokenizer.tokenize(
+            prompt, language_actions, state, is_vqa_sample=is_vqa_sample, is_prediction_sample=is_prediction_sample,
+            time_horizon_seconds=time_horizon_seconds, frame_description=frame_description,
+            state_dropout=self.state_dropout)
+        out = {**data, "tokenized_prompt": tokens, "tokenized_prompt_mask": pad_mask,
+               "tokenized_langact_mask": reasoning_mask, "token_loss_mask": token_loss_mask,
+               "tokenized_dataset_name": np.asarray(name_ids, dtype=np.int32)}
+        if self.verbose_mode:
+            # (np.logical_or(None, None) is None: inference samples carry no critical mask)
+            out.update(critical_token_mask=np.logical_or(number_mask, direction_mask), number_token_mask=number_mask,
+                       direction_token_mask=direction_mask)
+        return out
+
+
+@dataclasses.dataclass(frozen=True)
+class DetokenizeReasoning:
+    """src/lap/transforms.py:112-120: `tokens` (the output of `sample_tokens`) -> `reasoning` text."""
+    tokenizer: Any
+
+    def __call__(self, data: dict) -> dict:
+        if "tokens" in data:
+            return {**data, "reasoning": self.tokenizer.decode(np.asarray(data["tokens"]).squeeze().astype(np.int32))}
+        return data
+
+
+@dataclasses.dataclass(frozen=True)
+class SafeRepackTransform:
+    """src/lap/transforms.py:123-147: `structure` maps output paths to a source path or a list of fall-back source paths
+    ('/'-joined); missing sources are skipped unless `strict`."""
+    structure: Any
+    strict: bool = False
+
+    def __call__(self, data: dict) -> dict:
+        flat = flatten_dict(data)
+        out, missing = {}, []
+        for key, spec in flatten_dict(self.structure).items():
+            candidates = spec if isinstance(spec, (list, tuple)) else [spec]
+            hit = next((c for c in candidates if c in flat), None)
+            if hit is None:
+                missing.append((key, tuple(candidates)))
+            else:
+                out[key] = flat[hit]
+        if self.strict and missing:
+            raise KeyError(f"Missing source paths: {missing}")
+        return unflatten_dict(out)

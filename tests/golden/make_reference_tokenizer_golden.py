@@ -72,6 +72,54 @@ CASES = [
 ]
 
 
+TRANSFORM_CASES = [
+    dict(data=dict(prompt="pick up the red block", language_actions="move forward 3 cm and move left 2 cm",
+                   dataset_name="libero 10", is_vqa_sample=False, is_prediction_sample=False, extra=np.arange(3)),
+         kw=dict(verbose_mode=True, dataset_name_pad_len=12), max_len=96),
+    dict(data=dict(prompt=np.asarray("stack the cups"), is_vqa_sample=False, is_prediction_sample=False,
+                   frame_description="camera frame", state=np.array([0.1, -0.5, 0.9, 0.0, 0.3, -1.0, 1.0]),
+                   time_horizon_seconds=2.0),
+         kw=dict(discrete_state_input=True, dataset_name_pad_len=5), max_len=80),      # inference: no language actions
+    dict(data=dict(prompt="what is on the table", language_actions="a red block", dataset_name="a much longer name than pad",
+                   is_vqa_sample=True, is_prediction_sample=False),
+         kw=dict(verbose_mode=True, dataset_name_pad_len=4), max_len=64),              # VQA: no number/direction masks
+    dict(data=dict(prompt="which way does the arm move", language_actions="move right +3", dataset_name="p",
+                   is_vqa_sample=False, is_prediction_sample=True, state=np.array([0.2, 0.4])),
+         kw=dict(verbose_mode=True, discrete_state_input=True, dataset_name_pad_len=3), max_len=96),
+]
+REPACK = dict(structure={"images": {"base": ["observation/image", "observation/img"], "wrist": "observation/wrist"},
+                         "state": "observation/state", "gone": "observation/none"},
+              data={"observation": {"img": 1, "wrist": 2, "state": 3, "unused": 4}})
+
+
+def reference_transforms(mods, Ref, sp, fmt):
+    """TokenizePromptAndReasoning / DetokenizeReasoning / SafeRepackTransform of src/lap/transforms.py executed from source."""
+    import dataclasses
+    sys.path.insert(0, HERE)
+    import make_reference_transforms_golden as G
+    ns = G.load_reference()
+    ns.update(PaligemmaTokenizer=Ref)
+    exec(compile(G.defs(G.LAP_T, ["TokenizePromptAndReasoning", "DetokenizeReasoning", "SafeRepackTransform"]), G.LAP_T, "exec"), ns)
+    out = {}
+    for i, c in enumerate(TRANSFORM_CASES):
+        t = Ref.__new__(Ref)
+        t._tokenizer, t._max_len, t.reasoning_mask_prob = sp, c["max_len"], 0.0
+        t._prompt_format, t._prediction_format = fmt, mods["prompt"].PREDICTION_PROMPT_FORMAT_REGISTRY["default"]
+        t._vqa_format = mods["prompt"].DEFAULT_VQA_PROMPT_FORMAT
+        res = ns["TokenizePromptAndReasoning"](t, **c["kw"])(dict(c["data"]))
+        out[f"tf/{i}/keys"] = np.frombuffer("\x00".join(sorted(res)).encode(), dtype=np.uint8)
+        for k, v in res.items():
+            if v is not None and k not in c["data"]:
+                out[f"tf/{i}/{k}"] = np.asarray(v)
+        out[f"tf/{i}/none"] = np.frombuffer("\x00".join(sorted(k for k, v in res.items() if v is None)).encode(), dtype=np.uint8)
+        if i == 0:
+            det = ns["DetokenizeReasoning"](t)({"tokens": res["tokenized_prompt"][None].astype(np.int64), "a": 1})
+            out["tf/detok"] = np.frombuffer(det["reasoning"].encode(), dtype=np.uint8)
+    rp = ns["SafeRepackTransform"](REPACK["structure"])(REPACK["data"])
+    out["tf/repack"] = np.frombuffer(repr(rp).encode(), dtype=np.uint8)
+    return out
+
+
 def main():
     mods = load_prompt_utils()
     fmt = mods["prompt"].PROMPT_FORMAT_REGISTRY["lap"]
@@ -95,6 +143,7 @@ def main():
                 out[f"{i}/{name}"] = np.asarray(v)
         pieces = "\x00".join(p for p in ("right", "-", "+3", "back", "7", "cm") if fmt.direction_token_checker(p))
         out[f"{i}/direction_pieces"] = np.frombuffer(pieces.encode(), dtype=np.uint8)
+    out.update(reference_transforms(mods, Ref, sp, fmt))
     np.savez_compressed(os.path.join(HERE, "reference_tokenizer.npz"), **out)
     print({k: (v.shape if hasattr(v, "shape") else v) for k, v in list(out.items())[:9]})
 

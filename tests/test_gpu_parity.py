@@ -390,3 +390,25 @@ def test_unfused_attention_path_matches_fused():
     model.use_fused_attention = False
     l_unfused, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
     assert abs(l_fused.item() - l_unfused.item()) < 2e-4 * abs(l_unfused.item())
+
+
+def test_raw_text_samples_through_tokenizer_transform_match_oracle():
+    """Callers' side of the path: raw prompt / language-action strings -> `TokenizePromptAndReasoning` ->
+    `CoTObservation` -> loss and gradients, against the oracle on the same tokenised batch."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    from lap_b200 import prompt_format as pf, tokenizer as tk, transforms as T
+    tc, ref, model, b = _setup("debug_small", 2, seed=5, step=2)
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(GOLDEN, "tiny_sp.model"))
+    fmt = pf.PromptFormat(name="short", task_template="{prompt}", action_prefix="A: ", separator="; ",
+                          direction_token_checker=pf.is_direction_natural)
+    tf = T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp, max_len=tc.model.max_token_len, prompt_format=fmt), verbose_mode=True)
+    raw = [dict(prompt="stack the cups", language_actions="move left 2 cm and move up 1 cm"),
+           dict(prompt="open the drawer", language_actions="move left 12 cm")]
+    rows = [tf(dict(r, is_vqa_sample=False, is_prediction_sample=False)) for r in raw]
+    b = dict(b)
+    for k in ("tokenized_prompt", "tokenized_prompt_mask", "tokenized_langact_mask", "token_loss_mask"):
+        b[k] = np.stack([r[k] for r in rows])
+    b["sample_mask"] = np.ones(2, dtype=bool)
+    assert b["tokenized_langact_mask"].sum(1).min() >= 4 and b["tokenized_prompt"].max() < tc.model.vocab_size
+    assert all(r["number_token_mask"].any() and r["direction_token_mask"].any() for r in rows)
+    _grad_check(tc, ref, model, b)

@@ -237,3 +237,36 @@ def test_prompt_formats_match_reference_source():
     # the horizon template's unfilled {frame_description} raises like the reference (prompt.py:59)
     with pytest.raises(KeyError):
         pf.PromptFormat(name="h", include_time_horizon=True).format_prompt("x", time_horizon_seconds=1.0)
+
+
+def test_tokenizing_transforms_match_reference_source():
+    """`TokenizePromptAndReasoning` / `DetokenizeReasoning` / `SafeRepackTransform` against the reference classes executed from
+    src/lap/transforms.py (training, inference, VQA and prediction samples; fixture: reference_tokenizer.npz `tf/*`)."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    from lap_b200 import tokenizer as tk, transforms as T
+    from tests.golden.make_reference_tokenizer_golden import REPACK, TRANSFORM_CASES
+
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    z = np.load(os.path.join(gold, "reference_tokenizer.npz"))
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(gold, "tiny_sp.model"))
+    for i, c in enumerate(TRANSFORM_CASES):
+        t = tk.CoTTokenizer(sp, max_len=c["max_len"])
+        res = T.TokenizePromptAndReasoning(t, **c["kw"])(dict(c["data"]))
+        assert "\x00".join(sorted(res)).encode() == bytes(z[f"tf/{i}/keys"])
+        assert "\x00".join(sorted(k for k, v in res.items() if v is None)).encode() == bytes(z[f"tf/{i}/none"])
+        for k, v in res.items():
+            if v is not None and k not in c["data"]:
+                ref = z[f"tf/{i}/{k}"]
+                assert np.asarray(v).dtype == ref.dtype, k
+                np.testing.assert_array_equal(np.asarray(v), ref, err_msg=f"{i}/{k}")
+        if i == 0:
+            det = T.DetokenizeReasoning(t)({"tokens": res["tokenized_prompt"][None].astype(np.int64), "a": 1})
+            assert det["a"] == 1 and det["reasoning"].encode() == bytes(z["tf/detok"])
+            assert T.DetokenizeReasoning(t)({"a": 1}) == {"a": 1}
+    assert repr(T.SafeRepackTransform(REPACK["structure"])(REPACK["data"])).encode() == bytes(z["tf/repack"])
+    with pytest.raises(KeyError, match="Missing source paths"):
+        T.SafeRepackTransform(REPACK["structure"], strict=True)(REPACK["data"])
+    with pytest.raises(ValueError, match="Prompt is required"):
+        T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp))({"is_vqa_sample": False})
+    with pytest.raises(ValueError, match="State is required"):
+        T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp), discrete_state_input=True)({"prompt": "x"})
