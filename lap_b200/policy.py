@@ -28,9 +28,10 @@ def _compose(fns: Sequence[Callable[[dict], dict]]) -> Callable[[dict], dict]:
 
 
 def _tree_map(f, x):
+    """jax.tree.map over nested dicts; None is an empty subtree (stays None), as in JAX."""
     if isinstance(x, dict):
         return {k: _tree_map(f, v) for k, v in x.items()}
-    return f(x)
+    return None if x is None else f(x)
 
 
 class Policy:
@@ -71,3 +72,38 @@ class Policy:
     @property
     def metadata(self) -> dict[str, Any]:
         return self._metadata
+
+
+class ARPolicy:
+    """src/lap/policies/policy_adapter.py:13-61: the reasoning-decoding policy.  Wraps a `Policy`; `infer` runs the input
+    transforms, `model.sample_tokens` (greedy autoregressive decode of the language-action text) and the output transforms
+    (`DetokenizeReasoning` -> `CoTOutputs`), which see `{"state", "tokens", "raw_state"}` - batched, like the reference."""
+
+    def __init__(self, base: Policy, *, sample_kwargs: dict[str, Any] | None = None):
+        assert hasattr(base._model, "sample_tokens"), "Model must have a sample_tokens method"
+        self._base = base
+        self._ar_kwargs = sample_kwargs or {}
+
+    def __getattr__(self, name: str):
+        return getattr(self._base, name)
+
+    def infer_reasoning(self, obs: dict) -> dict:
+        from .observation import CoTObservation
+        inputs = _tree_map(lambda x: x, obs)
+        raw_state = np.array(inputs["observation"]["state"], copy=True)
+        inputs = self._base._input_transform(inputs)
+        inputs = _tree_map(lambda x: np.asarray(x)[np.newaxis, ...], inputs)
+        self._base._rng += 1
+        start = time.monotonic()
+        tokens = self._base._model.sample_tokens(self._base._rng, CoTObservation.from_dict(inputs), **self._ar_kwargs)
+        tokens = tokens.cpu().numpy() if isinstance(tokens, torch.Tensor) else np.asarray(tokens)
+        model_time = time.monotonic() - start
+        outputs = self._base._output_transform({"state": inputs["state"], "tokens": tokens, "raw_state": raw_state})
+        outputs["policy_timing"] = {"infer_ms": model_time * 1000}
+        return outputs
+
+    def infer(self, obs: dict, *, noise: np.ndarray | None = None) -> dict:
+        return self.infer_reasoning(obs)
+
+    def vqa_infer(self, obs: dict) -> dict:
+        return self.infer_reasoning(obs)

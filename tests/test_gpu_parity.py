@@ -412,3 +412,43 @@ def test_raw_text_samples_through_tokenizer_transform_match_oracle():
     assert b["tokenized_langact_mask"].sum(1).min() >= 4 and b["tokenized_prompt"].max() < tc.model.vocab_size
     assert all(r["number_token_mask"].any() and r["direction_token_mask"].any() for r in rows)
     _grad_check(tc, ref, model, b)
+
+
+def test_ar_policy_raw_request_to_parsed_action():
+    """`ARPolicy.infer` (policy_adapter.py:13-61) end to end: raw request -> CoTInputs -> tokenizer -> `sample_tokens` ->
+    DetokenizeReasoning -> CoTOutputs.  The decoded tokens equal a direct `sample_tokens` call on the same transformed inputs
+    and the action is the parse of the decoded text."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    from lap_b200 import lang_actions as LA, policy_io as IO, prompt_format as pf, tokenizer as tk, transforms as T
+    from lap_b200.observation import CoTObservation
+    from lap_b200.policy import ARPolicy, Policy
+    tc, ref, model, _ = _setup("debug_small", 1, seed=5, step=2)
+    cfg = tc.model
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(GOLDEN, "tiny_sp.model"))
+    fmt = pf.PromptFormat(name="short", task_template="{prompt}", action_prefix="A: ", separator="; ",
+                          direction_token_checker=pf.is_direction_natural)
+    tok = tk.CoTTokenizer(sp, max_len=cfg.max_token_len, prompt_format=fmt)
+    tfs = [IO.CoTInputs(action_dim=cfg.action_dim), T.TokenizePromptAndReasoning(tok), T.PadStates(cfg.action_dim)]
+    S = 6
+    pol = ARPolicy(Policy(model, transforms=tfs, output_transforms=[T.DetokenizeReasoning(tok),
+                                                                   IO.CoTOutputs("verbose_eef_with_rotation")]),
+                   sample_kwargs=dict(max_decoding_steps=S))
+    rng = np.random.default_rng(3)
+    R = cfg.image_size
+    state = np.array([0.3, -0.1, 0.4, 1.0, 0.1, 0.0, 0.0, 1.0, 0.2, 0.5])
+    req = {"observation": {"base_0_rgb": rng.integers(0, 256, (R, R, 3), dtype=np.uint8),
+                           "left_wrist_0_rgb": rng.random((3, R, R)).astype(np.float32), "state": state},
+           "prompt": b"stack the cups"}
+    out = pol.infer(req)
+    assert out["tokens"].shape == (1, S) and out["policy_timing"]["infer_ms"] > 0
+    d = req
+    for f in tfs:
+        d = f(dict(d) if f is tfs[0] else d)
+    batched = {k: ({kk: np.asarray(vv)[None] for kk, vv in v.items()} if isinstance(v, dict) else (None if v is None else np.asarray(v)[None]))
+               for k, v in d.items()}
+    direct = model.sample_tokens(0, CoTObservation.from_dict(batched), max_decoding_steps=S).cpu().numpy()
+    assert np.array_equal(out["tokens"], direct)
+    assert out["reasoning"] == tok.decode(direct.squeeze().astype(np.int32))
+    mv, grip = LA.VERBOSE_EEF_WITH_ROTATION_FORMAT.parse_language_to_deltas(out["reasoning"], initial_state=state)
+    np.testing.assert_array_equal(out["actions"], mv if grip is None else np.concatenate([mv, [grip]]))
+    assert np.array_equal(out["raw_state"], state)

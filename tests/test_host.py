@@ -270,3 +270,79 @@ def test_tokenizing_transforms_match_reference_source():
         T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp))({"is_vqa_sample": False})
     with pytest.raises(ValueError, match="State is required"):
         T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp), discrete_state_input=True)({"prompt": "x"})
+
+
+def test_language_actions_and_policy_io_match_reference_source():
+    """N2 fourth slice: action <-> text (`lap_b200.lang_actions`) and `CoTInputs` / `CoTOutputs` (`lap_b200.policy_io`) against
+    the reference modules run from source.  The SAME sweep (`run_all`) is executed on both sides; strings compare byte for
+    byte, arrays bit for bit (raw bytes), dict key order included."""
+    pytest.importorskip("scipy")
+    import gzip, json
+    from lap_b200 import lang_actions as LA, policy_io as IO
+    from tests.golden import make_reference_langaction_golden as G
+
+    ref = json.load(gzip.open(os.path.join(os.path.dirname(__file__), "golden", "reference_langactions.json.gz"), "rt", encoding="utf-8"))
+    got = json.loads(json.dumps(G.run_all(None, IO.CoTInputs, IO.CoTOutputs, LA, LA, LA, str)))
+    assert set(got) == set(ref)
+    for key in ref:
+        assert len(got[key]) == len(ref[key]), key
+        if isinstance(ref[key], list):
+            for i, (a, b) in enumerate(zip(got[key], ref[key])):
+                assert a == b, (key, i, a, b)
+        assert got[key] == ref[key], key
+    # the fixture is not vacuous: moving and idle samples, both frames, masked and unmasked cameras
+    flat = json.dumps(ref["inputs"])
+    assert '"end-effector frame"' in flat and '"robot base frame"' in flat and "move " in flat
+    assert any(ref["idle_generated"]) and not all(ref["idle_generated"])
+    with pytest.raises(ValueError, match="Unknown language action format"):
+        LA.get_language_action_format("nope")
+    with pytest.raises(NotImplementedError):
+        IO.CoTInputs(action_dim=7, enable_diverse_questions=True)
+
+
+def test_policy_and_ar_policy_host_plumbing_with_a_stub_model():
+    """`Policy.infer` / `ARPolicy.infer` (openpi policy.py:68-106, policy_adapter.py:26-50) around a stub model: transforms
+    run in order, inputs are batched to 1 (None leaves stay None), the text decoded from the model's tokens is parsed back
+    into an action, and the request dict is not modified."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    from lap_b200 import lang_actions as LA, policy_io as IO, prompt_format as pf, tokenizer as tk, transforms as T
+    from lap_b200.policy import ARPolicy, Policy
+
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(os.path.dirname(__file__), "golden", "tiny_sp.model"))
+    tok = tk.CoTTokenizer(sp, max_len=96)
+    answer = "move left 2 cm and move up 1 cm"
+    seen = {}
+
+    class Stub:
+        def sample_tokens(self, rng, obs, max_decoding_steps=8):
+            seen["obs"], seen["rng"] = obs, rng
+            ids = sp.encode(answer, add_eos=True)
+            return torch.tensor([ids + [0] * (max_decoding_steps - len(ids))], dtype=torch.int32)
+
+        def sample_actions(self, rng, obs, **kw):
+            seen["kw"] = kw
+            return torch.full((1, 10, 32), 0.5)
+
+    stats = {"actions": T.NormStats(mean=np.zeros(7), std=np.ones(7), q01=-np.ones(7), q99=np.ones(7) * 3)}
+    tfs = [IO.CoTInputs(action_dim=32), T.TokenizePromptAndReasoning(tok, discrete_state_input=True), T.PadStates(32)]
+    base = Policy(Stub(), transforms=tfs, output_transforms=[T.Unnormalize(stats, "bounds_q99")], metadata={"name": "stub"})
+    req = {"observation": {"base_0_rgb": np.full((8, 8, 3), 7, np.uint8), "state": np.linspace(-1, 1, 10)}, "prompt": "stack the cups"}
+    keys_before = set(req)
+    out = base.infer(req, noise=np.zeros((10, 32)))
+    assert out["actions"].shape == (10, 32) and seen["kw"]["noise"].shape == (1, 10, 32)
+    np.testing.assert_allclose(out["actions"][:, :7], (0.5 + 1) / 2 * (4 + 1e-6) - 1)   # BOUNDS_Q99 inverse on the 7 real dims
+    np.testing.assert_array_equal(out["actions"][:, 7:], 0.5)
+    assert set(req) == keys_before and "prompt" in req and base.metadata == {"name": "stub"}
+
+    ar = ARPolicy(Policy(Stub(), transforms=tfs, output_transforms=[T.DetokenizeReasoning(tok), IO.CoTOutputs("verbose_with_rotation")]),
+                  sample_kwargs=dict(max_decoding_steps=24))
+    out = ar.infer(req)
+    obs = seen["obs"]
+    assert obs.state.shape == (1, 32) and obs.tokenized_prompt.shape == (1, 96) and obs.tokenized_langact_mask is None
+    assert obs.image_masks["left_wrist_0_rgb"].tolist() == [False] and obs.image_masks["base_0_rgb"].tolist() == [True]
+    assert "State: " in tok.decode(obs.tokenized_prompt[0])      # the discretised state made it into the prompt
+    assert out["reasoning"] == answer
+    np.testing.assert_allclose(out["actions"], [0.0, 0.02, 0.01, 0, 0, 0])
+    assert ar.metadata == {} and out["policy_timing"]["infer_ms"] >= 0
+    mv, g = LA.VERBOSE_WITH_ROTATION_FORMAT.parse_language_to_deltas(answer + ", open gripper")
+    assert g == 1.0 and mv[1] == 0.02
