@@ -403,7 +403,7 @@ def test_raw_text_samples_through_tokenizer_transform_match_oracle():
                           direction_token_checker=pf.is_direction_natural)
     tf = T.TokenizePromptAndReasoning(tk.CoTTokenizer(sp, max_len=tc.model.max_token_len, prompt_format=fmt), verbose_mode=True)
     raw = [dict(prompt="stack the cups", language_actions="move left 2 cm and move up 1 cm"),
-           dict(prompt="open the drawer", language_actions="move left 12 cm")]
+           dict(prompt="open the drawer", language_actions="move up 12 cm and move down 3 cm")]
     rows = [tf(dict(r, is_vqa_sample=False, is_prediction_sample=False)) for r in raw]
     b = dict(b)
     for k in ("tokenized_prompt", "tokenized_prompt_mask", "tokenized_langact_mask", "token_loss_mask"):
@@ -440,15 +440,16 @@ def test_ar_policy_raw_request_to_parsed_action():
                            "left_wrist_0_rgb": rng.random((3, R, R)).astype(np.float32), "state": state},
            "prompt": b"stack the cups"}
     out = pol.infer(req)
-    assert out["tokens"].shape == (1, S) and out["policy_timing"]["infer_ms"] > 0
+    assert set(out) == {"actions", "reasoning", "policy_timing"} and out["policy_timing"]["infer_ms"] > 0
+    raw = ARPolicy(Policy(model, transforms=tfs), sample_kwargs=dict(max_decoding_steps=S)).infer(req)
+    assert raw["tokens"].shape == (1, S) and np.array_equal(raw["raw_state"], state)
     d = req
     for f in tfs:
         d = f(dict(d) if f is tfs[0] else d)
     batched = {k: ({kk: np.asarray(vv)[None] for kk, vv in v.items()} if isinstance(v, dict) else (None if v is None else np.asarray(v)[None]))
                for k, v in d.items()}
     direct = model.sample_tokens(0, CoTObservation.from_dict(batched), max_decoding_steps=S).cpu().numpy()
-    assert np.array_equal(out["tokens"], direct)
+    assert np.array_equal(raw["tokens"], direct)
     assert out["reasoning"] == tok.decode(direct.squeeze().astype(np.int32))
     mv, grip = LA.VERBOSE_EEF_WITH_ROTATION_FORMAT.parse_language_to_deltas(out["reasoning"], initial_state=state)
     np.testing.assert_array_equal(out["actions"], mv if grip is None else np.concatenate([mv, [grip]]))
-    assert np.array_equal(out["raw_state"], state)
