@@ -52,7 +52,18 @@ struct FaArgs {
   bf16* O1;
   int split_row;  // rows [0, split_row) of a sample -> O0, the rest -> O1
   int write_p;
+  int dbg;        // LAPB_FA_KNOBS builds only (tools/fa_knobs.py): bit mask of pipeline stages to skip; results are wrong
 };
+
+// Bottleneck attribution (tools/fa_knobs.py): a build with -DLAPB_FA_KNOBS can switch off one stage of the pipeline at a
+// time (1 exp2 -> FMUL, 2 pass 1, 4 the P V MMAs, 8 the P shared-memory write + TMA store, 16 the pass-2 S MMAs, 32 the
+// mask words).  In the product build FA_KNOB() is the constant false and all of it folds away.
+#ifdef LAPB_FA_KNOBS
+#define FA_KNOB(x) ((a.dbg & (x)) != 0)
+#else
+#define FA_KNOB(x) false
+#endif
+#define FA_EXP2(x) (FA_KNOB(1) ? (x) * 1e-3f : exp2f(x))
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -98,7 +109,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int q0 = blockIdx.x * FA_QT;
   const int NCH = a.NCH;
   constexpr int W_TMA = 4 * FA_WG, W_MMA = W_TMA + 1, W_ALLOC = W_TMA + 2;
-  const int U0 = (NCH + 1) / 2;  // uses of S slot 0 in pass 1
+  const int U0 = FA_KNOB(2) ? 0 : (NCH + 1) / 2;  // uses of S slot 0 in pass 1
 
   if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -170,7 +181,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         ++it;
       };
-      for (int j = 0; j < NCH; ++j) load_k_chunk(j);  // pass 1
+      if (!FA_KNOB(2))
+        for (int j = 0; j < NCH; ++j) load_k_chunk(j);  // pass 1
       load_k_chunk(0);                                // pass 2
       for (int j = 0; j < NCH; ++j) {
         const int ns = chunk_keys(j) / FA_KT;
@@ -184,7 +196,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr uint32_t idescPV = make_idesc_bf16(FA_QT, FA_HD, 0, 1);
     mbar_wait(q_full, 0);
     int it = 0;
-    auto issue_S = [&](int j, int slot, int use) {
+    auto issue_S = [&](int j, int slot, int use, bool skip = false) {
       const uint32_t idescS = make_idesc_bf16(FA_QT, chunk_keys(j), 0, 0);
       mbar_wait(&s_empty[slot], (use & 1) ^ 1);
       const uint32_t d = tmem_base + slot * FA_KC;
@@ -196,7 +208,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int kk = 0; kk < 4; ++kk) {
           uint64_t da = make_smem_desc_sw128(q_addr + c * (FA_QT * 128) + kk * 32, 16, 1024);
           uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * 32, 16, 1024);
-          umma_bf16_elect(d, da, db, idescS, (c | kk) != 0 ? 1u : 0u);
+          if (!skip) umma_bf16_elect(d, da, db, idescS, (c | kk) != 0 ? 1u : 0u);
         }
         if (CL > 1) umma_commit_mc_elect(&r_empty[st], CMASK);
         else umma_commit_elect(&r_empty[st]);
@@ -213,22 +225,23 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint64_t da = make_smem_desc_sw128(p_addr + kk * 32, 16, 1024);
         // V tile: MN-major, 4 atoms of 64 dims ([64 keys x 128 B] = 8 KB apart), 16 keys per step = 2 KB
         uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * (16 * 128), FA_KT * 128, 1024);
-        umma_bf16_elect(tmem_O, da, db, idescPV, (accumulate | (uint32_t)kk) != 0 ? 1u : 0u);
+        if (!FA_KNOB(4)) umma_bf16_elect(tmem_O, da, db, idescPV, (accumulate | (uint32_t)kk) != 0 ? 1u : 0u);
       }
       if (CL > 1) umma_commit_mc_elect(&r_empty[st], CMASK);
       else umma_commit_elect(&r_empty[st]);
       umma_commit_elect(&pv_done[s]);
       ++it;
     };
-    for (int j = 0; j < NCH; ++j) issue_S(j, j & 1, j >> 1);  // pass 1: logits only, S double-buffered
-    issue_S(0, 0, U0);                                         // pass 2
-    if (NCH / 2 > 0) mbar_wait(&s_empty[1], ((NCH / 2) - 1) & 1);  // O reuses the columns of S slot 1
+    if (!FA_KNOB(2))
+      for (int j = 0; j < NCH; ++j) issue_S(j, j & 1, j >> 1);  // pass 1: logits only, S double-buffered
+    issue_S(0, 0, U0, FA_KNOB(16));                             // pass 2
+    if (NCH / 2 > 0 && !FA_KNOB(2)) mbar_wait(&s_empty[1], ((NCH / 2) - 1) & 1);  // O reuses the columns of S slot 1
     uint32_t acc = 0;
     for (int j = 0; j < NCH; ++j) {
       const int ns = chunk_keys(j) / FA_KT;
       // S(j+1) goes first: it runs on the tensor pipe while the softmax warps spend their ~2 K MUFU cycles on chunk j
       // (its slot is free as soon as every softmax thread has pulled S(j) into registers)
-      if (j + 1 < NCH) issue_S(j + 1, 0, U0 + j + 1);
+      if (j + 1 < NCH) issue_S(j + 1, 0, U0 + j + 1, FA_KNOB(16));
       for (int s = 0; s < ns; ++s) {
         issue_PV(j, s, acc);
         acc = 1;
@@ -248,7 +261,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const float LOG2E = 1.4426950408889634f;
     float m = -3.4e38f, l = 0.f;
     // ---- pass 1: running max / sum over this warpgroup's keys ----
-    for (int j = 0; j < NCH; ++j) {
+    for (int j = 0; j < (FA_KNOB(2) ? 0 : NCH); ++j) {
       const int slot = j & 1;
       const bool active = wg * FA_KT < chunk_keys(j);
       mbar_wait(&s_full[slot], (j >> 1) & 1);
@@ -260,7 +273,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_32x32(tmem_base + lane_base + slot * FA_KC + wg * FA_KT + hf * 32, sv);
           tmem_ld_wait();
           const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
-          const uint32_t w = mrow[key0 >> 5];
+          const uint32_t w = FA_KNOB(32) ? 0xFFFFFFFFu : mrow[key0 >> 5];
           const int nvalid = a.S_len - key0;  // columns [0, nvalid) are real keys
           if (w != 0xFFFFFFFFu) {
 #pragma unroll
@@ -281,11 +294,11 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // (x - m) is formed BEFORE scaling by log2(e): for a fully masked row m = -2.38e38 and m*log2(e) would overflow
           if (nvalid >= 32) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) sum += exp2f((__uint_as_float(sv[c]) - m_new) * LOG2E);
+            for (int c = 0; c < 32; ++c) sum += FA_EXP2((__uint_as_float(sv[c]) - m_new) * LOG2E);
           } else {
 #pragma unroll
             for (int c = 0; c < 32; ++c)
-              if (c < nvalid) sum += exp2f((__uint_as_float(sv[c]) - m_new) * LOG2E);
+              if (c < nvalid) sum += FA_EXP2((__uint_as_float(sv[c]) - m_new) * LOG2E);
           }
           l = l * exp2f((m - m_new) * LOG2E) + sum;
           m = m_new;
@@ -295,6 +308,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_arrive_relaxed(&s_empty[slot]);
     }
     // combine the key slices of the warpgroups
+    if (FA_KNOB(2)) { m = 20.f; l = 1000.f; }
     stat[(wg * 128 + r) * 2 + 0] = m;
     stat[(wg * 128 + r) * 2 + 1] = l;
     softmax_bar();
@@ -330,7 +344,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (active) {
           const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
-          const uint32_t w = mrow[key0 >> 5];
+          const uint32_t w = FA_KNOB(32) ? 0xFFFFFFFFu : mrow[key0 >> 5];
           const int nvalid = a.S_len - key0;
           if (w != 0xFFFFFFFFu) {
 #pragma unroll
@@ -339,8 +353,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
 #pragma unroll
           for (int c = 0; c < 32; c += 2) {
-            float p0 = exp2f((__uint_as_float(sv[c]) - m) * LOG2E) * inv;
-            float p1 = exp2f((__uint_as_float(sv[c + 1]) - m) * LOG2E) * inv;
+            float p0 = FA_EXP2((__uint_as_float(sv[c]) - m) * LOG2E) * inv;
+            float p1 = FA_EXP2((__uint_as_float(sv[c + 1]) - m) * LOG2E) * inv;
             if (c >= nvalid) p0 = 0.f;
             if (c + 1 >= nvalid) p1 = 0.f;
             pk[hf * 16 + (c >> 1)] = pack_bf16x2(p0, p1);
@@ -359,13 +373,15 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         // K-major, 128B-swizzled A tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
         uint8_t* prow = Ps + r * 128;
+        if (!FA_KNOB(8)) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c)
-          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+          for (int c = 0; c < 8; ++c)
+            *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
         fence_proxy_async();
         wg_bar(wg);
         if (leader) {
-          if (a.write_p) {
+          if (a.write_p && !FA_KNOB(8)) {
             tma_store_4d(&tmP, Ps, j * FA_KC + wg * FA_KT, q0, b, 0);
             tma_store_commit();
           }
@@ -450,6 +466,10 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   a.B = (int)B; a.R = (int)R; a.G = (int)G; a.Tq = (int)Tq; a.S_len = (int)S_len; a.Tpad = (int)Tpad;
   a.W32 = (int)W32; a.NCH = (int)((Tpad + FA_KC - 1) / FA_KC);
   a.bits = bits; a.O0 = (bf16*)O0; a.O1 = (bf16*)O1; a.split_row = (int)split_row; a.write_p = P ? 1 : 0;
+  a.dbg = 0;
+#ifdef LAPB_FA_KNOBS
+  if (const char* e = getenv("LAPB_FA_KNOBS")) a.dbg = atoi(e);
+#endif
   static bool configured = false;
   if (!configured) {
     LAPB_CUDA_OK(cudaFuncSetAttribute(fa_gemma_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, FA_SMEM));
