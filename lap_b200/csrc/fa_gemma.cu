@@ -32,6 +32,10 @@ namespace lapb {
 typedef __nv_bfloat16 bf16;
 #define BIG_NEG (-2.3819763e38f)
 
+#ifndef FA_NPB
+#define FA_NPB 2  // P buffers.  Measured at the training shape on one box (tools/fa_variant.py, bit-identical outputs):
+#endif            // 1 buffer 273 us, 2 buffers 255 us: P V(w+1) no longer waits for P V(w) to retire before P(w+1) is written.
+                  // With more than one buffer the (m, l) exchange area is aliased onto them to stay within 227 KB.
 constexpr int FA_QT = 128;   // query rows per CTA
 constexpr int FA_KT = 64;    // keys per P V step (= keys per softmax warpgroup and chunk)
 constexpr int FA_KC = 256;   // keys per S chunk
@@ -39,11 +43,12 @@ constexpr int FA_HD = 256;   // head dim
 constexpr int FA_WG = 4;     // softmax warpgroups
 constexpr int FA_SOFT = 128 * FA_WG;
 constexpr int FA_THREADS = FA_SOFT + 96;
-constexpr int FA_NST = 4;                          // ring stages
+constexpr int FA_NST = FA_NPB >= 4 ? 3 : 4;        // ring stages (4 P buffers leave room for 3)
 constexpr int FA_Q_BYTES = FA_QT * FA_HD * 2;      // 64 KB: 4 dim-chunks of [128 rows x 128 B]
 constexpr int FA_ST_BYTES = 32 * 1024;             // a K slice [256 keys x 64 dims] or a V tile [64 keys x 256 dims]
 constexpr int FA_P_BYTES = FA_QT * FA_KT * 2;      // 16 KB
-constexpr int FA_SMEM = FA_Q_BYTES + FA_NST * FA_ST_BYTES + FA_P_BYTES + 1024 + 512 + FA_WG * 1024;
+constexpr int FA_SMEM = FA_Q_BYTES + FA_NST * FA_ST_BYTES + FA_NPB * FA_P_BYTES + 1024 + 512 + (FA_NPB == 1 ? FA_WG * 1024 : 0);
+static_assert(FA_SMEM <= 227 * 1024, "fa_gemma: shared memory");
 
 struct FaArgs {
   int B, R, G, Tq, S_len, Tpad, W32, NCH;
@@ -63,7 +68,18 @@ struct FaArgs {
 #else
 #define FA_KNOB(x) false
 #endif
+// One MUFU instruction; exp2f() without fast-math adds a range fix-up (≈3 more instructions per score) that the softmax
+// does not need: inputs are <= 0, -inf gives 0, and results below 2^-126 are far below bf16's resolution of the row sum.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#ifdef FA_PRECISE_EXP2  // measurement variant (tools/fa_variant.py)
 #define FA_EXP2(x) (FA_KNOB(1) ? (x) * 1e-3f : exp2f(x))
+#else
+#define FA_EXP2(x) (FA_KNOB(1) ? (x) * 1e-3f : ex2_approx(x))
+#endif
 
 __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem_src, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
@@ -91,7 +107,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* Qs = smem;
   uint8_t* Ring = smem + FA_Q_BYTES;
   uint8_t* Ps = Ring + FA_NST * FA_ST_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + FA_P_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + FA_NPB * FA_P_BYTES);
   uint64_t* q_full = bars;
   uint64_t* r_full = bars + 1;     // [4] ring stage filled by TMA
   uint64_t* r_empty = bars + 5;    // [4] ring stage consumed by the MMAs
@@ -102,7 +118,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* st_done = bars + 21;   // [4] TMA store of sub-tile w has read the P buffer
   uint64_t* o_full = bars + 25;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 26);
-  float* stat = reinterpret_cast<float*>(bars + 64);  // [FA_WG][128][2] (m, l) exchange between the warpgroups
+  // [FA_WG][128][2] (m, l) exchange between the warpgroups (with two P buffers it borrows them: P is not written before)
+  float* stat = FA_NPB == 1 ? reinterpret_cast<float*>(bars + 64) : reinterpret_cast<float*>(Ps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -121,6 +138,8 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int i = 0; i < FA_NST; ++i) {
       mbar_init(&r_full[i], 1);
       mbar_init(&r_empty[i], CL);  // released by the MMA warp of every CTA that received the multicast stage
+    }
+    for (int i = 0; i < FA_WG; ++i) {
       mbar_init(&p_full[i], 1);
       mbar_init(&pv_done[i], 1);
       mbar_init(&st_done[i], 1);
@@ -156,7 +175,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       int it = 0;
       auto load_k_chunk = [&](int j) {  // four 64-dim slices of 256 keys
         for (int c = 0; c < 4; ++c, ++it) {
-          const int st = it & (FA_NST - 1);
+          const int st = it % FA_NST;
           mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
           mbar_expect_tx(&r_full[st], FA_ST_BYTES);
           if (CL > 1)  // this CTA's key range of the slice, to every CTA of the cluster
@@ -167,7 +186,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       };
       auto load_v_tile = [&](int key0) {  // [64 keys x 256 dims]: 4 atoms of 64 dims ([64 keys x 128 B] each)
-        const int st = it & (FA_NST - 1);
+        const int st = it % FA_NST;
         mbar_wait(&r_empty[st], ((it / FA_NST) & 1) ^ 1);
         mbar_expect_tx(&r_full[st], FA_ST_BYTES);
 #pragma unroll
@@ -201,7 +220,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_wait(&s_empty[slot], (use & 1) ^ 1);
       const uint32_t d = tmem_base + slot * FA_KC;
       for (int c = 0; c < 4; ++c, ++it) {
-        const int st = it & (FA_NST - 1);
+        const int st = it % FA_NST;
         mbar_wait(&r_full[st], (it / FA_NST) & 1);
         tc_fence_after();
 #pragma unroll
@@ -216,13 +235,13 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       umma_commit_elect(&s_full[slot]);
     };
     auto issue_PV = [&](int j, int s, uint32_t accumulate) {
-      const int st = it & (FA_NST - 1);
+      const int st = it % FA_NST;
       mbar_wait(&p_full[s], j & 1);
       mbar_wait(&r_full[st], (it / FA_NST) & 1);
       tc_fence_after();
 #pragma unroll
       for (int kk = 0; kk < 4; ++kk) {
-        uint64_t da = make_smem_desc_sw128(p_addr + kk * 32, 16, 1024);
+        uint64_t da = make_smem_desc_sw128(p_addr + ((j * 4 + s) % FA_NPB) * FA_P_BYTES + kk * 32, 16, 1024);
         // V tile: MN-major, 4 atoms of 64 dims ([64 keys x 128 B] = 8 KB apart), 16 keys per step = 2 KB
         uint64_t db = make_smem_desc_sw128(ring_addr + st * FA_ST_BYTES + kk * (16 * 128), FA_KT * 128, 1024);
         if (!FA_KNOB(4)) umma_bf16_elect(tmem_O, da, db, idescPV, (accumulate | (uint32_t)kk) != 0 ? 1u : 0u);
@@ -322,6 +341,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l = lf;
       m = mf;
     }
+    if (FA_NPB > 1) softmax_bar();  // every thread has read the exchange area before P sub-tiles overwrite it
     // ---- pass 2: p = exp(s - max) / sum -> bf16 -> this warpgroup's P sub-tile [+ TMA store for the backward] ----
     const float inv = 1.0f / l;
     const bool leader = (warp & 3) == 0 && lane == 0;
@@ -362,17 +382,16 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
       }
       if (active) {
-        // the single P buffer is free once the previous sub-tile's P V has retired (and its TMA store has read it)
-        if (wg > 0) {
-          mbar_wait(&pv_done[wg - 1], j & 1);
-          if (a.write_p) mbar_wait(&st_done[wg - 1], j & 1);
-        } else if (j > 0) {
-          const int last = chunk_keys(j - 1) / FA_KT - 1;
-          mbar_wait(&pv_done[last], (j - 1) & 1);
-          if (a.write_p) mbar_wait(&st_done[last], (j - 1) & 1);
+        // P buffer (sub-tile n) % FA_NPB is free once the P V of sub-tile n - FA_NPB has retired (and its TMA store has read
+        // it); every chunk before the last has all four sub-tiles, so sub-tile n = 4 j + wg
+        const int prev = j * 4 + wg - FA_NPB;
+        if (prev >= 0) {
+          mbar_wait(&pv_done[prev & 3], (prev >> 2) & 1);
+          if (a.write_p) mbar_wait(&st_done[prev & 3], (prev >> 2) & 1);
         }
+        uint8_t* Pbuf = Ps + ((j * 4 + wg) % FA_NPB) * FA_P_BYTES;
         // K-major, 128B-swizzled A tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
-        uint8_t* prow = Ps + r * 128;
+        uint8_t* prow = Pbuf + r * 128;
         if (!FA_KNOB(8)) {
 #pragma unroll
           for (int c = 0; c < 8; ++c)
@@ -382,7 +401,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         wg_bar(wg);
         if (leader) {
           if (a.write_p && !FA_KNOB(8)) {
-            tma_store_4d(&tmP, Ps, j * FA_KC + wg * FA_KT, q0, b, 0);
+            tma_store_4d(&tmP, Pbuf, j * FA_KC + wg * FA_KT, q0, b, 0);
             tma_store_commit();
           }
           mbar_arrive(&p_full[wg]);
