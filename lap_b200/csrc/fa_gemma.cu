@@ -283,6 +283,13 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < (FA_KNOB(2) ? 0 : NCH); ++j) {
       const int slot = j & 1;
       const bool active = wg * FA_KT < chunk_keys(j);
+      // the two mask words of this thread's 64 keys are fetched BEFORE the wait, so their latency hides behind the MMAs
+      const int kbase = j * FA_KC + wg * FA_KT;
+      uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (active && !FA_KNOB(32)) {
+        mw[0] = mrow[kbase >> 5];
+        mw[1] = mrow[(kbase >> 5) + 1];
+      }
       mbar_wait(&s_full[slot], (j >> 1) & 1);
       tc_fence_after();
 #pragma unroll
@@ -292,7 +299,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           tmem_ld_32x32(tmem_base + lane_base + slot * FA_KC + wg * FA_KT + hf * 32, sv);
           tmem_ld_wait();
           const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
-          const uint32_t w = FA_KNOB(32) ? 0xFFFFFFFFu : mrow[key0 >> 5];
+          const uint32_t w = mw[hf];
           const int nvalid = a.S_len - key0;  // columns [0, nvalid) are real keys
           if (w != 0xFFFFFFFFu) {
 #pragma unroll
@@ -348,6 +355,12 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     for (int j = 0; j < NCH; ++j) {
       const int nkeys = chunk_keys(j);
       const bool active = wg * FA_KT < nkeys;
+      const int kbase = j * FA_KC + wg * FA_KT;
+      uint32_t mw[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+      if (active && !FA_KNOB(32)) {
+        mw[0] = mrow[kbase >> 5];
+        mw[1] = mrow[(kbase >> 5) + 1];
+      }
       mbar_wait(&s_full[0], (U0 + j) & 1);
       tc_fence_after();
       uint32_t pk[32];
@@ -364,7 +377,7 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (active) {
           const int key0 = j * FA_KC + wg * FA_KT + hf * 32;
-          const uint32_t w = FA_KNOB(32) ? 0xFFFFFFFFu : mrow[key0 >> 5];
+          const uint32_t w = mw[hf];
           const int nvalid = a.S_len - key0;
           if (w != 0xFFFFFFFFu) {
 #pragma unroll
