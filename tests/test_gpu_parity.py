@@ -453,3 +453,46 @@ def test_ar_policy_raw_request_to_parsed_action():
     assert out["reasoning"] == tok.decode(direct.squeeze().astype(np.int32))
     mv, grip = LA.VERBOSE_EEF_WITH_ROTATION_FORMAT.parse_language_to_deltas(out["reasoning"], initial_state=state)
     np.testing.assert_array_equal(out["actions"], mv if grip is None else np.concatenate([mv, [grip]]))
+
+
+def test_checkpoint_resume_restores_bit_exactly_and_continues(tmp_path):
+    """Save after two optimisation steps and restore into a FRESH train state (different random init): parameters, Adam
+    moments and EMA come back bit for bit; the third step from the restored state has a bit-identical loss (the forward is
+    deterministic) and lands on the same state up to the run-to-run noise of the split-K weight-gradient reductions
+    (reference: checkpoints.py save_state / restore_state + the resume branch of scripts/train.py).
+    `load_served_params` gives the EMA weights to a serving model."""
+    pytest.importorskip("safetensors")
+    from lap_b200 import checkpoint as C
+    from lap_b200.model import LAP
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+    tc, ref, model, _ = _setup("debug_tiny", 4, seed=0, step=1)
+    batches = [batch_from_dict(synthetic_batch(tc.model, 4, step=s)) for s in range(3)]
+    state = init_train_state(tc, model=model)
+    runner = TrainingStepRunner(tc, use_cuda_graph=False)
+    for s in range(2):
+        state, _ = runner(0, state, batches[s])
+    C.save_train_state(tmp_path, state)
+    assert C.latest_step(tmp_path) == 2
+    grab = lambda m, st: {"p": m.P.clone(), "mu": st.mu.clone(), "nu": st.nu.clone(), "ema": st.ema_params.clone()}
+    lay = model.layout
+    saved = grab(model, state)
+    state, info_a = runner(0, state, batches[2])
+    after_a = grab(model, state)
+
+    model_b = LAP(tc.model, seed=123)
+    state_b = init_train_state(tc, model=model_b)
+    assert C.restore_train_state(tmp_path, state_b) == 2 and state_b.ema_decay == state.ema_decay
+    restored = grab(model_b, state_b)
+    for k in saved:
+        assert all(torch.equal(lay.view(saved[k], n), lay.view(restored[k], n)) for n in lay.shapes), k
+    state_b, info_b = TrainingStepRunner(tc, use_cuda_graph=False)(0, state_b, batches[2])
+    assert state_b.step == 3 and float(info_a["loss"]) == float(info_b["loss"])
+    after_b = grab(model_b, state_b)
+    named = lambda flat: torch.cat([lay.view(flat, n).reshape(-1) for n in lay.shapes])   # (alignment gaps are not state)
+    for k, tol in (("p", 1e-6), ("ema", 1e-6), ("mu", 1e-4), ("nu", 1e-4)):
+        assert rel_err(named(after_b[k]), named(after_a[k])) < tol, (k, rel_err(named(after_b[k]), named(after_a[k])))
+    served = LAP(tc.model, seed=5)
+    C.load_served_params(tmp_path, served, step=2)
+    ema2 = C.load_tree(tmp_path / "2" / "params.safetensors")
+    got = served.params_reference()
+    assert all(torch.equal(got[k], ema2[k]) for k in ema2)

@@ -346,3 +346,73 @@ def test_policy_and_ar_policy_host_plumbing_with_a_stub_model():
     assert ar.metadata == {} and out["policy_timing"]["infer_ms"] >= 0
     mv, g = LA.VERBOSE_WITH_ROTATION_FORMAT.parse_language_to_deltas(answer + ", open gripper")
     assert g == 1.0 and mv[1] == 0.02
+
+
+def test_checkpoint_round_trip_in_reference_layout(tmp_path):
+    """`lap_b200.checkpoint` (reference: src/lap/training/checkpoints.py): save -> restore is bit-exact for params, Adam moments
+    and EMA; the `params` item follows the `_split_params` convention (EMA weights when EMA is on) and is a reference-layout
+    tree; `keep`, `latest_step`, unfinished saves and mismatching models behave.  Host logic only: the flat buffers live on
+    the CPU behind a stand-in with the four `LAP` members the module uses."""
+    pytest.importorskip("safetensors")
+    from lap_b200 import checkpoint as C
+    from lap_b200.train import TrainState
+
+    class CpuModel:
+        def __init__(self, cfg, seed):
+            self.cfg, self.layout = cfg, P.FlatLayout(cfg)
+            self.P = torch.randn(self.layout.total, generator=torch.Generator().manual_seed(seed))
+            self.refreshed = 0
+        def params_reference(self, flat=None):
+            eng = {k: v.detach().float().cpu() for k, v in P.engine_from_flat(self.layout, self.P if flat is None else flat).items()}
+            return P.engine_to_reference(self.cfg, eng)
+        def refresh_compute_copy(self):
+            self.refreshed += 1
+        def load_params(self, tree):
+            C._into_flat(self, self.P, tree)
+
+    cfg = get_config("debug_tiny").model
+    def state(seed, ema=True):
+        m = CpuModel(cfg, seed)
+        g = torch.Generator().manual_seed(seed + 100)
+        n = m.layout.total
+        return TrainState(step=seed, model=m, mu=torch.randn(n, generator=g), nu=torch.rand(n, generator=g),
+                          ema_params=torch.randn(n, generator=g) if ema else None, ema_decay=0.999 if ema else None)
+
+    a = state(7)
+    d = C.save_train_state(tmp_path, a, keep=2)
+    assert d == tmp_path / "7" and C.latest_step(tmp_path) == 7
+    served = C.load_tree(d / "params.safetensors")
+    assert {k: tuple(v.shape) for k, v in served.items()} == {k: tuple(s) for k, s in P.reference_shapes(cfg).items()}
+    ema_ref = a.model.params_reference(a.ema_params)
+    assert all(torch.equal(served[k], ema_ref[k]) for k in served)          # `params` item = EMA weights (checkpoints.py:529-538)
+    b = state(1)
+    assert C.restore_train_state(tmp_path, b) == 7 and b.step == 7 and b.model.refreshed == 1
+    lay = a.model.layout
+    same = lambda x, y: all(torch.equal(lay.view(x, n), lay.view(y, n)) for n in lay.shapes)   # (alignment gaps are not state)
+    for x, y in ((a.model.P, b.model.P), (a.mu, b.mu), (a.nu, b.nu), (a.ema_params, b.ema_params)):
+        assert same(x, y)
+    m = CpuModel(cfg, 3)
+    assert C.load_served_params(tmp_path, m) == 7 and same(m.P, a.ema_params)   # what serve_policy.py loads
+    # no EMA: `params` holds the raw weights, train_state carries none; restoring drops a stale EMA buffer
+    c = state(9, ema=False)
+    C.save_train_state(tmp_path, c, keep=2)
+    assert not (tmp_path / "9" / "train_state" / "params.safetensors").exists()
+    e = state(2)
+    C.restore_train_state(tmp_path, e, step=9)
+    assert same(e.model.P, c.model.P) and e.ema_params is None and e.ema_decay is None
+    # keep=2 prunes the oldest; an unfinished save (no manifest / tmp name) is never picked up
+    a.step = 11
+    C.save_train_state(tmp_path, a, keep=2)
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["11", "9"]
+    (tmp_path / "12.tmp-1").mkdir(); (tmp_path / "13").mkdir()
+    assert C.latest_step(tmp_path) == 11
+    with pytest.raises(FileNotFoundError):
+        C.restore_train_state(tmp_path, e, step=13)
+    with pytest.raises(FileNotFoundError):
+        C.restore_train_state(tmp_path / "nowhere", e)
+    other = TrainState(step=0, model=CpuModel(get_config("debug_small").model, 0), mu=None, nu=None, ema_params=None, ema_decay=None)
+    with pytest.raises(ValueError, match="different model"):
+        C.restore_train_state(tmp_path, other)
+    bad = dict(served); bad.pop(next(iter(bad)))
+    with pytest.raises(ValueError, match="missing"):
+        C._into_flat(m, m.P, bad)
