@@ -465,6 +465,10 @@ fa_gemma_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 int make_tmap_bf16_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, int64_t s1,
                       int64_t s2, int64_t s3, uint32_t box0, uint32_t box1);  // gemm.cu
 
+int fa_gemma_fwd_pair_launch(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* P, void* O0,
+                             void* O1, int64_t B, int64_t R, int64_t G, int64_t Tq, int64_t S_len, int64_t Tpad,
+                             int64_t W32, int64_t split_row, cudaStream_t stream);  // fa_gemma_pair.cu (experimental)
+
 }  // namespace lapb
 
 using namespace lapb;
@@ -477,6 +481,12 @@ extern "C" int lapb200_fa_gemma_fwd(const void* Q, const void* Kc, const void* V
   LAPB_REQUIRE(head_dim == FA_HD, "fa_gemma_fwd: head_dim must be %d (got %ld)", FA_HD, (long)head_dim);
   LAPB_REQUIRE(Tpad % FA_KT == 0 && S_len <= Tpad && W32 * 32 >= Tpad, "fa_gemma_fwd: Tpad must be a multiple of %d", FA_KT);
   LAPB_REQUIRE(R == Tq * G && split_row >= 0 && split_row <= R, "fa_gemma_fwd: inconsistent row counts");
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("LAPB_FA_PAIR");
+    pair_env = e ? atoi(e) : 0;  // experimental cta_group::2 kernel (fa_gemma_pair.cu), off by default
+  }
+  if (pair_env) return fa_gemma_fwd_pair_launch(Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, stream);
   CUtensorMap tmQ, tmK, tmV, tmP;
   int rc;
   if ((rc = make_tmap_bf16_4d(&tmQ, Q, FA_HD, R, B, 1, FA_HD, R * FA_HD, 0, 64, FA_QT))) return rc;
