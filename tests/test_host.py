@@ -416,3 +416,52 @@ def test_checkpoint_round_trip_in_reference_layout(tmp_path):
     bad = dict(served); bad.pop(next(iter(bad)))
     with pytest.raises(ValueError, match="missing"):
         C._into_flat(m, m.P, bad)
+
+
+def test_language_action_round_trip_properties():
+    """Size-independent properties of the action <-> text path (no fixture involved):
+    (1) base -> end-effector -> base frame is the identity for the default axis convention (frame_transforms.py:22-129);
+    (2) text -> deltas inverts deltas -> text up to the rounding the text format applies (1 cm, 10 degrees, gripper bit);
+    (3) a chunk is idle exactly when its summed translation rounds below 1 cm and its rotation below 10 degrees."""
+    pytest.importorskip("scipy")
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st_
+    from lap_b200 import lang_actions as LA
+
+    f = lambda lo, hi: st_.floats(lo, hi, allow_nan=False, allow_infinity=False, width=64)
+
+    @settings(max_examples=60, deadline=None)
+    @given(st_.lists(f(-0.2, 0.2), min_size=3, max_size=3), st_.lists(f(-0.6, 0.6), min_size=3, max_size=3),
+           st_.lists(f(-1, 1), min_size=6, max_size=6), f(0, 1))
+    def frames(dp, dr, r6, g):
+        r6 = np.asarray(r6)
+        a1, a2 = r6[:3], r6[3:]
+        if np.linalg.norm(a1) < 0.2 or np.linalg.norm(np.cross(a1, a2)) < 0.2 * np.linalg.norm(a1):
+            return  # degenerate 6-D rotation (no unique frame)
+        state = np.concatenate([[0.1, 0.2, 0.3], r6, [g]])
+        a = np.array([*dp, *dr, g])
+        back = LA.transform_actions_from_eef_frame(LA.transform_actions_to_eef_frame(a, state, "droid"), state, "droid")[0]
+        np.testing.assert_allclose(back, a, atol=1e-9)
+
+    @settings(max_examples=120, deadline=None)
+    @given(st_.lists(st_.lists(f(-0.08, 0.08), min_size=7, max_size=7), min_size=1, max_size=5))
+    def text(rows):
+        a = np.asarray(rows)
+        a[:, 3:6] *= 8.0                       # rotations up to ~0.6 rad per row
+        a[:, 6] = np.abs(a[:, 6]) * 12.0       # gripper in [0, ~1)
+        fmt = LA.VERBOSE_WITH_ROTATION_FORMAT
+        s = LA.summarize_numeric_actions(a, fmt.get_sum_decimal(), fmt.include_rotation)
+        mv, grip = fmt.parse_language_to_deltas(s)
+        tot = a.sum(0)
+        assert np.all(np.abs(mv[:3] * 100 - tot[:3] * 100) <= 0.5 + 1e-9), (s, tot)
+        # writer and parser agree on the signs ("tilt back" = +pitch, "tilt left" = +roll, counterclockwise = +yaw); the
+        # text carries angles to the nearest 10 degrees, so all three come back within 5
+        assert np.all(np.abs(np.degrees(mv[3:6]) - np.degrees(tot[3:6])) <= 5.0 + 1e-9), (s, tot)
+        assert grip == (1.0 if a[-1, 6] >= 0.5 else 0.0)
+        cm = np.round(np.abs(tot[:3] * 100))
+        deg = np.array([LA._nearest(abs(v) * 180 / np.pi, 10) for v in tot[3:6]])
+        idle = bool(np.sqrt((cm ** 2).sum()) < 1.0 and np.sqrt((deg ** 2).sum()) < 10.0)
+        assert LA.is_idle_language_action(s, "0f", True) == idle, (s, cm, deg)
+
+    frames()
+    text()
