@@ -465,3 +465,52 @@ def test_language_action_round_trip_properties():
 
     frames()
     text()
+
+
+def test_tokenizer_mask_invariants_property():
+    """Invariants of `CoTTokenizer.tokenize` over random prompts, reasoning strings and lengths: the valid tokens are a left
+    aligned run padded with pad_id; the lang-action span is a contiguous run inside it that starts right after the prompt
+    tokens and (when nothing is truncated) decodes back to the cleaned reasoning text and ends in EOS; number / direction masks
+    live inside the span; the loss mask only ever removes span positions."""
+    sentencepiece = pytest.importorskip("sentencepiece")
+    pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st_
+    from lap_b200 import tokenizer as tk
+
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(os.path.dirname(__file__), "golden", "tiny_sp.model"))
+    words = st_.lists(st_.sampled_from(["move", "left", "right", "up", "down", "3", "12", "cm", "and", "open", "gripper",
+                                        "the", "cup", "pick", "rotate", "clockwise", "degrees"]), min_size=1, max_size=12)
+
+    @settings(max_examples=80, deadline=None)
+    @given(words, st_.one_of(st_.none(), words), st_.integers(8, 160), st_.sampled_from([0.0, 0.5]), st_.integers(0, 2**31 - 1))
+    def check(pw, rw, max_len, drop, seed):
+        prompt, reasoning = " ".join(pw), None if rw is None else " ".join(rw)
+        t = tk.CoTTokenizer(sp, max_len=max_len, prompt_format="lap", reasoning_mask_prob=drop)
+        np.random.seed(seed)
+        tokens, attn, span, num, dirn, loss = t.tokenize(prompt, reasoning)
+        assert tokens.shape == attn.shape == loss.shape == (max_len,) and tokens.dtype == np.int32
+        n = int(attn.sum())
+        assert attn[:n].all() and not attn[n:].any() and (tokens[n:] == sp.pad_id()).all()
+        assert tokens[0] == sp.bos_id()
+        if reasoning is None:
+            assert span is None and num is None and dirn is None and loss.all()
+            return
+        idx = np.flatnonzero(span)
+        n_prompt = len(sp.encode(t._prompt_format.format_prompt(prompt), add_bos=True))
+        if idx.size:
+            assert idx[0] == n_prompt and np.array_equal(idx, np.arange(idx[0], idx[-1] + 1)) and idx[-1] < n
+        else:
+            assert n_prompt >= max_len                      # the prompt alone filled the window
+        assert not (num & ~span).any() and not (dirn & ~span).any()
+        assert loss[~span].all()                            # dropout only touches lang-action positions
+        if drop == 0.0:
+            assert loss.all()
+        full = n_prompt + len(sp.encode(reasoning, add_eos=True))
+        if full <= max_len:
+            assert n == full and tokens[n - 1] == sp.eos_id()
+            assert sp.decode(tokens[idx].tolist()) == reasoning
+            pieces = [sp.id_to_piece(int(v)) for v in tokens[idx]]
+            assert num[idx].tolist() == [tk.is_number(p) for p in pieces]
+            assert dirn[idx].tolist() == [tk.is_direction_natural(p) for p in pieces]
+
+    check()
