@@ -13,8 +13,9 @@ PARITY PIN (what the restatement has been checked against, tests/test_reference_
     converter to an index tree) agree with autograd through this file to <= 1e-3 per tensor
     (fixtures tests/golden/reference_pi05_*.npz, generator tests/golden/make_reference_golden.py);
   * LAP.compute_loss / embed_prefix / prepare_suffix / the lang-action mask builders / the language CE and loss
-    weighting / sample_actions, executed from src/lap/models/lap.py's own source with numpy standing in for
-    jax.numpy and the PyTorch port as leaf modules: masks and positions bit-exact, loss and metrics to <= 2e-4
+    weighting / sample_actions / sample_tokens (greedy), executed from src/lap/models/lap.py's own source with numpy
+    standing in for jax.numpy and the PyTorch port as leaf modules: masks and positions bit-exact, loss and metrics to
+    <= 2e-4, decoded tokens identical and per-step logits to <= 2e-4 incl. the all-EOS early stop
     (fixtures tests/golden/reference_lap_*.npz, generator tests/golden/make_reference_lap_golden.py);
   * the three worked `make_attn_mask` examples of OP/models/pi0.py:26-33 and structural invariants
     (tests/test_oracle.py).

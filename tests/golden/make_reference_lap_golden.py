@@ -4,7 +4,8 @@ make_reference_golden.py pins what LAP shares with π0.5 by running the referenc
 no PyTorch statement — the lang-action prefix-LM mask and action-rows-skip-langact mask (`lap.py:303-377`), `embed_prefix`
 with `tokenized_langact_mask` as AR mask (`lap.py:118-170`), `prepare_suffix` (`:185-207`), the language CE loss
 (`:209-289`), the action loss (`:291-301`), the loss weighting / normalisation of `compute_loss` (`:380-602`) and
-`sample_actions` (`:605-675`, incl. its quirk of letting action rows see lang-action keys) — is JAX code.  Its *leaf*
+`sample_actions` (`:605-675`, incl. its quirk of letting action rows see lang-action keys) and the greedy autoregressive
+`sample_tokens` (`:678-766`, with `pi0_fast.left_to_right_align / put_along_last_axis`) — is JAX code.  Its *leaf*
 modules (SigLIP, the two-expert Gemma stack, the nnx.Linear projections) are exactly the ones the PyTorch port restates, and
 everything between the leaves is plain `jax.numpy` array algebra.  So this script executes the reference's method bodies
 as they stand in /root/reference (compiled from the source files' AST, annotations and decorators dropped because they
@@ -12,7 +13,8 @@ need jaxtyping/flax at definition time), with
 
   * `jnp`   -> numpy (fp32 in, fp32 out; `.at[idx].set(v)` provided by an ndarray subclass),
   * `jax.random.normal/beta` -> the explicit `noise` / `time` the test also feeds the oracle (JAX's threefry stream cannot be
-    reproduced), `jax.random.split` -> dummy keys, `jax.lax.while_loop` -> a Python while loop,
+    reproduced), `jax.random.split` -> dummy keys, `jax.lax.while_loop` -> a Python while loop, `jax.lax.cond` -> if/else,
+    `jax.vmap` -> a per-example loop,
   * `jax.nn.one_hot / log_softmax`, `nnx.swish`, `einops` -> their textbook definitions (third-party: jax 0.5.3 / flax 0.10.2,
     not under /root/reference),
   * `preprocess_observation` -> identity (lap_libero: `enable_image_augmentation=False`, images already 224x224),
@@ -116,14 +118,14 @@ class _Jnp:
 def make_jax_shim(noise, time):
     jax = types.SimpleNamespace()
     jax.random = types.SimpleNamespace(
-        split=lambda rng, n: [None] * n,
+        split=lambda rng, n=2: [None] * n,
         normal=lambda rng, shape: np.asarray(noise, dtype=np.float32).reshape(shape),
         # prepare_suffix computes beta * 0.999 + 0.001; hand back the beta draw that yields exactly `time`
         beta=lambda rng, a, b, shape: _BetaDraw(np.asarray(time, dtype=np.float32).reshape(shape)),
     )
 
-    def one_hot(x, n):
-        return (np.asarray(x)[..., None] == np.arange(n)).astype(np.float32)
+    def one_hot(x, n, dtype=np.float32):
+        return (np.asarray(x)[..., None] == np.arange(n)).astype(dtype)
 
     def log_softmax(x, axis=-1):
         x = np.asarray(x, dtype=np.float32)
@@ -137,7 +139,17 @@ def make_jax_shim(noise, time):
             carry = body(carry)
         return carry
 
-    jax.lax = types.SimpleNamespace(while_loop=while_loop, Precision=types.SimpleNamespace(HIGHEST=None))
+    def cond(pred, true_fn, false_fn, operand=None):
+        return true_fn(operand) if pred else false_fn(operand)
+
+    def vmap(f):  # per-example Python loop (pi0_fast.left_to_right_align is written for ONE example and vmapped)
+        def g(*args):
+            outs = [f(*[a[i] for a in args]) for i in range(len(args[0]))]
+            return tuple(np.stack([o[k] for o in outs]) for k in range(len(outs[0])))
+        return g
+
+    jax.lax = types.SimpleNamespace(while_loop=while_loop, cond=cond, Precision=types.SimpleNamespace(HIGHEST=None))
+    jax.vmap = vmap
     return jax
 
 
@@ -187,14 +199,15 @@ def exec_functions(path, fns, ns):
 
 LAP_METHODS = {"_configure_shared_training_attributes", "embed_prefix", "_embed_prefix_for_loss", "prepare_suffix",
                "_compute_language_loss", "_compute_action_loss", "_build_prefix_action_mask",
-               "_build_combined_attention_mask", "_build_combined_positions", "compute_loss", "sample_actions"}
+               "_build_combined_attention_mask", "_build_combined_positions", "compute_loss", "sample_actions", "sample_tokens"}
+PI0_FAST_PY = os.path.join(G.OP_SRC, "openpi/models/pi0_fast.py")
 
 
 class _Leaves:
     """The reference's PyTorch-port modules behind the call signatures lap.py uses."""
 
     def __init__(self, model, E):
-        self.m, self.E, self.calls = model, E, []
+        self.m, self.E, self.calls, self.decoded = model, E, [], []
 
     def img(self, image, train=False):
         x = torch.from_numpy(np.ascontiguousarray(image)).permute(0, 3, 1, 2).contiguous()
@@ -207,16 +220,28 @@ class _Leaves:
                 e = self.m.paligemma_with_expert.embed_language_tokens(torch.from_numpy(np.asarray(embedded)).long())
                 return (e * math.sqrt(e.shape[-1])).numpy()
         if method == "decode":  # gemma.py:153-154
-            return np.asarray(embedded, dtype=np.float32) @ self.E.T
+            logits = np.asarray(embedded, dtype=np.float32) @ self.E.T
+            self.decoded.append(logits)
+            return logits
         assert method is None
         t = lambda a: None if a is None else torch.from_numpy(np.ascontiguousarray(a))
-        m4 = self.m._prepare_attention_masks_4d(t(np.asarray(mask, dtype=bool)))
+        mask = np.asarray(mask, dtype=bool)
+        if embedded[1] is None:
+            # sample_tokens (lap.py:702-711, 744-750) addresses a cache PRE-ALLOCATED to prefill + max_decoding_steps slots and
+            # masks the slots that are not written yet; the port's cache grows one slot per step instead, so only the columns
+            # of the slots that exist are passed on (the dropped columns are all False in the prefill mask and select
+            # not-yet-written slots in the decode mask - asserted)
+            have = (0 if kv_cache is None else kv_cache.get_seq_length()) + np.asarray(embedded[0]).shape[1]
+            if kv_cache is None:
+                assert not mask[..., have:].any()
+            mask = mask[..., :have]
+        m4 = self.m._prepare_attention_masks_4d(t(mask))
         with torch.no_grad():
             (p, s), cache = self.m.paligemma_with_expert.forward(
                 attention_mask=m4, position_ids=t(np.asarray(positions)).long(), past_key_values=kv_cache,
                 inputs_embeds=[t(embedded[0]), t(embedded[1])], use_cache=(embedded[1] is None),
                 adarms_cond=[None, t(adarms_cond[1])])
-        self.calls.append(dict(mask=np.asarray(mask, dtype=bool), positions=np.asarray(positions)))
+        self.calls.append(dict(mask=mask, positions=np.asarray(positions)))
         n = lambda a: None if a is None else a.numpy()
         return [n(p), n(s)], cache
 
@@ -238,8 +263,13 @@ def build_reference_lap(pp, cfg, params, noise, time):
     exec_functions(PI0_PY, functions_from(PI0_PY, {"embed_suffix"}, cls="Pi0"), pi0_ns)
     pi0_ns["nnx"] = types.SimpleNamespace(swish=swish)
     met_ns = exec_functions(METRICS_PY, functions_from(METRICS_PY, {"compute_sample_specific_metrics"}), dict(jnp=jnp))
+    fast_ns = exec_functions(PI0_FAST_PY, functions_from(PI0_FAST_PY, {"left_to_right_align", "put_along_last_axis"}),
+                             dict(jnp=jnp, jax=jax))
     ns = dict(jnp=jnp, jax=jax, einops=einops, logger=logging.getLogger("openpi"), VQA_DATASET_ID_MAP={},
               _pi0=types.SimpleNamespace(make_attn_mask=pi0_ns["make_attn_mask"]),
+              # (`@jax.vmap` on left_to_right_align is dropped with the other decorators and re-applied here)
+              _pi0_fast=types.SimpleNamespace(left_to_right_align=jax.vmap(fast_ns["left_to_right_align"]),
+                                              put_along_last_axis=fast_ns["put_along_last_axis"]),
               preprocess_observation=lambda rng, obs, **kw: obs,
               compute_sample_specific_metrics=met_ns["compute_sample_specific_metrics"],
               compute_per_vqa_dataset_metrics=None, compute_token_accuracy_metrics=None)
@@ -254,6 +284,7 @@ def build_reference_lap(pp, cfg, params, noise, time):
     self = RefLAP()
     self._configure_shared_training_attributes(cfg)
     self.VOCAB_SIZE = cfg.vocab_size  # lap.py:33 hard-codes the PaliGemma vocabulary; the test model's is smaller
+    self.EOS_TOKEN = 1                # lap.py:32
     self.action_horizon, self.action_dim = cfg.action_horizon, cfg.action_dim
     leaves = _Leaves(model, params["PaliGemma/llm/embedder/input_embedding"])
     self.PaliGemma = types.SimpleNamespace(img=leaves.img, llm=leaves.llm)
@@ -303,6 +334,12 @@ def run_case(pp, case):
                                                    dtype=np.float32)
     out["sampled_actions_serve_4"] = np.asarray(
         ref.sample_actions(None, RefCoTObservation(cfg, inp, langact=False), num_steps=4, noise=inp["noise"]), dtype=np.float32)
+    # sample_tokens (lap.py:678-766), greedy: tokens + the logits every decode call produced (prefill logit first)
+    S = 6
+    leaves.decoded.clear()
+    toks = ref.sample_tokens(None, RefCoTObservation(cfg, inp, langact=False), max_decoding_steps=S, temperature=0.0)
+    out["ar_tokens"] = np.asarray(toks).astype(np.int32)
+    out["ar_logits"] = np.concatenate([np.asarray(l, dtype=np.float32) for l in leaves.decoded], axis=1)  # [B, steps+1, V]
     # stand-alone helpers on awkward inputs (ragged validity, AR blocks)
     rng = np.random.default_rng(seed + 5)
     im = rng.random((3, 37)) < 0.8

@@ -144,6 +144,16 @@ def test_oracle_matches_reference_lap_source(case):
     assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=10, bf16=False), g["sampled_actions_serve"]) < TOL_F32
     assert rel_err(O.sample_actions(p, cfg, obs_s, noise, num_steps=4, bf16=False), g["sampled_actions_serve_4"]) < TOL_F32
     assert np.array_equal(O.make_attn_mask(_t(g["kat_input_mask"]), _t(g["kat_ar_mask"])).numpy(), g["kat_attn_mask"])
+    # greedy autoregressive decode: LAP.sample_tokens (lap.py:678-766) executed from source, incl. the right-aligned prefix,
+    # the slot-RANGE decode mask and the early stop once every sample has emitted EOS (case b stops after one step)
+    S = g["ar_tokens"].shape[1]
+    toks, logits = O.sample_tokens(p, cfg, obs_s, max_decoding_steps=S, bf16=False, return_logits=True)
+    n = logits.shape[1]                                        # steps the oracle executed
+    assert n == g["ar_logits"].shape[1] - 1                    # the reference decodes once more after its last token
+    assert rel_err(logits, g["ar_logits"][:, :n]) < TOL_F32
+    assert np.array_equal(toks.numpy().astype(np.int32), g["ar_tokens"])
+    top2 = np.sort(g["ar_logits"][:, :n], axis=-1)[..., -2:]
+    assert ((top2[..., 1] - top2[..., 0]) > 20 * TOL_F32 * np.abs(g["ar_logits"][:, :n]).max()).all()  # no near-ties decide a token
 
 
 # ----------------------------------------------------------------------------------------------------------------
