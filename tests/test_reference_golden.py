@@ -233,3 +233,37 @@ def test_engine_matches_reference_lap_source(case):
     assert rel_err(a, g["sampled_actions_eval"]) < 1.5e-2
     a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, "none")), num_steps=10, noise=inp["noise"])
     assert rel_err(a, g["sampled_actions_serve"]) < 1.5e-2
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# oracle attention (incl. stop_action_to_vlm_grad) vs the reference's Attention.__call__ executed from source
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", ["a", "b"])
+@pytest.mark.parametrize("stop", [False, True])
+def test_oracle_attention_matches_reference_source_forward_and_gradients(case, stop):
+    """`gemma.Attention.__call__` (src/lap/models/backbones/gemma.py:167-290) run from its source under torch autograd
+    (tests/golden/make_reference_attention_golden.py): the oracle's forward and EVERY gradient (both experts' inputs and
+    q / kv / out weights) agree to fp32 round-off, with and without `stop_action_to_vlm_grad` — the two `stop_gradient`
+    sites of the `lap` pre-training config are pinned on the reference's own statements."""
+    from lap_b200.config import get_gemma_config
+    g = np.load(os.path.join(HERE, "golden", "reference_attention.npz"))
+    cfgs = [get_gemma_config("pin_" + case), get_gemma_config(f"pin_{case}_expert")]
+    leaf = lambda a: torch.from_numpy(a.copy()).requires_grad_(True)
+    pre = "PaliGemma/llm/layers/attn/"
+    names = ["q_einsum/w", "kv_einsum/w", "attn_vec_einsum/w", "q_einsum_1/w", "kv_einsum_1/w", "attn_vec_einsum_1/w"]
+    p = {pre + n: leaf(g[f"{case}/w/{n}"]) for n in names}
+    x0, x1 = leaf(g[f"{case}/x0"]), leaf(g[f"{case}/x1"])
+    out, _ = O.gemma_attention(p, cfgs, 0, [x0, x1], _t(g[f"{case}/pos"]), _t(g[f"{case}/mask"]), None, False,
+                               stop_action_to_vlm_grad=stop)
+    ((out[0] * _t(g[f"{case}/c0"])).sum() + (out[1] * _t(g[f"{case}/c1"])).sum()).backward()
+    key = f"{case}/stop{int(stop)}/"
+    tol = 2e-5
+    assert rel_err(out[0], g[key + "out0"]) < tol and rel_err(out[1], g[key + "out1"]) < tol
+    assert rel_err(x0.grad, g[key + "gx0"]) < tol and rel_err(x1.grad, g[key + "gx1"]) < tol
+    for n in names:
+        assert rel_err(p[pre + n].grad, g[key + "g/" + n]) < tol, n
+    # the fixture is sensitive to the flag: expert 0's K/V path loses the action rows' gradient, the action expert's does not
+    other = f"{case}/stop{int(not stop)}/"
+    assert rel_err(g[key + "g/kv_einsum/w"], g[other + "g/kv_einsum/w"]) > 1e-2
+    assert rel_err(g[key + "gx0"], g[other + "gx0"]) > 1e-2
+    assert rel_err(g[key + "g/attn_vec_einsum_1/w"], g[other + "g/attn_vec_einsum_1/w"]) < 1e-5
