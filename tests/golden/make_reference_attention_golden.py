@@ -77,9 +77,14 @@ class _Jnp:
     def split(x, n, axis=-1):
         return torch.chunk(x, n, dim=axis)
 
+    bfloat16 = torch.bfloat16
+
     @staticmethod
     def einsum(eq, *ops, preferred_element_type=None):
-        return torch.einsum(_eq(eq), *ops)
+        # XLA semantics for half-precision operands: exact products, fp32 accumulation, ONE rounding to the result type
+        # (the operands' type unless preferred_element_type says otherwise)
+        out = torch.einsum(_eq(eq), *[o.float() for o in ops])
+        return out.to(preferred_element_type or ops[0].dtype)
 
     @staticmethod
     def where(c, a, b):
@@ -114,8 +119,9 @@ def load_reference_attention(params, layer, prefix="PaliGemma/llm/layers/attn/")
             self.w = params[prefix + name + "/w"][layer]
             assert tuple(self.w.shape) == tuple(shape), (name, self.w.shape, shape)
 
-        def __call__(self, eq, x):
-            return torch.einsum(_eq(eq), x, self.w)
+        def __call__(self, eq, x):  # OP/models/lora.py:54-57: the fp32 parameter is cast to the activation dtype at use
+            dtype = x.dtype
+            return _Jnp.einsum(eq, x, self.w.astype(dtype))
 
     jax = types.SimpleNamespace(lax=types.SimpleNamespace(stop_gradient=lambda x: x.detach()),
                                 nn=types.SimpleNamespace(softmax=lambda x, axis=-1: torch.softmax(x, dim=axis)))
@@ -169,6 +175,20 @@ def main():
             res[key + "gx0"], res[key + "gx1"] = x0.grad.numpy(), x1.grad.numpy()
             for n, p_ in params.items():
                 res[key + "g/" + n.rsplit("attn/", 1)[1]] = p_.grad.numpy()
+        # bf16 activations (LAPConfig.dtype = "bfloat16"): the same source statements on bfloat16 inputs; forward values only.
+        # torch follows the same promotion rules on these statements (bf16 x python scalar -> bf16, bf16 x fp32 -> fp32)
+        for stop in (False, True):
+            cast = lambda a: jt(torch.from_numpy(a.copy()).to(torch.bfloat16))
+            params = {"PaliGemma/llm/layers/attn/" + k: jt(torch.from_numpy(v.copy())) for k, v in c["w"].items()}
+            attention_call = load_reference_attention(params, 0)
+            self = types.SimpleNamespace(configs=[types.SimpleNamespace(head_dim=k.head_dim, num_heads=k.num_heads, num_kv_heads=k.num_kv_heads,
+                                                                        width=k.width, lora_configs={}) for k in (c["g"], c["e"])],
+                                         stop_action_to_vlm_grad=stop, cache_dtype=None)
+            with torch.no_grad():
+                out, _ = attention_call(self, [cast(c["x0"]), cast(c["x1"])], jt(torch.from_numpy(c["pos"])),
+                                        jt(torch.from_numpy(c["mask"]))[:, None], None)
+            assert out[0].dtype == out[1].dtype == torch.bfloat16
+            res[f"{tag}/bf16/stop{int(stop)}/out0"], res[f"{tag}/bf16/stop{int(stop)}/out1"] = out[0].float().numpy(), out[1].float().numpy()
         for n, a in (("x0", c["x0"]), ("x1", c["x1"]), ("mask", c["mask"]), ("pos", c["pos"]), ("c0", c["c0"]), ("c1", c["c1"])):
             res[f"{tag}/{n}"] = a
         for n, a in c["w"].items():

@@ -267,3 +267,12 @@ def test_oracle_attention_matches_reference_source_forward_and_gradients(case, s
     assert rel_err(g[key + "g/kv_einsum/w"], g[other + "g/kv_einsum/w"]) > 1e-2
     assert rel_err(g[key + "gx0"], g[other + "gx0"]) > 1e-2
     assert rel_err(g[key + "g/attn_vec_einsum_1/w"], g[other + "g/attn_vec_einsum_1/w"]) < 1e-5
+    # bf16 mode: the same source statements executed on bfloat16 tensors (half-precision einsums = exact products, fp32
+    # accumulation, one rounding) — the oracle's rounding points reproduce them BIT FOR BIT
+    rb = lambda a: torch.from_numpy(a).to(torch.bfloat16).float()
+    pf = {pre + n: torch.from_numpy(g[f"{case}/w/{n}"]) for n in names}
+    outb, _ = O.gemma_attention(pf, cfgs, 0, [rb(g[f"{case}/x0"]), rb(g[f"{case}/x1"])], _t(g[f"{case}/pos"]),
+                                _t(g[f"{case}/mask"]), None, True, stop_action_to_vlm_grad=stop)
+    for i in (0, 1):
+        ref = torch.from_numpy(g[f"{case}/bf16/stop{int(stop)}/out{i}"])
+        assert torch.equal(outb[i], ref), (i, float((outb[i] != ref).float().mean()))
