@@ -17,10 +17,20 @@ PARITY PIN (what the restatement has been checked against, tests/test_reference_
     standing in for jax.numpy and the PyTorch port as leaf modules: masks and positions bit-exact, loss and metrics to
     <= 2e-4, decoded tokens identical and per-step logits to <= 2e-4 incl. the all-EOS early stop
     (fixtures tests/golden/reference_lap_*.npz, generator tests/golden/make_reference_lap_golden.py);
+  * the two-expert Gemma stack executed from the reference's own source under torch (tensors standing in for jax arrays):
+    gemma.Module.__call__ -> Block -> RMSNorm / Attention / _gated_residual (src/lap/models/backbones/gemma.py) and
+    lora.Einsum / FeedForward (OP/models/lora.py), on bfloat16 and float32 activations, joint / prefix-only / suffix-with-
+    cache passes, with and without stop_action_to_vlm_grad: the bf16 mode of this file reproduces the bfloat16 results BIT
+    FOR BIT (a single dropped rounding changes 74 % of the outputs), fp32 agrees to 3e-7, and the attention block's
+    gradients — including the two stop_gradient sites — agree with autograd through the reference statements to 2e-5
+    (fixtures tests/golden/reference_stack.npz, reference_attention.npz; generators make_reference_stack_golden.py,
+    make_reference_attention_golden.py, which also list the flax/XLA behaviours assumed: half-precision einsum = fp32
+    accumulation + one rounding, nn.Dense(dtype=bf16) = dot then bias add, gelu evaluated in fp32 and rounded once);
   * the three worked `make_attn_mask` examples of OP/models/pi0.py:26-33 and structural invariants
     (tests/test_oracle.py).
 STILL UNPINNED (the JAX/Flax program itself cannot run here: no jax/flax/optax wheels, no network; the reference's
-tests hold no numeric vector): WHERE the JAX program rounds to bfloat16 (the bf16=True mode follows SURVEY.md
+tests hold no numeric vector): where XLA's fusions keep excess precision relative to the source's dtype flow (the dtype
+flow of the Gemma stack itself is pinned above; SigLIP's flax modules and the lap.py-level casts follow SURVEY.md
 Appendix A by reading the source), and the optax/EMA train-step arithmetic (third-party optax, restated from its
 published definitions; checked against closed forms and against torch.optim.AdamW as an independent implementation).  Every function cites the file:line it follows
 (`OP/` = third_party/openpi/src/openpi/).

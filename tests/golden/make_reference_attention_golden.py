@@ -27,6 +27,8 @@ class JT(torch.Tensor):
     """torch.Tensor with the two jax.Array members the executed code uses."""
 
     def astype(self, dtype):
+        if isinstance(dtype, str):  # jax accepts dtype names ("bfloat16")
+            dtype = getattr(torch, dtype)
         return self.to(dtype)
 
     @property

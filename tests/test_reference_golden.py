@@ -276,3 +276,44 @@ def test_oracle_attention_matches_reference_source_forward_and_gradients(case, s
     for i in (0, 1):
         ref = torch.from_numpy(g[f"{case}/bf16/stop{int(stop)}/out{i}"])
         assert torch.equal(outb[i], ref), (i, float((outb[i] != ref).float().mean()))
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# oracle two-expert Gemma stack vs gemma.Module / Block / RMSNorm / Attention / lora.FeedForward executed from source
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(RC.CASES))
+def test_oracle_gemma_stack_is_bit_identical_to_reference_source_in_bf16(case):
+    """tests/golden/make_reference_stack_golden.py runs `Module.__call__` -> `Block` -> `RMSNorm` / `Attention` /
+    `lora.FeedForward` / `_gated_residual` from the reference's source files on bfloat16 and float32 activations (3- and
+    2-layer stacks, adaRMS expert, masked keys, prefix-LM blocks).  The oracle's bf16 mode — i.e. WHERE it rounds to
+    bfloat16 — must give the same bits for the joint pass (with and without stop_action_to_vlm_grad), the prefix-only pass
+    and the suffix pass against the prefix KV cache; the fp32 mode agrees to round-off."""
+    g = np.load(os.path.join(HERE, "golden", "reference_stack.npz"))
+    cfg = RC.lap_config(case)
+    p = {k: torch.from_numpy(np.ascontiguousarray(v, dtype=np.float32))
+         for k, v in RC.seeded_reference_params(cfg, RC.CASES[case][5]).items() if k.startswith("PaliGemma/llm/")}
+    cfgs = [cfg.gemma, cfg.expert]
+    P0 = int(g[f"{case}/P0"])
+    x0, x1, cond, mask, pos = (_t(g[f"{case}/{k}"]) for k in ("x0", "x1", "cond", "mask", "pos"))
+
+    def check(out, ref, exact):
+        ref = _t(ref)
+        if exact:
+            assert torch.equal(out, ref), float((out != ref).float().mean())
+        else:
+            assert rel_err(out, ref) < 2e-6
+
+    for dname, bf16 in (("bfloat16", True), ("float32", False)):
+        for stop in (False, True):
+            (o0, o1), _ = O.gemma_forward(p, cfgs, [x0, x1], pos, mask, [None, cond], bf16, stop_action_to_vlm_grad=stop)
+            key = f"{case}/{dname}/stop{int(stop)}/"
+            check(o0, g[key + "joint0"], bf16)
+            check(o1, g[key + "joint1"], bf16)
+        key = f"{case}/{dname}/stop0/"
+        (q0, _), cache = O.gemma_forward(p, cfgs, [x0, None], pos[:, :P0], mask[:, :P0, :P0], [None, None], bf16)
+        check(q0, g[key + "prefix0"], bf16)
+        (_, s1), _ = O.gemma_forward(p, cfgs, [None, x1], pos[:, P0:], mask[:, P0:, :], [None, cond], bf16, kv_cache=cache)
+        check(s1, g[key + "suffix1"], bf16)
+    # the bf16 results are not simply the rounded fp32 results: the test can tell a missing rounding point
+    assert (np.abs(g[f"{case}/bfloat16/stop0/joint0"] - g[f"{case}/float32/stop0/joint0"]).max()
+            > 1e-3 * np.abs(g[f"{case}/float32/stop0/joint0"]).max())
