@@ -514,3 +514,25 @@ def test_tokenizer_mask_invariants_property():
             assert dirn[idx].tolist() == [tk.is_direction_natural(p) for p in pieces]
 
     check()
+
+
+def test_ema_schedule_matches_reference_source():
+    """`TrainConfig.get_ema_init` / `get_ema_decay_for_step` against the reference's TrainConfig methods and EmaSchedule classes
+    executed from src/lap/training/config.py (tests/golden/make_reference_schedule_golden.py): every schedule kind x decay x
+    start step x training length, at steps around every boundary."""
+    import dataclasses, json
+    from lap_b200.config import EmaScheduleChoice
+    z = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_schedules.json")))
+    base = get_config("lap_libero")
+    n_enabled = 0
+    for r in z["rows"]:
+        c = dataclasses.replace(base, ema_decay=r["decay"], num_train_steps=r["num_train_steps"],
+                                ema_schedule_choice=EmaScheduleChoice(kind=r["kind"], start_step=r["start"]))
+        d0, e0 = c.get_ema_init()
+        assert (None if d0 is None else float(d0)) == r["init"][0] and bool(e0) == r["init"][1], (r["kind"], r["decay"], r["start"])
+        for step, (dr, er) in zip(z["steps"], r["steps"]):
+            d, e = c.get_ema_decay_for_step(step)
+            assert bool(e) == er, (r, step)
+            assert abs(float(d) - dr) <= 2e-7 * max(1.0, abs(dr)), (r["kind"], r["decay"], r["start"], step, d, dr)  # reference: fp32
+            n_enabled += er
+    assert n_enabled > 200
