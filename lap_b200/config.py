@@ -123,10 +123,22 @@ class LAPConfig:
     prediction_loss_weight: float = 1.0
     vqa_loss_weight: float = 0.1
     stop_action_to_vlm_grad: bool = False
+    # host-side (tokenizer / prompt) fields of the reference config, consumed by `make_tokenizer`
+    prompt_format: str = "lap"
+    prediction_format: str = "default"
+    state_dropout: float = 0.0
+    reasoning_mask_prob: float = 0.0
     # --- not in the reference: knobs the reference hard-codes, exposed so small test models exist ---
     siglip_variant: str = "So400m/14"  # lap.py:79
     vocab_size: int = PALIGEMMA_VOCAB_SIZE  # lap.py:27
     image_size: int = 224  # OP/models/model.py IMAGE_RESOLUTION
+
+    def make_tokenizer(self, sp_processor):
+        """The tokenizer this config implies (lap_config.py model_transforms: PaligemmaTokenizer(max_token_len, prompt_format,
+        prediction_format, reasoning_mask_prob)), around an injected SentencePiece processor."""
+        from .tokenizer import CoTTokenizer
+        return CoTTokenizer(sp_processor, max_len=self.max_token_len, prompt_format=self.prompt_format,
+                            prediction_format=self.prediction_format, reasoning_mask_prob=self.reasoning_mask_prob)
 
     @property
     def image_keys(self) -> tuple[str, ...]:

@@ -536,3 +536,55 @@ def test_ema_schedule_matches_reference_source():
             assert abs(float(d) - dr) <= 2e-7 * max(1.0, abs(dr)), (r["kind"], r["decay"], r["start"], step, d, dr)  # reference: fp32
             n_enabled += er
     assert n_enabled > 200
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reads the reference sources (build container only)")
+def test_model_dimensions_match_reference_source():
+    """The LAP-3B dimensions this engine is built for are the reference's: `gemma.get_config` (backbones/gemma.py:56-110) and
+    `siglip.decode_variant` (OP/models/siglip.py:298-370) executed from source.  (Skipped where /root/reference is absent.)"""
+    import ast, dataclasses, types
+    from lap_b200.config import get_gemma_config, get_siglip_config
+    src = "/root/reference/src/lap/models/backbones/gemma.py"
+    tree = ast.parse(open(src).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "get_config")
+    fn.returns = None
+    fn.args.args[0].annotation = None
+    ns = {"Config": lambda **kw: types.SimpleNamespace(**kw), "lora": types.SimpleNamespace(LoRAConfig=lambda **kw: kw)}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src, "exec"), ns)
+    for variant in ("dummy", "gemma_300m", "gemma_2b"):
+        r, m = ns["get_config"](variant), get_gemma_config(variant)
+        for f in ("width", "depth", "mlp_dim", "num_heads", "num_kv_heads", "head_dim"):
+            assert getattr(r, f) == getattr(m, f), (variant, f)
+    src = "/root/reference/third_party/openpi/src/openpi/models/siglip.py"
+    tree = ast.parse(open(src).read())
+    fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "decode_variant")
+    ns = {}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src, "exec"), ns)
+    r, m = ns["decode_variant"]("So400m/14"), get_siglip_config("So400m/14", 2048)
+    assert (r["width"], r["depth"], r["mlp_dim"], r["num_heads"], r["patch_size"]) == (m.width, m.depth, m.mlp_dim, m.num_heads, (m.patch_size, m.patch_size))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reads the reference sources (build container only)")
+def test_lap_config_defaults_match_reference_source():
+    """Every field `LAPConfig` shares with the reference dataclass (src/lap/models/lap_config.py:22-75) has the same default;
+    the reference fields this engine does not carry are exactly the ones for out-of-scope heads."""
+    import ast, dataclasses
+    tree = ast.parse(open("/root/reference/src/lap/models/lap_config.py").read())
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LAPConfig")
+    mine = {f.name: f.default for f in dataclasses.fields(LAPConfig)}
+    absent = []
+    for n in cls.body:
+        if isinstance(n, ast.AnnAssign) and n.value is not None:
+            try:
+                ref_default = ast.literal_eval(n.value)
+            except ValueError:
+                continue
+            if n.target.id in mine:
+                assert mine[n.target.id] == ref_default, n.target.id
+            else:
+                absent.append(n.target.id)
+    assert sorted(absent) == ["use_fast", "vqa_loss_weights"], absent
+    sentencepiece = pytest.importorskip("sentencepiece")
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(os.path.dirname(__file__), "golden", "tiny_sp.model"))
+    t = LAPConfig(max_token_len=33, reasoning_mask_prob=0.25).make_tokenizer(sp)
+    assert t._max_len == 33 and t.reasoning_mask_prob == 0.25 and t._prompt_format.name == "lap"
