@@ -231,14 +231,15 @@ class TrainConfig:
 
     name: str = "lap"
     model: LAPConfig = dataclasses.field(default_factory=LAPConfig)
-    lr_schedule: CosineDecaySchedule = dataclasses.field(
-        default_factory=lambda: CosineDecaySchedule(warmup_steps=1000, peak_lr=5e-5, decay_steps=40_000, decay_lr=5e-5)
+    lr_schedule: CosineDecaySchedule = dataclasses.field(  # build_cosine_lr() defaults, config.py:41-55
+        default_factory=lambda: CosineDecaySchedule(warmup_steps=5000, peak_lr=1e-4, decay_steps=40_000, decay_lr=1e-4)
     )
     optimizer: AdamW = dataclasses.field(default_factory=lambda: AdamW(weight_decay=0.0001))
     num_train_steps: int = 40_000
-    batch_size: int = 256
+    batch_size: int = 32  # OP/training/config.py:497
     log_interval: int = 50
     save_interval: int = 1000
+    keep_period: int | None = 5000
     seed: int = 0
     fsdp_devices: int = 1
     ema_decay: float | None = 0.999
@@ -295,15 +296,14 @@ _CONFIGS = {
         name="lap",
         model=LAPConfig(action_dim=7, action_horizon=16, max_token_len=180, enable_action_training=True,
                         stop_action_to_vlm_grad=True),
-        lr_schedule=_LR, num_train_steps=40_001, batch_size=256, save_interval=2000,
-        ema_schedule_choice=EmaScheduleChoice(kind="cosine_delayed", start_step=1000),
+        batch_size=2048,  # everything else is the TrainConfig default (cosine LR 1e-4 / 5000 warm-up, cosine-delayed EMA from 5000)
     ),
     # src/lap/training/config.py:751-785
     "lap_libero": TrainConfig(
         name="lap_libero",
         model=LAPConfig(action_dim=7, action_horizon=10, max_token_len=180, enable_action_training=True,
                         stop_action_to_vlm_grad=False, language_loss_weight=0.4, enable_image_augmentation=False),
-        lr_schedule=_LR, num_train_steps=40_001, batch_size=256, save_interval=2000,
+        lr_schedule=_LR, num_train_steps=40_001, batch_size=256, save_interval=2000, keep_period=2000,
         ema_schedule_choice=EmaScheduleChoice(kind="constant"),
     ),
     # test-only: tiny models that exercise the same code paths

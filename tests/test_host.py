@@ -9,7 +9,7 @@ import torch
 
 from lap_b200 import _lib
 from lap_b200 import params as P
-from lap_b200.config import LAPConfig, get_config
+from lap_b200.config import LAPConfig, TrainConfig, get_config
 from lap_b200.data import synthetic_batch
 from lap_b200.observation import CoTObservation, Observation
 
@@ -588,3 +588,66 @@ def test_lap_config_defaults_match_reference_source():
     sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(os.path.dirname(__file__), "golden", "tiny_sp.model"))
     t = LAPConfig(max_token_len=33, reasoning_mask_prob=0.25).make_tokenizer(sp)
     assert t._max_len == 33 and t.reasoning_mask_prob == 0.25 and t._prompt_format.name == "lap"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reads the reference sources (build container only)")
+def test_train_configs_match_reference_source():
+    """`get_config("lap")` / `get_config("lap_libero")` and the TrainConfig defaults against src/lap/training/config.py, read
+    through its AST: every keyword the reference passes (and every default it leaves) that this engine's TrainConfig carries."""
+    import ast, dataclasses
+    tree = ast.parse(open("/root/reference/src/lap/training/config.py").read())
+    lit = ast.literal_eval
+
+    def kwargs(call):
+        return {k.arg: k.value for k in call.keywords}
+
+    # class defaults
+    tc = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "TrainConfig")
+    ref_default = {}
+    for n in tc.body:
+        if isinstance(n, ast.AnnAssign) and n.value is not None:
+            try:
+                ref_default[n.target.id] = lit(n.value)
+            except ValueError:
+                pass
+    ema_def = next(n for n in tc.body if isinstance(n, ast.AnnAssign) and n.target.id == "ema_schedule_choice")
+    ema_call = next(c for c in ast.walk(ema_def.value) if isinstance(c, ast.Call) and getattr(c.func, "id", "") == "EmaScheduleChoice")
+    ref_default["ema_schedule_choice"] = {k: lit(v) for k, v in kwargs(ema_call).items()}
+    lr_fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == "build_cosine_lr")
+    ref_default["lr_schedule"] = {a.arg: lit(d) for a, d in zip(lr_fn.args.kwonlyargs, lr_fn.args.kw_defaults)}
+    ref_default["batch_size"] = 32   # inherited: OP/training/config.py:497
+    mine_default = TrainConfig()
+    for f in ("num_train_steps", "save_interval", "log_interval", "keep_period", "seed", "ema_decay", "batch_size"):
+        assert getattr(mine_default, f) == ref_default[f], f
+    assert dataclasses.asdict(mine_default.lr_schedule) == ref_default["lr_schedule"]
+    assert dataclasses.asdict(mine_default.ema_schedule_choice) == ref_default["ema_schedule_choice"]
+    assert mine_default.optimizer.weight_decay == 1e-4
+
+    # the two named configurations of the hot path
+    cfgs = next(n for n in tree.body if isinstance(n, ast.Assign) and getattr(n.targets[0], "id", None) == "_CONFIGS").value
+    seen = set()
+    for call in cfgs.elts:
+        if not isinstance(call, ast.Call):
+            continue
+        kw = kwargs(call)
+        name = lit(kw["name"])
+        if name not in ("lap", "lap_libero"):
+            continue
+        seen.add(name)
+        mine = get_config(name)
+        model_kw = {k: lit(v) for k, v in kwargs(kw["model"]).items()}
+        for k, v in model_kw.items():
+            assert getattr(mine.model, k) == v, (name, k)
+        for k, v in dataclasses.asdict(LAPConfig()).items():   # fields the reference leaves at their defaults
+            if k not in model_kw:
+                assert getattr(mine.model, k) == v, (name, k)
+        for f in ("num_train_steps", "save_interval", "keep_period", "batch_size"):
+            want = lit(kw[f]) if f in kw else ref_default[f]
+            assert getattr(mine, f) == want, (name, f, getattr(mine, f), want)
+        want_lr = {k: lit(v) for k, v in kwargs(kw["lr_schedule"]).items()} if "lr_schedule" in kw else ref_default["lr_schedule"]
+        assert dataclasses.asdict(mine.lr_schedule) == want_lr, name
+        want_ema = dict(ref_default["ema_schedule_choice"])
+        if "ema_schedule_choice" in kw:
+            want_ema = {**{"kind": "delayed", "start_step": 10000}, **{k: lit(v) for k, v in kwargs(kw["ema_schedule_choice"]).items()}}
+        assert dataclasses.asdict(mine.ema_schedule_choice) == want_ema, (name, want_ema)
+    assert seen == {"lap", "lap_libero"}
