@@ -4,7 +4,7 @@ What mirrors the reference (src/lap/training/checkpoints.py):
   * one directory per step; written to `<step>.tmp-<pid>` and renamed when complete (an interrupted save never looks valid);
   * the `_split_params` / `_merge_params` convention (:529-547): item `params` holds the weights to SERVE — the EMA weights when
     EMA is enabled, the raw weights otherwise — and item `train_state` holds the rest (step, raw params if EMA is on, Adam mu/nu);
-  * `latest_step`, `keep` newest checkpoints.
+  * `latest_step`; retention = `keep` newest checkpoints plus every `keep_period`-th step (the reference: max_to_keep=1).
 Every tensor is stored under its reference parameter-tree path ('/'-joined, no `value` leaf), in the reference's shapes and
 fp32, so `params.safetensors` of a checkpoint IS a reference-layout `params` tree (`LAP.load_params(load_tree(...))`).
 What does not: the container is safetensors + a JSON manifest, not Orbax/OCDBT (orbax is not installable offline); reading a
@@ -50,8 +50,11 @@ def _model_signature(cfg) -> dict:
     return {"n_tensors": len(shapes), "n_params": int(sum(int(torch.Size(s).numel()) for s in shapes.values()))}
 
 
-def save_train_state(directory, state, step: int | None = None, *, keep: int | None = None) -> Path:
-    """Write checkpoint `<directory>/<step>/`.  Call on rank 0 only (the state is replicated across data-parallel ranks)."""
+def save_train_state(directory, state, step: int | None = None, *, keep: int | None = None,
+                     keep_period: int | None = None) -> Path:
+    """Write checkpoint `<directory>/<step>/`.  Call on rank 0 only (the state is replicated across data-parallel ranks).
+    Retention as in the reference's CheckpointManagerOptions(max_to_keep, keep_period) (checkpoints.py:58-63, where
+    max_to_keep = 1): only the `keep` newest checkpoints stay, except that steps divisible by `keep_period` are never removed."""
     directory = Path(directory)
     step = int(state.step if step is None else step)
     final = directory / str(step)
@@ -74,6 +77,8 @@ def save_train_state(directory, state, step: int | None = None, *, keep: int | N
     os.replace(tmp, final)
     if keep is not None:
         for s in _steps(directory)[:-keep]:
+            if keep_period and s % keep_period == 0:
+                continue
             shutil.rmtree(directory / str(s))
     return final
 

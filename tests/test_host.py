@@ -354,6 +354,7 @@ def test_checkpoint_round_trip_in_reference_layout(tmp_path):
     tree; `keep`, `latest_step`, unfinished saves and mismatching models behave.  Host logic only: the flat buffers live on
     the CPU behind a stand-in with the four `LAP` members the module uses."""
     pytest.importorskip("safetensors")
+    import shutil
     from lap_b200 import checkpoint as C
     from lap_b200.train import TrainState
 
@@ -404,6 +405,15 @@ def test_checkpoint_round_trip_in_reference_layout(tmp_path):
     a.step = 11
     C.save_train_state(tmp_path, a, keep=2)
     assert sorted(p.name for p in tmp_path.iterdir()) == ["11", "9"]
+    # keep_period: steps divisible by it survive pruning (CheckpointManagerOptions(max_to_keep=1, keep_period=...))
+    for st_ in (20, 25, 30):
+        a.step = st_
+        C.save_train_state(tmp_path, a, keep=1, keep_period=10)
+    assert sorted(int(p.name) for p in tmp_path.iterdir()) == [20, 30]
+    for st_ in (20, 30):
+        shutil.rmtree(tmp_path / str(st_))
+    a.step = 11
+    C.save_train_state(tmp_path, a)
     (tmp_path / "12.tmp-1").mkdir(); (tmp_path / "13").mkdir()
     assert C.latest_step(tmp_path) == 11
     with pytest.raises(FileNotFoundError):
