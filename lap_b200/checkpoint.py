@@ -69,7 +69,9 @@ def save_train_state(directory, state, step: int | None = None, *, keep: int | N
         save_tree(tmp / "train_state" / "params.safetensors", model.params_reference(model.P))
     save_tree(tmp / "train_state" / "mu.safetensors", model.params_reference(state.mu))
     save_tree(tmp / "train_state" / "nu.safetensors", model.params_reference(state.nu))
-    meta = {"format": FORMAT, "step": step, "has_ema": has_ema, "ema_decay": state.ema_decay,
+    # `step` names the directory (the loop step that triggered the save); `state_step` is TrainState.step, which the train step
+    # has already advanced - resuming continues from it, as scripts/train.py does with the restored state (:528-530)
+    meta = {"format": FORMAT, "step": step, "state_step": int(state.step), "has_ema": has_ema, "ema_decay": state.ema_decay,
             "model": _model_signature(model.cfg)}
     (tmp / "meta.json").write_text(json.dumps(meta, indent=1))
     if final.exists():
@@ -98,7 +100,7 @@ def _into_flat(model, flat: torch.Tensor, tree: dict[str, torch.Tensor]) -> None
 
 def restore_train_state(directory, state, step: int | None = None) -> int:
     """Load checkpoint `step` (default: the latest) into `state` IN PLACE (params, Adam moments, EMA, step) and refresh the
-    bf16 compute copy.  Returns the restored step.  Raises FileNotFoundError / ValueError on a missing or mismatching one."""
+    bf16 compute copy.  Returns the restored `TrainState.step`.  Raises FileNotFoundError / ValueError on a missing or mismatching one."""
     directory = Path(directory)
     step = latest_step(directory) if step is None else int(step)
     if step is None or not (directory / str(step) / "meta.json").exists():
@@ -122,7 +124,7 @@ def restore_train_state(directory, state, step: int | None = None) -> int:
     _into_flat(model, state.mu, load_tree(d / "train_state" / "mu.safetensors"))
     _into_flat(model, state.nu, load_tree(d / "train_state" / "nu.safetensors"))
     state.ema_decay = meta["ema_decay"]
-    state.step = int(meta["step"])
+    state.step = int(meta.get("state_step", meta["step"]))
     model.refresh_compute_copy()
     return state.step
 

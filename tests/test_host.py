@@ -661,3 +661,55 @@ def test_train_configs_match_reference_source():
             want_ema = {**{"kind": "delayed", "start_step": 10000}, **{k: lit(v) for k, v in kwargs(kw["ema_schedule_choice"]).items()}}
         assert dataclasses.asdict(mine.ema_schedule_choice) == want_ema, (name, want_ema)
     assert seen == {"lap", "lap_libero"}
+
+
+def test_training_loop_resume_save_and_log_cadence(tmp_path):
+    """`run_training` (the loop of scripts/train.py:main, :458-620) with a stand-in runner: checkpoints at the reference's
+    cadence with its retention, resume continues from the newest checkpoint's step with its state, logs average the infos."""
+    pytest.importorskip("safetensors")
+    import dataclasses
+    from lap_b200 import checkpoint as C
+    from lap_b200.train import TrainState
+    from lap_b200.train_loop import run_training
+
+    cfg = get_config("debug_tiny")
+    cfg = dataclasses.replace(cfg, num_train_steps=23, save_interval=5, keep_period=10, log_interval=4)
+
+    class CpuModel:
+        def __init__(self, mc):
+            self.cfg, self.layout = mc, P.FlatLayout(mc)
+            self.P = torch.zeros(self.layout.total)
+        def params_reference(self, flat=None):
+            eng = {k: v.detach().float().cpu() for k, v in P.engine_from_flat(self.layout, self.P if flat is None else flat).items()}
+            return P.engine_to_reference(self.cfg, eng)
+        def refresh_compute_copy(self):
+            pass
+
+    def fresh():
+        m = CpuModel(cfg.model)
+        n = m.layout.total
+        return TrainState(step=0, model=m, mu=torch.zeros(n), nu=torch.zeros(n), ema_params=torch.zeros(n), ema_decay=0.999)
+
+    calls = []
+    def runner(rng, state, batch, step):        # "training": params count the steps, loss = the batch value
+        assert step == state.step
+        state.model.P += 1.0
+        state.step = step + 1
+        calls.append(step)
+        return state, {"loss": torch.tensor(float(batch)), "skipped": None}
+
+    logs = []
+    s1 = run_training(cfg, iter(range(100, 112)), checkpoint_dir=tmp_path, state=fresh(), runner=runner, log_fn=lambda s, m: logs.append((s, m)))
+    assert calls == list(range(12)) and s1.step == 12                       # the data ran out after 12 batches
+    # saves at steps 5 and 10 (step % 5 == 0 and step > 0); retention keeps the newest + multiples of keep_period
+    assert sorted(int(p.name) for p in tmp_path.iterdir()) == [10]
+    assert [s for s, _ in logs] == [0, 4, 8] and logs[1][1] == {"loss": (101 + 102 + 103 + 104) / 4}
+    calls.clear()
+    s2 = run_training(cfg, iter(range(1000)), checkpoint_dir=tmp_path, state=fresh(), runner=runner)
+    # the checkpoint written DURING step 10 holds the state AFTER that step (state.step = 11), as in the reference
+    assert calls[0] == 11 and calls[-1] == 22 and s2.step == 23
+    assert float(s2.model.P[0]) == 23.0                                     # 11 restored + 12 new steps
+    assert sorted(int(p.name) for p in tmp_path.iterdir()) == [10, 20]      # 15 was pruned, 10 and 20 are keep_period steps
+    calls.clear()
+    run_training(cfg, iter(range(1000)), checkpoint_dir=tmp_path, resume=False, state=fresh(), runner=runner)
+    assert calls[0] == 0
