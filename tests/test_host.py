@@ -713,3 +713,71 @@ def test_training_loop_resume_save_and_log_cadence(tmp_path):
     calls.clear()
     run_training(cfg, iter(range(1000)), checkpoint_dir=tmp_path, resume=False, state=fresh(), runner=runner)
     assert calls[0] == 0
+
+
+def test_create_trained_policy_assembles_the_reference_chain(tmp_path):
+    """`policy_config.create_trained_policy(_ar)` (policy_config_adapter.py:86-160): served weights come from the checkpoint's
+    `params` item, norm stats from `assets/<id>/norm_stats.json` (`state_eef_pose` read as `state`), and the transform chain
+    runs in the reference's order — CoTInputs, Normalize, tokenizer, pad | detokenize, Unnormalize, CoTOutputs."""
+    pytest.importorskip("safetensors")
+    sentencepiece = pytest.importorskip("sentencepiece")
+    import json
+    from lap_b200 import checkpoint as C, policy_config as PC, transforms as T
+    from lap_b200.policy_io import CoTInputs, CoTOutputs
+
+    sp = sentencepiece.SentencePieceProcessor(model_file=os.path.join(os.path.dirname(__file__), "golden", "tiny_sp.model"))
+    import dataclasses
+    tc = get_config("debug_tiny")
+    tc = dataclasses.replace(tc, model=dataclasses.replace(tc.model, max_token_len=96))
+    # a checkpoint directory as lap_b200.checkpoint writes it, plus the assets the training run stored next to it
+    ref_tree = {k: torch.full(s, 0.5) for k, s in P.reference_shapes(tc.model).items()}
+    (tmp_path / "7").mkdir()
+    C.save_tree(tmp_path / "7" / "params.safetensors", ref_tree)
+    (tmp_path / "7" / "meta.json").write_text(json.dumps({"format": C.FORMAT, "step": 7}))
+    (tmp_path / "assets" / "libero").mkdir(parents=True)
+    stats = {"norm_stats": {"state_eef_pose": {"mean": [0.0] * 8, "std": [1.0] * 8, "q01": [-2.0] * 8, "q99": [2.0] * 8},
+                            "actions": {"mean": [0.0] * 7, "std": [1.0] * 7, "q01": [-1.0] * 7, "q99": [3.0] * 7, "num_transitions": 5}}}
+    (tmp_path / "assets" / "libero" / "norm_stats.json").write_text(json.dumps(stats))
+
+    seen = {}
+
+    class Stub:
+        def load_params(self, tree):
+            seen["loaded"] = {k: tuple(v.shape) for k, v in tree.items()}
+        def sample_actions(self, rng, obs, **kw):
+            seen["obs"] = obs
+            return torch.full((1, tc.model.action_horizon, tc.model.action_dim), 0.5)
+        def sample_tokens(self, rng, obs, **kw):
+            ids = sp.encode("move up 3 cm", add_eos=True)
+            return torch.tensor([ids + [0] * 8], dtype=torch.int32)
+
+    pol = PC.create_trained_policy(tc, tmp_path, sp_processor=sp, model=Stub(), default_prompt="stack the cups")
+    assert seen["loaded"] == {k: tuple(s) for k, s in P.reference_shapes(tc.model).items()}
+    kinds = [type(t).__name__ for t in pol._input_transform.__closure__[0].cell_contents]
+    assert kinds == ["InjectDefaultPrompt", "CoTInputs", "Normalize", "InjectDefaultPrompt", "TokenizePromptAndReasoning", "PadStatesAndActions"]
+    outs = [type(t).__name__ for t in pol._output_transform.__closure__[0].cell_contents]
+    assert outs == ["DetokenizeReasoning", "Unnormalize", "CoTOutputs"]
+    req = {"observation": {"base_0_rgb": np.full((8, 8, 3), 9, np.uint8), "state": np.full(8, 1.0)}, "prompt": "stack the cups"}
+    out = pol.infer(req)
+    obs = seen["obs"]
+    # state 1.0 under BOUNDS_Q99 with q01 = -2, q99 = 2 -> 0.5 (then discretised into the prompt and padded to action_dim)
+    np.testing.assert_allclose(np.asarray(obs.state)[0, :7], 0.5, atol=1e-6)
+    tok = pol._input_transform.__closure__[0].cell_contents[4].tokenizer
+    text = tok.decode(np.asarray(obs.tokenized_prompt)[0])
+    assert "Task: stack the cups" in text and "State: 191 191" in text      # 0.5 -> bin 191 of 256 on [-1, 1)
+    # reference quirk kept: an injected default prompt is a 0-d array, which TextParser.decode_text reads as "" (text_utils.py:8-22)
+    pol.infer({"observation": req["observation"]})
+    assert "Task: , predict" in tok.decode(np.asarray(seen["obs"].tokenized_prompt)[0])
+    # actions 0.5 -> (0.5 + 1) / 2 * (3 - -1 + 1e-6) - 1 = 2.0 on the 7 dims the statistics cover
+    np.testing.assert_allclose(out["actions"][:, :7], 2.0, atol=1e-5)
+    ar = PC.create_trained_policy_ar(tc, tmp_path, sp_processor=sp, model=Stub(), default_prompt="stack the cups",
+                                     data=PC.DataConfig(language_action_format_name="verbose_with_rotation"))
+    out = ar.infer(req)
+    assert out["reasoning"] == "move up 3 cm"
+    np.testing.assert_allclose(out["actions"], [0, 0, 0.03, 0, 0, 0])
+    # vla0 strategy: CoTOutputs carries the statistics itself, no separate Unnormalize
+    _, o2 = PC.policy_transforms(tc.model, tc.model.make_tokenizer(sp), PC.load_norm_stats(tmp_path / "assets"),
+                                 data=PC.DataConfig(language_action_format_name="vla0_chunked", transform_strategy="vla0"))
+    assert [type(t).__name__ for t in o2] == ["DetokenizeReasoning", "CoTOutputs"] and o2[1].norm_stats is not None
+    with pytest.raises(AssertionError, match="exactly one norm stats directory"):
+        PC.load_norm_stats(tmp_path)
