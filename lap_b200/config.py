@@ -107,10 +107,10 @@ class LAPConfig:
     action_expert_variant: str = "gemma_300m"
     action_dim: int = 7
     action_horizon: int = 16
-    max_token_len: int = 220
+    max_token_len: int | None = 220
     verbose_mode: bool = False
     pi05: bool = True
-    discrete_state_input: bool = True
+    discrete_state_input: bool | None = True
     aug_wrist_image: bool = True
     enable_image_augmentation: bool = True
     use_bimanual: bool = False
@@ -132,6 +132,13 @@ class LAPConfig:
     siglip_variant: str = "So400m/14"  # lap.py:79
     vocab_size: int = PALIGEMMA_VOCAB_SIZE  # lap.py:27
     image_size: int = 224  # OP/models/model.py IMAGE_RESOLUTION
+
+    def __post_init__(self):
+        """lap_config.py:76-80: `None` selects the variant-dependent defaults."""
+        if self.max_token_len is None:
+            object.__setattr__(self, "max_token_len", 200 if self.pi05 else 48)
+        if self.discrete_state_input is None:
+            object.__setattr__(self, "discrete_state_input", self.pi05)
 
     def make_tokenizer(self, sp_processor):
         """The tokenizer this config implies (lap_config.py model_transforms: PaligemmaTokenizer(max_token_len, prompt_format,
