@@ -26,12 +26,19 @@ PARITY PIN (what the restatement has been checked against, tests/test_reference_
     (fixtures tests/golden/reference_stack.npz, reference_attention.npz; generators make_reference_stack_golden.py,
     make_reference_attention_golden.py, which also list the flax/XLA behaviours assumed: half-precision einsum = fp32
     accumulation + one rounding, nn.Dense(dtype=bf16) = dot then bias add, gelu evaluated in fp32 and rounded once);
+  * end to end in bfloat16: LAP.compute_loss and sample_actions from lap.py / pi0.py source on real bfloat16 (ml_dtypes)
+    arrays with the Gemma stack from source underneath (SigLIP leaf = this file's own): losses agree to fp32 round-off and
+    the sampled actions (prefill + ten Euler steps through the KV cache) are BIT-IDENTICAL to the bf16 mode of this file
+    (fixtures reference_lap_bf16_*.npz, generator make_reference_lap_bf16_golden.py).  A finding of that exercise:
+    posemb_sincos (pi0.py:47-63) is ill-conditioned in fp32 — periods down to 4e-3 make one ulp of `pow` move the sine by
+    1e-4 — so two correct implementations of the time embedding differ by ~1e-5 in the adaRMS condition, which flips an
+    occasional bfloat16 rounding and moves sampled actions by ~7e-4 normwise: that is the floor any bf16 parity claim has;
   * the three worked `make_attn_mask` examples of OP/models/pi0.py:26-33 and structural invariants
     (tests/test_oracle.py).
 STILL UNPINNED (the JAX/Flax program itself cannot run here: no jax/flax/optax wheels, no network; the reference's
 tests hold no numeric vector): where XLA's fusions keep excess precision relative to the source's dtype flow (the dtype
-flow of the Gemma stack itself is pinned above; SigLIP's flax modules and the lap.py-level casts follow SURVEY.md
-Appendix A by reading the source), and the optax/EMA train-step arithmetic (third-party optax, restated from its
+flow of the Gemma stack and of lap.py is pinned above; SigLIP's flax modules in bf16 follow SURVEY.md Appendix A by
+reading the source, their fp32 arithmetic is pinned by the PyTorch port), and the optax/EMA train-step arithmetic (third-party optax, restated from its
 published definitions; checked against closed forms and against torch.optim.AdamW as an independent implementation).  Every function cites the file:line it follows
 (`OP/` = third_party/openpi/src/openpi/).
 

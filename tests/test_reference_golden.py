@@ -317,3 +317,32 @@ def test_oracle_gemma_stack_is_bit_identical_to_reference_source_in_bf16(case):
     # the bf16 results are not simply the rounded fp32 results: the test can tell a missing rounding point
     assert (np.abs(g[f"{case}/bfloat16/stop0/joint0"] - g[f"{case}/float32/stop0/joint0"]).max()
             > 1e-3 * np.abs(g[f"{case}/float32/stop0/joint0"]).max())
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# end to end in bfloat16: oracle vs lap.py + pi0.py + gemma.py + lora.py executed from source on bfloat16 arrays
+# ----------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("case", list(RC.LAP_CASES))
+def test_oracle_bf16_mode_matches_reference_sources_end_to_end(case):
+    """tests/golden/make_reference_lap_bf16_golden.py: `LAP.compute_loss` / `sample_actions` from lap.py's source on real
+    bfloat16 arrays, with the two-expert Gemma stack from gemma.py / lora.py source (SigLIP leaf: the oracle's own, see the
+    generator).  The oracle's bf16 mode gives the same sampled actions BIT FOR BIT (ten Euler steps through the KV cache) and
+    the same losses to fp32 round-off."""
+    g = np.load(os.path.join(HERE, "golden", f"reference_lap_bf16_{case}.npz"))
+    cfg = RC.lap_case_config(case)
+    batch, seed = RC.LAP_CASES[case]["batch"], RC.LAP_CASES[case]["seed"]
+    params = RC.seeded_reference_params(cfg, seed)
+    assert RC.params_digest(params) == bytes(g["params_sha256"]).decode()
+    p = {k: _t(v) for k, v in params.items()}
+    inp = RC.lap_case_inputs(cfg, batch, seed)
+    obs = _oracle_obs(cfg, inp, langact="real")
+    loss, m = O.compute_loss(p, cfg, obs, _t(inp["actions"]), _t(inp["noise"]), _t(inp["time"]), bf16=True)
+    assert abs(float(loss) - float(g["loss"])) < 1e-6 * abs(float(g["loss"]))
+    for k in ("lang_loss", "langact_loss", "action_loss"):
+        assert abs(float(m[k]) - float(g[k])) < 1e-6 * abs(float(g[k])), k
+    for tag, la in (("eval", "real"), ("serve", "none")):
+        a = O.sample_actions(p, cfg, _oracle_obs(cfg, inp, langact=la), _t(inp["noise"]), num_steps=10, bf16=True)
+        assert torch.equal(a, _t(g[f"sampled_actions_{tag}"])), tag
+    # bf16 is a different function from fp32 here: the fixture separates the two modes
+    g32 = np.load(os.path.join(HERE, "golden", f"reference_lap_{case}.npz"))
+    assert abs(float(g["loss"]) - float(g32["loss"])) > 1e-5 * abs(float(g32["loss"]))
