@@ -1,4 +1,5 @@
 """GPU tests of individual kernels through the C ABI, each against a plain PyTorch fp32 reference of the same op."""
+import os
 import math
 
 import numpy as np
@@ -456,3 +457,25 @@ def test_fused_attention_matches_unfused(B, Tq, T, split_tok):
     O0b, O1b = torch.zeros_like(O0), torch.zeros_like(O1)
     ops.fa_gemma_fwd(Q, Kc, Vc, bits32, None, O0b, O1b, B, R, NH, Tq, T, Tpad, W32, split, HD)
     assert torch.equal(O0b, O0) and torch.equal(O1b, O1)
+
+
+@pytest.mark.skipif(os.environ.get("LAPB_EXPERIMENTAL_TESTS") != "1",
+                    reason="experimental kernel variants: run with LAPB_EXPERIMENTAL_TESTS=1")
+def test_fa_pair_variant_is_bit_identical_to_the_product_kernel():
+    """`LAPB_FA_PAIR=1` (fa_gemma_pair.cu, cta_group::2) against the product K1 through tools/fa_variant.py in two
+    subprocesses (the switch is read once per process): identical checksums of O0, O1 and P on the training shape and on a
+    ragged one (T = 333: 128-key last chunk, odd tile count).  First verified on hardware at the end of round 1."""
+    import json, subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(pair):
+        env = dict(os.environ, LAPB_FA_PAIR=str(pair))
+        out = subprocess.run([sys.executable, os.path.join(root, "tools", "fa_variant.py")], env=env, capture_output=True,
+                             text=True, timeout=300, cwd=root)
+        assert out.returncode == 0, out.stderr[-2000:]
+        return json.loads(out.stdout.strip().splitlines()[-1])
+
+    a, b = run(0), run(1)
+    for shape in ("train", "ragged"):
+        for k in ("O0", "O1", "P", "finite"):
+            assert a[shape][k] == b[shape][k], (shape, k)
