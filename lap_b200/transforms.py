@@ -259,3 +259,16 @@ class SafeRepackTransform:
         if self.strict and missing:
             raise KeyError(f"Missing source paths: {missing}")
         return unflatten_dict(out)
+
+
+@dataclasses.dataclass(frozen=True)
+class ResizeImages:
+    """third_party/openpi/src/openpi/transforms.py:184-191, with the JAX path's `resize_with_pad` (lap_b200.image_tools) — put
+    it in front of the tokenizer transform when a client sends images that are not already height x width."""
+    height: int
+    width: int
+
+    def __call__(self, data: dict) -> dict:
+        from .image_tools import resize_with_pad
+        data["image"] = {k: resize_with_pad(np.asarray(v), self.height, self.width) for k, v in data["image"].items()}
+        return data

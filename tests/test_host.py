@@ -781,3 +781,49 @@ def test_create_trained_policy_assembles_the_reference_chain(tmp_path):
     assert [type(t).__name__ for t in o2] == ["DetokenizeReasoning", "CoTOutputs"] and o2[1].norm_stats is not None
     with pytest.raises(AssertionError, match="exactly one norm stats directory"):
         PC.load_norm_stats(tmp_path)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="executes the reference's torch implementation (build container only)")
+def test_resize_with_pad_matches_reference_torch_implementation():
+    """`image_tools.resize_with_pad(antialias=False)` against `resize_with_pad_torch` of the reference
+    (third_party/openpi/src/openpi/shared/image_tools.py:55-128) compiled from its source: float32 and uint8 images, up- and
+    down-scaling, both aspect directions, batched and single images.  With antialiasing (the JAX path's default) upscaling
+    is the same function and downscaling keeps constants, the padding and the value range."""
+    import ast
+    import torch.nn.functional as F
+    from lap_b200.image_tools import resize_with_pad
+    src = "/root/reference/third_party/openpi/src/openpi/shared/image_tools.py"
+    fn = next(n for n in ast.parse(open(src).read()).body if isinstance(n, ast.FunctionDef) and n.name == "resize_with_pad_torch")
+    fn.returns = None
+    for a in fn.args.args:
+        a.annotation = None
+    ns = {"torch": torch, "F": F}
+    exec(compile(ast.Module(body=[fn], type_ignores=[]), src, "exec"), ns)
+    ref = ns["resize_with_pad_torch"]
+    rng = np.random.default_rng(0)
+    for shape, (h, w) in [((2, 20, 32, 3), (56, 56)), ((2, 96, 60, 3), (56, 56)), ((1, 300, 400, 3), (224, 224)),
+                          ((3, 40, 40, 3), (56, 56)), ((2, 56, 56, 3), (56, 56)), ((17, 33, 3), (24, 40))]:
+        f32 = rng.uniform(-1, 1, shape).astype(np.float32)
+        u8 = rng.integers(0, 256, shape, dtype=np.uint8)
+        for img in (f32, u8):
+            want = ref(torch.from_numpy(img), h, w).numpy()
+            got = resize_with_pad(img, h, w, antialias=False)
+            assert got.shape == (*shape[:-3], h, w, 3) and got.dtype == img.dtype
+            want = want.reshape(got.shape)   # (the torch version drops a batch dimension of 1; the JAX version keeps it)
+            if img.dtype == np.uint8:
+                # torch interpolates uint8 tensors with its own integer kernel (its rounding differs from "interpolate in
+                # float, then round" of the JAX path, which this function follows): agreement to one grey level
+                assert (np.abs(got.astype(int) - want.astype(int)) <= 1).all()
+            else:
+                np.testing.assert_allclose(got, want, atol=1e-4)   # torch evaluates the source coordinates in fp32 (error grows with size)
+            aa = resize_with_pad(img, h, w, antialias=True)
+            ratio = max(shape[-2] / w, shape[-3] / h)
+            if ratio <= 1.0:            # upscaling: the antialiasing kernel has unit width
+                np.testing.assert_array_equal(aa, got)
+            assert aa.shape == got.shape and aa.dtype == img.dtype
+    const = np.full((1, 300, 400, 3), 0.25, np.float32)
+    out = resize_with_pad(const, 224, 224)
+    rows = out[0, :, 0, 0]
+    assert np.allclose(rows[28:196], 0.25, atol=1e-6) and (rows[:28] == -1).all() and (rows[196:] == -1).all()   # 168 rows + 28 + 28
+    with pytest.raises(ValueError, match="Unsupported image dtype"):
+        resize_with_pad(const.astype(np.float64), 224, 224)
