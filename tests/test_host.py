@@ -827,3 +827,29 @@ def test_resize_with_pad_matches_reference_torch_implementation():
     assert np.allclose(rows[28:196], 0.25, atol=1e-6) and (rows[:28] == -1).all() and (rows[196:] == -1).all()   # 168 rows + 28 + 28
     with pytest.raises(ValueError, match="Unsupported image dtype"):
         resize_with_pad(const.astype(np.float64), 224, 224)
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reads the reference sources (build container only)")
+def test_param_norm_filter_matches_reference_source():
+    """`param_norm` is the global norm of the KERNEL parameters: nnx.All(Param, Not(PathRegex(<pattern>)), ndim > 1)
+    (scripts/train.py:402-409) with PathRegex = re.fullmatch on the '/'-joined path (OP/shared/nnx_utils.py:47-63).  The pattern
+    is read from the reference's train.py; the oracle's predicate and the engine's contiguous kernel range [0, kernel_end)
+    select exactly those parameters of the LAP-3B tree."""
+    import ast, re
+    from oracle import lap_oracle as O
+    tree = ast.parse(open("/root/reference/scripts/train.py").read())
+    call = next(n for n in ast.walk(tree) if isinstance(n, ast.Call) and getattr(n.func, "attr", "") == "PathRegex")
+    pattern = re.compile(ast.literal_eval(call.args[0]))
+    cfg = get_config("lap_libero").model
+    shapes = P.reference_shapes(cfg)
+    want = {k for k, s in shapes.items() if len(s) > 1 and pattern.fullmatch(k) is None}
+    assert 0 < len(want) < len(shapes)
+    got_oracle = {k for k, s in shapes.items() if O.is_kernel_param(k, torch.empty(0).reshape((0,) * len(s)) if len(s) else torch.empty(()))}
+    assert got_oracle == want
+    # engine: the kernel tensors are one contiguous prefix of the flat buffer; every reference kernel parameter maps into it and
+    # nothing else does (element counts agree)
+    lay = P.FlatLayout(cfg)
+    n_kernel_ref = sum(int(np.prod(shapes[k])) for k in want)
+    n_kernel_eng = sum(int(np.prod(lay.shapes[n])) for n in lay.kernel_names)
+    assert n_kernel_eng == n_kernel_ref
+    assert lay.kernel_end >= n_kernel_eng      # (alignment gaps are zeros and do not change a norm)
