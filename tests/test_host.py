@@ -853,3 +853,24 @@ def test_param_norm_filter_matches_reference_source():
     n_kernel_eng = sum(int(np.prod(lay.shapes[n])) for n in lay.kernel_names)
     assert n_kernel_eng == n_kernel_ref
     assert lay.kernel_end >= n_kernel_eng      # (alignment gaps are zeros and do not change a norm)
+
+
+def test_product_package_never_touches_the_oracle_or_the_reference():
+    """The rule of the tier: only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use
+    `oracle/`; nothing under lap_b200/ imports it, reads /root/reference, or falls back to a CPU path."""
+    import ast, glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for path in glob.glob(os.path.join(root, "lap_b200", "*.py")):
+        src = open(path).read()
+        tree = ast.parse(src)
+        for n in ast.walk(tree):
+            if isinstance(n, ast.Import):
+                assert not any(a.name.split(".")[0] == "oracle" for a in n.names), path
+            if isinstance(n, ast.ImportFrom):
+                assert (n.module or "").split(".")[0] != "oracle", path
+        assert "/root/reference" not in src, path
+    # bench.py: the oracle only inside the two CPU-baseline functions
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    users = {f.name for f in ast.walk(tree) if isinstance(f, ast.FunctionDef)
+             for n in ast.walk(f) if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle"}
+    assert users and all("cpu" in u or "reference" in u for u in users), users
