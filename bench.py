@@ -10,11 +10,15 @@ configuration (LAP-3B: SigLIP-So400m + Gemma-2B + Gemma-300M expert; 2x224x224x3
 action chunk) on a synthetic RLDS-shaped batch of 32 samples per GPU with random-init weights.
   value : samples/s with the step's inputs already resident in HBM (CUDA events, max over ranks)
   e2e   : samples/s through the public API `TrainingStepRunner(rng, state, (obs, actions))` with HOST numpy
-          buffers: pinned H2D copy of the batch and D2H read of the loss inside the timed region
-  roofline : all tcgen05 GEMM launches of the timed region (the dominant kernel, >90 % of step FLOPs): algorithmic
-          FLOPs / CUDA-event time of those launches, against the measured sustained bf16 peak
+          buffers (uint8 camera frames, the loader's wire format): pinned H2D copy of the batch and D2H read of the
+          loss inside the timed region
+  roofline : the tcgen05 GEMM family — every GEMM launch of the step (>90 % of step FLOPs): algorithmic FLOPs /
+          summed CUDA-event time of those launches, against the measured sustained bf16 peak; per-shape table as extra
+  infer : (N = 1) the second headline metric, action-chunk latency p50/p90 of `sample_actions` at batch 1, with the
+          device-side split and the HBM roofline of the denoise-loop kernel
   cpu_baseline : the oracle (CPU restatement of the reference, torch fp32 eager) timed on this box's host cores on a
-          bounded sample (batch 1, forward+backward) — a reported baseline, not the target
+          bounded sample (batch 1; forward + backward + clip/AdamW/EMA, 3 timed steps) — a reported baseline, not the
+          target
 """
 from __future__ import annotations
 
@@ -99,6 +103,9 @@ class ClockSampler:
 # CPU reference arm / cpu_baseline: the oracle on the host cores
 # ------------------------------------------------------------------------------------------------------------
 def cpu_reference(steps: int, warmup: int, *, budget_s: float = 150.0) -> dict:
+    """The oracle (CPU restatement of the reference) doing whole train steps of the lap_libero workload at batch 1 on
+    the host cores: forward + backward (torch autograd through the fp32 restatement) + clip_by_global_norm + AdamW +
+    EMA, the last three in place when the host has the memory for params + grads + mu + nu + ema (5 x 13.4 GB)."""
     import numpy as np
     import torch
 
@@ -126,8 +133,20 @@ def cpu_reference(steps: int, warmup: int, *, budget_s: float = 150.0) -> dict:
             fan_in = s[-2] if len(s) >= 2 else s[-1]
             t.normal_(0.0, 0.01 if k.endswith("input_embedding") else 1.0 / (fan_in ** 0.5), generator=gen)
         params[k] = t
+    n_bytes = 4 * sum(v.numel() for v in params.values())
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        avail = 0
+    with_opt = avail > 4.6 * n_bytes + (16 << 30)  # grads + mu + nu + ema + activations next to the params
+    if with_opt:
+        mu = {k: torch.zeros_like(v) for k, v in params.items()}
+        nu = {k: torch.zeros_like(v) for k, v in params.items()}
+        ema = {k: v.clone() for k, v in params.items()}
     init_s = time.time() - t0
     tt = lambda x: torch.from_numpy(np.asarray(x))
+    o = tc.optimizer
 
     def one_step(i: int) -> float:
         b = synthetic_batch(cfg, 1, step=i)
@@ -140,23 +159,44 @@ def cpu_reference(steps: int, warmup: int, *, budget_s: float = 150.0) -> dict:
         t1 = time.time()
         loss, _ = O.compute_loss(ps, cfg, obs, tt(b["actions"]), tt(b["noise"]), tt(b["time"]), bf16=False)
         loss.backward()
+        if with_opt:  # scripts/train.py:363-396 (optax clip_by_global_norm -> adamw -> EMA), in place
+            with torch.no_grad():
+                gn = float(torch.sqrt(sum((v.grad.double() ** 2).sum() for v in ps.values() if v.grad is not None)))
+                scale = 1.0 if gn < o.clip_gradient_norm else o.clip_gradient_norm / gn
+                lr = tc.lr_schedule.lr(i)
+                bc1, bc2 = 1.0 - o.b1 ** (i + 1), 1.0 - o.b2 ** (i + 1)
+                decay, ema_on = tc.get_ema_decay_for_step(i)
+                for k, v in ps.items():
+                    if v.grad is None:
+                        continue
+                    g = v.grad.mul_(scale)
+                    mu[k].mul_(o.b1).add_(g, alpha=1 - o.b1)
+                    nu[k].mul_(o.b2).addcmul_(g, g, value=1 - o.b2)
+                    upd = (nu[k] / bc2).sqrt_().add_(o.eps).reciprocal_().mul_(mu[k]).div_(bc1).add_(v, alpha=o.weight_decay)
+                    v.sub_(upd, alpha=lr)
+                    if ema_on:
+                        ema[k].mul_(decay).add_(v, alpha=1 - decay)
         for v in ps.values():
             v.grad = None
         return time.time() - t1
 
     times = []
     spent = 0.0
+    warmup = max(1, min(warmup, 1))  # one untimed step (first-touch of 67 GB of state); CPU steps take ~30 s each
     for i in range(warmup + steps):
         dt = one_step(i)
         spent += dt
         if i >= warmup:
             times.append(dt)
-        if spent > budget_s and len(times) >= 1:
+        if spent > budget_s and len(times) >= min(3, steps):
             break
     ms = 1e3 * sum(times) / len(times)
+    what = "forward + backward + clip + AdamW + EMA" if with_opt else \
+        "forward + backward only (host memory too small for the optimizer state)"
     return {"value": 1e3 / ms, "ms_per_step": ms, "cores": cores, "steps_timed": len(times), "init_s": init_s,
+            "with_optimizer": with_opt,
             "sample": "batch 1 of the lap_libero workload, full LAP-3B (fp32 eager torch restatement of the JAX "
-                      "reference, forward+backward, no optimizer), %d timed steps" % len(times)}
+                      "reference: %s), %d timed steps after %d warm-up" % (what, len(times), warmup)}
 
 
 def run_reference(args) -> None:
@@ -208,8 +248,8 @@ def run_train(args) -> None:
     runner = TrainingStepRunner(tc)
     model = state.model
 
-    def host_batch(i):
-        return batch_from_dict(synthetic_batch(tc.model, B, step=i, rank=rank))
+    def host_batch(i, uint8=False):
+        return batch_from_dict(synthetic_batch(tc.model, B, step=i, rank=rank, uint8_images=uint8))
 
     def sync():
         if world > 1:
@@ -243,8 +283,7 @@ def run_train(args) -> None:
     # roofline of the dominant kernel: the same steps once more, launched eagerly so every tcgen05 GEMM launch can be
     # bracketed by CUDA events on its stream (a captured graph cannot be instrumented per kernel)
     eager = TrainingStepRunner(tc, use_cuda_graph=False)
-    eager._partials, eager._stats, eager._hyper_host, eager._hyper, eager._np = (
-        runner._partials, runner._stats, runner._hyper_host, runner._hyper, runner._np)
+    eager.share_scratch(runner)
     ops.gemm_profile_begin()
     n0 = ops.launch_count
     nprof = max(1, min(args.steps, 3))
@@ -254,7 +293,9 @@ def run_train(args) -> None:
     gemm_flops, gemm_ms, gemm_launches, by_shape = ops.gemm_profile_end()
     gemm_flops, gemm_ms, gemm_launches = gemm_flops / nprof, gemm_ms / nprof, gemm_launches / nprof
     # ---------------- end-to-end timing through the public API with host buffers (`e2e`) ----------------
-    hb = [host_batch(100 + i) for i in range(2)]
+    # the loader contract ships uint8 images (data_loader.py:324): 9.6 MB per 32-sample batch, converted to
+    # [-1, 1] inside the patchify kernel
+    hb = [host_batch(100 + i, uint8=True) for i in range(2)]
     for i in range(max(1, min(args.warmup, 2))):
         obs, actions, extra = hb[i % 2]
         _, info = runner(0, state, (obs, actions, extra), with_metrics=False)
@@ -280,30 +321,43 @@ def run_train(args) -> None:
     achieved_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     value = world * B / (ms_dev * 1e-3)
     e2e = world * B / (ms_e2e * 1e-3)
-    # the dominant kernel INSTANCE: the GEMM shape with the largest share of the step (the Gemma-2B gate/up projection
-    # with the fused GeGLU epilogue); `traffic` = dram bytes per launch of that instance from the committed ncu capture
-    dom_key, dom = max(by_shape.items(), key=lambda kv: kv[1][1])
-    dom_tf = dom[0] / (dom[1] * 1e-3) / 1e12
-    traffic = None
+    # the dominant kernel = the tcgen05 GEMM FAMILY (one kernel template, >90 % of the step's FLOPs): every launch of the
+    # profiled steps, algorithmic 2*M*N*K over the summed CUDA-event durations.  `traffic` = DRAM bytes per launch of the
+    # same family from the committed ncu capture (profiles/ncu_traffic.json), averaged over one step's launches.
+    epi_names = {0: "none", 1: "bias+gelu", 2: "residual", 3: "gated residual", 4: "GeGLU (dual B)", 5: "q-scale"}
+    traffic, traffic_alg = None, None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get("x".join(str(v) for v in dom_key[:3]))
-    epi_names = {0: "none", 1: "bias+gelu", 2: "residual", 3: "gated residual", 4: "GeGLU (dual B)", 5: "q-scale"}
+            tj = json.load(f)
+        fam = tj.get("gemm_family_per_step")
+        if fam:
+            traffic = fam["dram_bytes"] / fam["launches"]
+            traffic_alg = fam.get("algorithmic_bytes", 0) / fam["launches"] or None
+    shapes = sorted(by_shape.items(), key=lambda kv: (-kv[1][1], kv[0]))  # by time, ties by shape: deterministic
+    table = [{"M": k[0], "N": k[1], "K": k[2], "batches": k[3], "epilogue": epi_names.get(k[6], k[6]),
+              "launches_per_step": v[2] // nprof, "ms_per_step": v[1] / nprof,
+              "tflops": v[0] / (v[1] * 1e-3) / 1e12, "frac": v[0] / (v[1] * 1e-3) / 1e12 / peak_tf} for k, v in shapes[:10]]
     roofline = {
         "bound": "tensor",
-        "kernel": f"gemm_bf16_tcgen05 M={dom_key[0]} N={dom_key[1]} K={dom_key[2]} epilogue={epi_names.get(dom_key[6], dom_key[6])}"
-                  f" ({dom[2] // nprof} launches/step, {100 * dom[1] / (gemm_ms * nprof):.0f}% of GEMM time)",
-        "achieved": dom_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": dom_tf / peak_tf,
+        "kernel": "gemm_bf16_tcgen05 (all launches of the step: %d per step, %.0f%% of the step time)"
+                  % (round(gemm_launches), 100 * gemm_ms / ms_dev),
+        "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
         "peak_kind": f"{peak_kind} sustained bf16 (kernel timed inside a long step)",
-        "traffic": traffic,
-        "algorithmic_flops_per_launch": dom[0] / dom[2], "avg_launch_ms": dom[1] / dom[2],
-        "all_gemm_launches": {"achieved": achieved_tf, "frac": achieved_tf / peak_tf, "launches_per_step": gemm_launches,
-                              "gemm_ms_per_step": gemm_ms},
-        "measured": "CUDA events around every GEMM launch on the launching stream, same steps replayed eagerly (the "
-                    "timed region itself runs as three CUDA graphs per step)",
+        "traffic": traffic, "algorithmic_bytes_per_launch": traffic_alg,
+        "algorithmic_flops_per_launch": gemm_flops / max(gemm_launches, 1), "avg_launch_ms": gemm_ms / max(gemm_launches, 1),
+        "launches_per_step": gemm_launches, "gemm_ms_per_step": gemm_ms, "gemm_share_of_step": gemm_ms / ms_dev,
+        "per_shape_top10": table,
+        "measured": "CUDA events around every GEMM launch on the launching stream, the same steps replayed eagerly right "
+                    "after the timed region (which runs as CUDA graphs and cannot be instrumented per kernel)",
         "step_model_flops_frac": (world * B * 10.35e12 / (ms_dev * 1e-3)) / (world * peak_tf * 1e12),
     }
+    infer = None
+    if not args.no_infer and world == 1:  # inference is single-GPU (replicas only): reported at N = 1
+        try:
+            infer = infer_metrics(model, steps=100, warmup=10)
+        except Exception as ex:  # pragma: no cover
+            infer = {"error": repr(ex)}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -312,6 +366,7 @@ def run_train(args) -> None:
                                "per-GPU batch 32, random-init weights",
                    "per_gpu_batch": B, "global_batch": world * B, "images": "2x224x224x3", "text_tokens": 180,
                    "action_horizon": 10, "parallelism": f"dp{world}", "l2": "inputs_exceed_l2 (activations >> 126 MB)", "cuda_graph": True,
+                   "e2e_images": "uint8 (loader contract), converted on the device",
                    "flops_per_sample_train": 10.35e12},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e, "h2d_bytes_per_step": int(h2d),
@@ -319,11 +374,12 @@ def run_train(args) -> None:
         "gpu_launches": int(launches) * args.steps,
         "gpu_launches_per_step": int(launches),
         "roofline": roofline,
+        "infer": infer,
         "loss": loss_host,
     }
     if world == 1 and not args.no_cpu_baseline:
         try:
-            r = cpu_reference(1, 0, budget_s=30.0)
+            r = cpu_reference(3, 1, budget_s=60.0)
             line["cpu_baseline"] = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         except Exception as ex:  # pragma: no cover
@@ -334,25 +390,19 @@ def run_train(args) -> None:
         dist.destroy_process_group()
 
 
-def run_infer(args) -> None:
-    """Second headline metric: wall time of Policy-level `sample_actions` at batch 1 (host observation in, host actions
-    out, 10 Euler steps), p50/p90 over >= 100 timed calls after >= 10 warm-up calls.  After warm-up the call
-    is ONE CUDA graph: prefix pass (SigLIP + Gemma-2B, ~400 kernels) + the persistent denoise-loop kernel (K10)."""
-    import numpy as np
+def infer_metrics(model, *, steps: int = 100, warmup: int = 10) -> dict:
+    """Second headline metric (BASELINE.json configs[3]): wall time of `sample_actions` at batch 1 — host observation
+    in (uint8 camera frames, the serving wire format), host action chunk out, 10 Euler steps — p50/p90 over `steps`
+    timed calls after `warmup` calls.  After warm-up the call is ONE CUDA graph: prefix pass (SigLIP +
+    Gemma-2B) + the persistent denoise-loop kernel (K10).  Also the device-side split and K10's HBM roofline."""
     import torch
 
     from lap_b200 import ops
-    from lap_b200.config import get_config
     from lap_b200.data import synthetic_batch
-    from lap_b200.model import LAP
     from lap_b200.observation import Observation
 
-    steps = args.steps if args.steps_given else 100
-    warmup = args.warmup if args.warmup_given else 10
-    tc = get_config("lap_libero")
-    cfg = tc.model
-    model = LAP(cfg, seed=0)
-    b = synthetic_batch(cfg, 1, step=0, with_langact=False)
+    cfg = model.cfg
+    b = synthetic_batch(cfg, 1, step=0, with_langact=False, uint8_images=True)
     obs = Observation.from_dict(b)
     times = []
     for i in range(warmup + steps):
@@ -363,6 +413,7 @@ def run_infer(args) -> None:
         dt = time.perf_counter() - t0
         if i >= warmup:
             times.append(dt * 1e3)
+    h2d = int(model.last_h2d_bytes)
     times.sort()
     # device-side split: the whole graph, and the denoise loop alone (K10 + the V transpose), CUDA events
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -374,7 +425,7 @@ def run_infer(args) -> None:
             g.replay()
         e1.record(); torch.cuda.synchronize()
         graph_ms = e0.elapsed_time(e1) / 20
-    denoise_ms, n0 = None, ops.launch_count
+    denoise_ms = None
     bufs = model._bufs
     fused = model.use_denoise_megakernel and "dn.sync" in bufs
     if fused:
@@ -393,22 +444,32 @@ def run_infer(args) -> None:
     kv = 2 * 2 * cfg.prefix_len * e.head_dim
     dn_bytes = 10 * L * (per_layer + kv) + 2 * nm * 3 * e.width * e.width
     peaks, _ = _peaks()
-    line = {"metric": "action-chunk infer p50 ms", "value": times[len(times) // 2], "unit": "ms",
-            "p90": times[int(len(times) * 0.9)], "n_gpus": 1, "steps": steps, "warmup": warmup,
+    return {"metric": "action-chunk infer p50 ms", "value": times[len(times) // 2], "unit": "ms",
+            "p90": times[int(len(times) * 0.9)], "min": times[0], "n_gpus": 1, "steps": steps, "warmup": warmup,
             "higher_is_better": False, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "lap_libero sample_actions, batch 1, 2x224px cameras, 180-token prompt, 10 Euler steps",
+            "config": {"workload": "lap_libero sample_actions, batch 1, 2x224px uint8 cameras, 180-token prompt, 10 Euler steps",
                        "cuda_graph": g is not None, "fused_denoise_loop": bool(fused)},
             "device_ms": {"graph_replay": graph_ms, "denoise_loop": denoise_ms,
                           "prefix_pass": (graph_ms - denoise_ms) if (graph_ms and denoise_ms) else None},
-            "e2e": {"value": times[len(times) // 2], "unit": "ms", "h2d_bytes_per_step": int(model.last_h2d_bytes),
+            "e2e": {"value": times[len(times) // 2], "unit": "ms", "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": int(a_host.numel() * 4)},
+            "floor_ms": 3.4,
             "roofline": None if not denoise_ms else {
                 "bound": "hbm", "kernel": "denoise_loop_kernel (K10: 10 Euler steps x 18 expert layers, one launch)",
                 "achieved": dn_bytes / (denoise_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                 "frac": dn_bytes / (denoise_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
-                "algorithmic_bytes_per_launch": dn_bytes, "avg_launch_ms": denoise_ms,
-                "note": "latency/barrier-bound: 1083 grid barriers per launch; see profiles/r01_denoise_loop.md"}}
-    print(json.dumps(line), flush=True)
+                "algorithmic_bytes_per_launch": dn_bytes, "avg_launch_ms": denoise_ms}}
+
+
+def run_infer(args) -> None:
+    """`--mode infer`: the inference metric alone, as its own JSON line."""
+    from lap_b200.config import get_config
+    from lap_b200.model import LAP
+
+    steps = args.steps if args.steps_given else 100
+    warmup = args.warmup if args.warmup_given else 10
+    model = LAP(get_config("lap_libero").model, seed=0)
+    print(json.dumps(infer_metrics(model, steps=steps, warmup=warmup)), flush=True)
 
 
 def main():
@@ -419,6 +480,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="train", choices=["train", "infer"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-infer", action="store_true", help="skip the inference-latency block of the train line")
     args = ap.parse_args()
     args.steps_given = any(a == "--steps" or a.startswith("--steps=") for a in sys.argv[1:])
     args.warmup_given = any(a == "--warmup" or a.startswith("--warmup=") for a in sys.argv[1:])

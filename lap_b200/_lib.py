@@ -46,9 +46,26 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile every .cu under csrc/ to objects (in parallel) and link liblapb200.so."""
+    """Compile every .cu under csrc/ to objects (in parallel) and link liblapb200.so.
+
+    Safe under torchrun on a fresh checkout: an inter-process file lock serialises the ranks (the first one builds, the
+    others find an up-to-date library when they get the lock), objects and the library are written to temporary names
+    and moved into place atomically."""
+    import fcntl
+
     if not force and not needs_build():
         return LIB_PATH
+    with open(CSRC / ".build.lock", "w") as lockf:
+        fcntl.flock(lockf, fcntl.LOCK_EX)
+        try:
+            if not force and not needs_build():
+                return LIB_PATH
+            return _build_locked(force, verbose)
+        finally:
+            fcntl.flock(lockf, fcntl.LOCK_UN)
+
+
+def _build_locked(force: bool, verbose: bool) -> Path:
     srcs = [CSRC / s for s in SOURCES if (CSRC / s).exists()]
     objs = []
     procs = []
@@ -59,20 +76,26 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         objs.append(o)
         if not force and o.exists() and o.stat().st_mtime > max(s.stat().st_mtime, hdr_mtime):
             continue
-        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(s), "-o", str(o)]
+        tmp = o.with_suffix(f".o.tmp{os.getpid()}")
+        cmd = [nvcc, *NVCC_FLAGS, "-I", str(INCLUDE), "-c", str(s), "-o", str(tmp)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
-        procs.append((s, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
-    for s, p in procs:
+        procs.append((s, o, tmp, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for s, o, tmp, p in procs:
         out, _ = p.communicate()
         if p.returncode != 0:
+            tmp.unlink(missing_ok=True)
             raise RuntimeError(f"nvcc failed on {s.name}:\n{out}")
+        os.replace(tmp, o)
         if verbose and out.strip():
             print(f"--- {s.name}\n{out}")
-    cmd = [nvcc, "-shared", "-o", str(LIB_PATH), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
+    tmp_lib = LIB_PATH.with_suffix(f".so.tmp{os.getpid()}")
+    cmd = [nvcc, "-shared", "-o", str(tmp_lib), *map(str, objs), "-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
+        tmp_lib.unlink(missing_ok=True)
         raise RuntimeError(f"link failed:\n{r.stdout}")
+    os.replace(tmp_lib, LIB_PATH)
     return LIB_PATH
 
 

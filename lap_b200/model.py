@@ -86,10 +86,15 @@ class LAP:
         D = cfg.gemma.width
         self.E_split = torch.zeros(cfg.vocab_size, 2 * D, dtype=BF16, device=self.device)
         self.G: torch.Tensor | None = None  # flat grads, allocated by the trainer
+        # Workspaces.  `_bufs[name]` is the tensor most recently handed out under `name`; `_pool` owns EVERY tensor ever
+        # handed out, keyed by (name, shape, dtype).  A workspace is therefore never freed or moved while the model
+        # lives: a captured CUDA graph (training at B=32, serving at B=1, ...) keeps valid addresses even when another
+        # shape is run under the same buffer names in between.
         self._bufs: dict[str, torch.Tensor] = {}
-        self._io: dict[str, tuple[torch.Tensor, torch.Tensor]] = {}  # persistent (pinned host, device) input buffers
+        self._pool: dict[tuple, torch.Tensor] = {}
+        self._io: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}  # persistent (pinned host, device) input buffers
         self._io_event = None
-        self.R_cap: int | None = None
+        self._R_caps: dict[int, int] = {}  # batch size -> capacity of the language-loss row list (fixed shapes per B)
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
@@ -184,10 +189,12 @@ class LAP:
 
     def buf(self, name: str, shape, dtype=BF16, zero: bool = False) -> torch.Tensor:
         shape = tuple(int(s) for s in shape)
-        t = self._bufs.get(name)
-        if t is None or tuple(t.shape) != shape or t.dtype != dtype:
+        key = (name, shape, dtype)
+        t = self._pool.get(key)
+        if t is None:
             t = (torch.zeros if zero else torch.empty)(shape, dtype=dtype, device=self.device)
-            self._bufs[name] = t
+            self._pool[key] = t
+        self._bufs[name] = t
         return t
 
     # ------------------------------------------------------------------------------------------
@@ -208,11 +215,12 @@ class LAP:
             nonlocal nbytes
             t = x if isinstance(x, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(x))
             dtype = dtype or t.dtype
-            ent = self._io.get(name)
-            if ent is None or tuple(ent[1].shape) != tuple(t.shape) or ent[1].dtype != dtype:
+            key = (name, tuple(t.shape), dtype)
+            ent = self._io.get(key)
+            if ent is None:  # keyed by shape too: a captured graph's input buffers are never reallocated
                 ent = (torch.empty(tuple(t.shape), dtype=dtype).pin_memory(),
                        torch.empty(tuple(t.shape), dtype=dtype, device=dev))
-                self._io[name] = ent
+                self._io[key] = ent
             host, devbuf = ent
             if t.is_cuda:
                 devbuf.copy_(t)
@@ -275,9 +283,9 @@ class LAP:
             bb, jj = np.nonzero(lm)
             R = len(bb)
             # fixed row capacity (padding rows weigh 0) so that the captured step keeps its shapes; grows if needed
-            if self.R_cap is None or R > self.R_cap:
-                self.R_cap = max(_round_up(int(R * 1.25) + 1, 128), 128)
-            Rp = self.R_cap
+            if R > self._R_caps.get(B, 0):
+                self._R_caps[B] = max(_round_up(int(R * 1.25) + 1, 128), 128)
+            Rp = self._R_caps[B]
             rows = np.zeros(Rp, np.int64)
             tgt = np.zeros(Rp, np.int32)
             wts = np.zeros(Rp, np.float32)
@@ -649,7 +657,7 @@ class LAP:
 
     def _metrics(self, st: Staged) -> dict[str, torch.Tensor]:
         """Scalar metrics of lap.py:260,300,548-554,567 from the per-row nll / per-sample action loss (tiny arrays)."""
-        nll, aloss = self._bufs["loss.nll"], self._bufs["loss.aloss"]
+        nll, aloss = self.buf("loss.nll", (st.R,), F32), self.buf("loss.aloss", (st.B,), F32)
         per_sample = torch.zeros(st.B, dtype=F32, device=self.device)
         per_sample.index_add_(0, st.ce_sample, nll * st.ce_inv_count)
         m = {"lang_loss": per_sample.mean(), "action_loss": aloss.mean()}
@@ -669,8 +677,8 @@ class LAP:
             gen = torch.Generator().manual_seed(int(rng) if rng is not None else 0)
             if noise is None:
                 noise = torch.randn((B, cfg.action_horizon, cfg.action_dim), generator=gen)
-            if time is None:
-                time = torch.distributions.Beta(1.5, 1.0).sample((B,)) * 0.999 + 0.001
+            if time is None:  # Beta(1.5, 1) by inverse CDF, from the same seeded generator (lap.py:194)
+                time = torch.rand((B,), generator=gen).pow(1.0 / 1.5) * 0.999 + 0.001
         st = self._stage(observation, actions, noise, time, with_loss=True)
         loss, _ = self._forward_loss(st, save=False, compute_grad_seed=False)
         metrics = self._metrics(st)

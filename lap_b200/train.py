@@ -111,7 +111,10 @@ class TrainingStepRunner:
         mc = cfg.model
         if noise is None or time is None:
             # train_rng = fold_in(rng, step) (scripts/train.py:355); torch generator stands in for threefry
-            gen = torch.Generator().manual_seed((int(rng) if rng is not None else 0) * 1_000_003 + step)
+            # every data-parallel rank draws for ITS shard of the global batch: the rank is folded into the seed (the
+            # reference draws independent noise / time for each sample of the global batch)
+            rank = dist.get_rank() if self.world > 1 else 0
+            gen = torch.Generator().manual_seed(((int(rng) if rng is not None else 0) * 1_000_003 + step) * 4099 + rank)
             if noise is None:
                 noise = torch.randn((B, mc.action_horizon, mc.action_dim), generator=gen)
             if time is None:
@@ -138,7 +141,7 @@ class TrainingStepRunner:
         model = state.model
         step = state.step if step is None else int(step)
         self._set_hyper(state, step)
-        key = (st.B, st.R)
+        key = (st.B, st.R, id(state), id(model))  # a graph is bound to the buffers of ONE state / model
         g = self._graphs.get(key)
         if g is None and self.use_cuda_graph and self._warm.get(key, 0) >= 2:
             g = self._capture(state, st)
@@ -159,10 +162,12 @@ class TrainingStepRunner:
             works += self._allreduce_begin(model.G[:lo]) + self._allreduce_begin(model.G[hi:])
             self._allreduce_end(works)
             g[2].replay()
-            loss = model._bufs["loss.total"]
+            loss = model.buf("loss.total", (1,), F32)
         state.step = step + 1
-        stats = self._stats
-        return {"loss": loss[0], "grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
+        # fresh scalars (the reference returns new arrays): the persistent buffers are overwritten by the next step,
+        # and callers accumulate info dicts over log_interval steps.  Stream-ordered clones, no host sync.
+        stats = self._stats.clone()
+        return {"loss": loss[0].clone(), "grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
     def _backward_vision(self, model, st) -> None:
         """SigLIP backward; with world > 1 the persistent GEMMs leave `comm_sms` SMs to the concurrent all-reduce."""
@@ -198,17 +203,33 @@ class TrainingStepRunner:
             self._np = ops.opt_num_partials()
             self._partials = torch.zeros(self._np, dtype=F32, device=model.device)
             self._stats = torch.zeros(4, dtype=F32, device=model.device)
-            self._hyper_host = torch.zeros(8, dtype=F32).pin_memory()
+            # ring of pinned staging vectors: slot i is rewritten only after the copy that last read it has executed
+            self._hyper_host = [torch.zeros(8, dtype=F32).pin_memory() for _ in range(4)]
+            self._hyper_events = [None] * 4
+            self._hyper_slot = 0
             self._hyper = torch.zeros(8, dtype=F32, device=model.device)
         count = step + 1
         decay, ema_on = cfg.get_ema_decay_for_step(step)
-        h = self._hyper_host
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % len(self._hyper_host)
+        if self._hyper_events[slot] is not None:
+            self._hyper_events[slot].synchronize()
+        h = self._hyper_host[slot]
         h[0] = cfg.lr_schedule.lr(step)
         h[1] = 1.0 - o.b1 ** count
         h[2] = 1.0 - o.b2 ** count
         h[3] = float(decay)
         h[4] = 1.0 if (ema_on and state.ema_params is not None) else 0.0
         self._hyper.copy_(h, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record()
+        self._hyper_events[slot] = ev
+
+    def share_scratch(self, other: "TrainingStepRunner") -> None:
+        """Use another runner's optimizer scratch (norm partials, stats, hyper-parameter staging): bench.py replays the
+        timed steps through a second, eager runner to time individual launches."""
+        for n in ("_partials", "_stats", "_hyper_host", "_hyper_events", "_hyper_slot", "_hyper", "_np"):
+            setattr(self, n, getattr(other, n))
 
     def _apply_gradients_device(self, state: TrainState) -> None:
         """clip_by_global_norm -> adamw -> apply -> EMA (scripts/train.py:363-396) + norms (:370-371,402-415); all
@@ -229,7 +250,7 @@ class TrainingStepRunner:
         self._set_hyper(state, step)
         self._apply_gradients_device(state)
         state.step = step + 1
-        stats = self._stats
+        stats = self._stats.clone()
         return {"grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
 

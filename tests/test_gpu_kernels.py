@@ -453,14 +453,21 @@ def test_fused_attention_matches_unfused(B, Tq, T, split_tok):
     assert (P.float() - P_ref.float()).abs().max() < 2 ** -7  # at most one bf16 ulp of a probability
     O = torch.cat([O0[:, :split], O1[:, : R - split]], 1) if 0 < split < R else (O0 if split == R else O1)
     assert rel_err(O, O_ref) < 4e-3
+    # direct fp32 PyTorch statement of gemma.py:234-272 (rows are (token, head); the mask is per token)
+    logits = torch.einsum("bthd,bsd->bths", Q.float(), Kc[:, :T].float())
+    logits = torch.where(dense[:, :, None, :], logits, torch.tensor(-2.3819763e38, device=DEV))
+    p32 = torch.softmax(logits, -1)
+    O32 = torch.einsum("bths,bsd->bthd", p32.bfloat16().float(), Vc[:, :T].float()).reshape(B, R, HD)
+    assert rel_err(P[:, :, :T], p32.reshape(B, R, T)) < 3e-3
+    assert (P[:, :, :T].float() - p32.reshape(B, R, T)).abs().max() < 2 ** -8 + 1e-6  # half a bf16 ulp at p ~ 1
+    assert P[:, :, T:].abs().max() == 0 if Tpad > T else True
+    assert rel_err(O, O32) < 4e-3
     # without P output (inference)
     O0b, O1b = torch.zeros_like(O0), torch.zeros_like(O1)
     ops.fa_gemma_fwd(Q, Kc, Vc, bits32, None, O0b, O1b, B, R, NH, Tq, T, Tpad, W32, split, HD)
     assert torch.equal(O0b, O0) and torch.equal(O1b, O1)
 
 
-@pytest.mark.skipif(os.environ.get("LAPB_EXPERIMENTAL_TESTS") != "1",
-                    reason="experimental kernel variants: run with LAPB_EXPERIMENTAL_TESTS=1")
 def test_fa_pair_variant_is_bit_identical_to_the_product_kernel():
     """`LAPB_FA_PAIR=1` (fa_gemma_pair.cu, cta_group::2) against the product K1 through tools/fa_variant.py in two
     subprocesses (the switch is read once per process): identical checksums of O0, O1 and P on the training shape and on a

@@ -496,3 +496,60 @@ def test_checkpoint_resume_restores_bit_exactly_and_continues(tmp_path):
     ema2 = C.load_tree(tmp_path / "2" / "params.safetensors")
     got = served.params_reference()
     assert all(torch.equal(got[k], ema2[k]) for k in ema2)
+
+
+def test_cuda_graphs_survive_shape_changes():
+    """A captured graph keeps raw pointers to its workspaces: serving at B=1, then B=2, then B=1 again — and training
+    steps with a validation / sampling call in between — must replay on live buffers (workspaces are pooled by
+    (name, shape, dtype) and never reallocated), not on freed or re-purposed ones."""
+    from lap_b200.observation import Observation
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+    tc, ref, model, b = _setup("debug_small", 2)
+    b1 = synthetic_batch(tc.model, 1, step=3, with_langact=False)
+    b2 = synthetic_batch(tc.model, 2, step=4, with_langact=False)
+    o1, o2 = Observation.from_dict(b1), Observation.from_dict(b2)
+    a1 = [model.sample_actions(0, o1, num_steps=10, noise=b1["noise"]) for _ in range(3)]  # eager, capture, replay
+    assert (1, 10) in model._infer_graphs
+    a2 = [model.sample_actions(0, o2, num_steps=10, noise=b2["noise"]) for _ in range(3)]
+    obs, actions, extra = batch_from_dict(b)
+    l0, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    a1b = model.sample_actions(0, o1, num_steps=10, noise=b1["noise"])  # replays the (1, 10) graph
+    a2b = model.sample_actions(0, o2, num_steps=10, noise=b2["noise"])
+    assert torch.equal(a1b, a1[0]) and torch.equal(a1[1], a1[0]) and torch.equal(a1[2], a1[0])
+    assert torch.equal(a2b, a2[0]) and torch.equal(a2[2], a2[0])
+    # training graphs with other shapes interleaved
+    def run(interleave):
+        m = type(model)(tc.model, init=False)
+        m.load_params(ref)
+        state = init_train_state(tc, model=m)
+        runner = TrainingStepRunner(tc)
+        losses = []
+        for s in range(5):  # steps 0-1 eager, 2 captures, 3-4 replay
+            state, info = runner(0, state, batch_from_dict(synthetic_batch(tc.model, 2, step=20 + s)))
+            losses.append(float(info["loss"]))
+            if interleave:
+                m.sample_actions(0, o1, num_steps=10, noise=b1["noise"])
+                m.compute_loss(0, *batch_from_dict(synthetic_batch(tc.model, 3, step=40 + s))[:2],
+                               noise=synthetic_batch(tc.model, 3, step=40 + s)["noise"],
+                               time=synthetic_batch(tc.model, 3, step=40 + s)["time"])
+        assert len(runner._graphs) == 1
+        return losses
+    la, lb = run(False), run(True)
+    for x, y in zip(la, lb):
+        assert abs(x - y) < 1e-4 * abs(x), (la, lb)
+    assert la[0] != la[4]
+
+
+def test_info_dict_values_are_not_aliased_by_later_steps():
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+    tc, ref, model, b = _setup("debug_tiny", 4, seed=0, step=1)
+    state = init_train_state(tc, model=model)
+    runner = TrainingStepRunner(tc, use_cuda_graph=False)
+    infos = []
+    for s in range(3):
+        state, info = runner(0, state, batch_from_dict(synthetic_batch(tc.model, 4, step=s)))
+        infos.append((info, {k: float(v) for k, v in info.items()}))
+    for info, snap in infos:
+        for k, v in snap.items():
+            assert float(info[k]) == v, k
+    assert infos[0][1]["loss"] != infos[2][1]["loss"]

@@ -236,8 +236,6 @@ def test_engine_matches_reference_lap_source(case):
 
 
 @pytest.mark.gpu
-@pytest.mark.skipif(os.environ.get("LAPB_EXPERIMENTAL_TESTS") != "1",
-                    reason="written after the round's GPU budget was spent: run once with LAPB_EXPERIMENTAL_TESTS=1, then drop the guard")
 @pytest.mark.parametrize("case", list(RC.LAP_CASES))
 def test_engine_matches_reference_sources_in_bf16(case):
     """The engine against the reference sources executed in bfloat16 (reference_lap_bf16_*.npz) — the precision it is built to

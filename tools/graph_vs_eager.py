@@ -11,7 +11,7 @@ model = state.model
 obs, actions, extra = batch_from_dict(synthetic_batch(tc.model, 32, step=0))
 st = model._stage(obs, actions, extra["noise"], extra["time"], with_loss=True)
 for _ in range(4): rg.step_staged(state, st)
-re_._partials, re_._stats, re_._hyper_host, re_._hyper, re_._np = rg._partials, rg._stats, rg._hyper_host, rg._hyper, rg._np
+re_.share_scratch(rg)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 def tm(r, n=10):
     torch.cuda.synchronize(); e0.record()
