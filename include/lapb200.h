@@ -200,6 +200,7 @@ int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uin
  * sample as ONE persistent cooperative kernel (one CTA per SM, grid barriers between dependent phases, next-phase weights
  * prefetched into L2 while waiting).  All pointers are device pointers; bf16 tensors are row-major [out, in] weights /
  * [rows, features] activations; `*_ls` = element stride between consecutive layers.  Scratch buffers are caller-owned. */
+#define LAPB_DENOISE_SYNC_WORDS 32   /* uint32 words behind `sync` */
 typedef struct {
   int32_t A, ad, D1, NH, HD, F1, L, Pn, Tpad, TpadK, W32, nm, num_steps; /* TpadK = round_up(Pn, 64) = row length of VcT */
   float dt, qscale;                  /* Euler step (-1/num_steps), head_dim^-0.5 */
@@ -220,7 +221,8 @@ typedef struct {
   void *cond16, *mod;                /* scratch bf16 [num_steps*D1], [num_steps * nm*3*D1] */
   void *XE, *XE1, *qkv, *O, *act;    /* scratch bf16 [16*D1] x2, [16*(NH+2)*HD], [16*NH*HD], [16*F1] */
   float *part_o, *part_ml;           /* scratch [NH*(TpadK/64+1)*16*HD], [NH*(TpadK/64+1)*16*2] */
-  uint32_t* sync;                    /* [2]: barrier counter, error flag (set if a barrier timed out) */
+  uint32_t* sync;                    /* [LAPB_DENOISE_SYNC_WORDS], zeroed by the launcher: [0] barrier counter, [1] error flag
+                                        (set if a barrier timed out), [2..] per-head arrival counters (LAPB_DENOISE_FOLD=1) */
   unsigned long long* prof;          /* optional [32]: ns per phase slot seen by CTA 0 (16.. = sub-phase marks); (0 prologue, 1 action_in, 2/3 P1 work /
                                         barrier, 4/5 P2, 6/7 P2b, 8/9 P3, 10/11 P4, 12/13 P5, 14 final); NULL = off */
 } lapb_denoise_params_t;

@@ -268,7 +268,10 @@ __host__ __device__ inline size_t dn_smem_bytes(int D1, int HD, int OD, int F1) 
          (size_t)16 * (HD / 2) * 8 + (size_t)6 * D1 * 2 + (size_t)16 * 32 * 4 + 16;
 }
 
-__global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_denoise_params_t p) {
+// `fold` (LAPB_DENOISE_FOLD=1, experimental, off by default): the chunk combine P2b is done by the LAST CTA to finish a head's
+// partials (per-head arrival counters in p.sync[2 .. 2+NH)), which removes one grid barrier per layer; same arithmetic in the
+// same order, so the outputs are identical to the default path.
+__global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_denoise_params_t p, const int fold) {
   extern __shared__ __align__(16) unsigned char dn_smem[];
   const int A = p.A, ad = p.ad, D1 = p.D1, NH = p.NH, HD = p.HD, F1 = p.F1, L = p.L, Pn = p.Pn, W32 = p.W32;
   const int QKV = (NH + 2) * HD, OD = NH * HD, nm3 = p.nm * 3 * D1, S = p.num_steps;
@@ -297,6 +300,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   const int g = lane >> 2, t4 = lane & 3;
   const int tslot = warp >> 3, kpart = warp & 7;
   GridBarrier bar{p.sync, p.sync + 1, 0u, gridDim.x};
+  __shared__ int fold_last;
   // optional phase profile (CTA 0, thread 0): nanoseconds accumulated per phase slot
   unsigned long long prof_last = 0;
   const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
@@ -617,13 +621,43 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
             po[a * HD + d] = o;
           }
         }
+        if (fold) {
+          // last-arriver combine (the "threadfence reduction" pattern): publish this item's partials, count the arrival on
+          // the head's monotonic counter, and let whichever CTA completes the head fold its NCH chunks into O
+          __threadfence();
+          __syncthreads();
+          if (threadIdx.x == 0) {
+            const unsigned old = atomicAdd(p.sync + 2 + h, 1u);
+            fold_last = (old + 1u == (unsigned)(step * L + l + 1) * (unsigned)NCH) ? 1 : 0;
+            __threadfence();
+          }
+          __syncthreads();
+          if (fold_last) {
+            for (int i = threadIdx.x; i < A * HD; i += DN_THREADS) {
+              const int m = i / HD, d = i % HD;
+              const float* ml = p.part_ml + ((long)h * NCH * 16 + m) * 2;
+              const float* oc = p.part_o + ((long)h * NCH * 16 + m) * HD + d;
+              float mx = -3.4e38f;
+#pragma unroll 4
+              for (int c2 = 0; c2 < NCH; ++c2) mx = fmaxf(mx, __ldcg(ml + (long)c2 * 32));
+              float den = 0.f, num = 0.f;
+#pragma unroll 4
+              for (int c2 = 0; c2 < NCH; ++c2) {
+                const float w = __expf(__ldcg(ml + (long)c2 * 32) - mx);
+                den += w * __ldcg(ml + (long)c2 * 32 + 1);
+                num += w * __ldcg(oc + (long)c2 * 16 * HD);
+              }
+              Obuf[(long)m * OD + h * HD + d] = __float2bfloat16_rn(num / den);
+            }
+          }
+        }
       }
       tick(4);
-      bar.sync();
+      if (!fold) bar.sync();
       tick(5);
 
       // ---------------- P2b: combine the chunks -> O [A, NH*HD]; outputs interleaved over the grid ----------------
-      const int per_cta = (A * OD + gridDim.x - 1) / gridDim.x;
+      const int per_cta = fold ? 0 : (A * OD + gridDim.x - 1) / gridDim.x;
       for (int i0 = threadIdx.x; i0 < per_cta; i0 += DN_THREADS) {
         const int i = blockIdx.x * per_cta + i0;
         if (i >= A * OD) break;
@@ -1312,7 +1346,7 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
   int per_sm = 0;
   LAPB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, denoise_loop_kernel, DN_THREADS, smem));
   LAPB_REQUIRE(per_sm >= 1, "denoise_loop: kernel does not fit on an SM (smem %zu)", smem);
-  LAPB_CUDA_OK(cudaMemsetAsync(p.sync, 0, 2 * sizeof(uint32_t), STREAM(s)));
+  LAPB_CUDA_OK(cudaMemsetAsync(p.sync, 0, LAPB_DENOISE_SYNC_WORDS * sizeof(uint32_t), STREAM(s)));
   cudaLaunchConfig_t cfg = {};
   // Grid: one CTA per SM by default.  128 CTAs balance LAP-3B's phases exactly (128 o/down tiles, 512 gate/up pairs);
   // LAPB_DENOISE_CTAS overrides for experiments.
@@ -1330,7 +1364,12 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
   attr[0].val.cooperative = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, denoise_loop_kernel, p));
+  static int fold_env = -1;
+  if (fold_env < 0) {
+    const char* e = getenv("LAPB_DENOISE_FOLD");
+    fold_env = (e && atoi(e) != 0 && p.NH <= LAPB_DENOISE_SYNC_WORDS - 2) ? 1 : 0;
+  }
+  LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, denoise_loop_kernel, p, fold_env));
   return 0;
 }
 

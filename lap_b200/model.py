@@ -958,7 +958,7 @@ class LAP:
             mod=self.buf("dn.mod", (S, nm * 3 * D1)), XE=self.buf("dn.XE", (16, D1)), XE1=self.buf("dn.XE1", (16, D1)),
             qkv=self.buf("dn.qkv", (16, (NH + 2) * HD)), O=self.buf("dn.O", (16, NH * HD)), act=self.buf("dn.act", (16, F1)),
             part_o=self.buf("dn.part_o", (NH * nch, 16, HD), F32), part_ml=self.buf("dn.part_ml", (NH * nch, 16, 2), F32),
-            sync=self.buf("dn.sync", (2,), torch.int32, zero=True))
+            sync=self.buf("dn.sync", (32,), torch.int32, zero=True))  # LAPB_DENOISE_SYNC_WORDS
         if self.denoise_profile:
             ptrs["prof"] = self.buf("dn.prof", (32,), torch.int64, zero=True)
 
