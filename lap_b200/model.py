@@ -386,6 +386,12 @@ class LAP:
                  a_bs=(Np * W, C * Np * W), c_bs=(Np * D, rows_per_sample * D), ldc=D)
 
     def _siglip_bwd(self, st: Staged, dX0: torch.Tensor, rows_per_sample: int) -> None:
+        self._siglip_bwd_head(st, dX0, rows_per_sample)
+        self._siglip_bwd_layers(st, self.cfg.siglip.depth, 0)
+        self._siglip_bwd_tail(st)
+
+    def _siglip_bwd_head(self, st: Staged, dX0: torch.Tensor, rows_per_sample: int) -> None:
+        """head Dense + encoder_norm backward; leaves d(last block output) in `img.dx`."""
         cfg, s = self.cfg, self.cfg.siglip
         B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
         D = cfg.gemma.width
@@ -403,11 +409,22 @@ class LAP:
         dx = self.buf("img.dx", (Ms, W))
         ops.layernorm_bwd(dy, self._bufs[f"img.x.{s.depth}"], self.p("img.enc_s"), self._bufs["img.mean_e"],
                           self._bufs["img.rstd_e"], None, dx, self.g("img.enc_s"), self.g("img.enc_b"), Ms, W)
+
+    def _siglip_bwd_layers(self, st: Staged, l_hi: int, l_lo: int) -> None:
+        """Encoder blocks l_hi-1 ... l_lo; their weight gradients are final on return."""
+        cfg, s = self.cfg, self.cfg.siglip
+        B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
+        D = cfg.gemma.width
+        Ni, Ms = B * C, B * C * Np
+        pk = s.patch_size * s.patch_size * 3
+        q_div = _bf16_round(math.sqrt(hd))
+        dy = self.buf("img.dy", (Ms, W))
+        dx = self.buf("img.dx", (Ms, W))
         dh = self.buf("img.dh", (Ms, F))
         dqkv = self.buf("img.dqkv", (Ms, 3 * W))
         do = self.buf("img.do", (Ms, W))
         dP = self.buf("img.dP", (Ni, nh, Np, Np))
-        for l in reversed(range(s.depth)):
+        for l in reversed(range(l_lo, l_hi)):
             g = lambda n: self.g(n, l)
             hact, hpre, y1, x1 = (self._bufs[f"img.{n}.{l}"] for n in ("hact", "hpre", "y1", "x1"))
             # fc2
@@ -448,6 +465,16 @@ class LAP:
             self._dgrad(dqkv, self.w("img.qkv_w", l), dy, Ms, 3 * W, W)
             ops.layernorm_bwd(dy, x, self.p("img.ln0_s", l), self._bufs[f"img.mean0.{l}"], self._bufs[f"img.rstd0.{l}"],
                               dx, dx, g("img.ln0_s"), g("img.ln0_b"), Ms, W)
+
+    def _siglip_bwd_tail(self, st: Staged) -> None:
+        """Patch-embedding gradients (position table, bias, fp32 conv kernel)."""
+        cfg, s = self.cfg, self.cfg.siglip
+        B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
+        D = cfg.gemma.width
+        Ni, Ms = B * C, B * C * Np
+        pk = s.patch_size * s.patch_size * 3
+        q_div = _bf16_round(math.sqrt(hd))
+        dx = self.buf("img.dx", (Ms, W))
         # patch embedding: pos (sum over images), bias, kernel (fp32)
         ops.colsum(dx, Np * W, self.g("img.pos"), Ni, Np * W)
         ops.colsum(dx, W, self.g("img.patch_b"), Ms, W)
@@ -702,26 +729,59 @@ class LAP:
         """SigLIP tower backward (the last ~12 % of the step); needs forward_backward_llm to have run."""
         self._siglip_bwd(st, self._bufs["bwd.dX"], self.cfg.prefix_len)
 
+    def backward_vision_segment(self, st: Staged, l_hi: int, l_lo: int) -> None:
+        """Encoder blocks l_hi-1 ... l_lo of the SigLIP backward; the first segment (l_hi = depth) also does the head,
+        the last one (l_lo = 0) the patch embedding."""
+        depth = self.cfg.siglip.depth
+        if l_hi == depth:
+            d = self._bwd_dims(st)
+            self._siglip_bwd_head(st, self.buf("bwd.dX", (d["Mg"], d["D"])), self.cfg.prefix_len)
+        self._siglip_bwd_layers(st, l_hi, l_lo)
+        if l_lo == 0:
+            self._siglip_bwd_tail(st)
+
+    LLM_LAYER_GRADS = ("g.qkv_w", "g.o_w", "g.gu_w", "g.down_w", "e.qkv_w", "e.o_w", "e.gu_w", "e.down_w")
+    VIS_LAYER_GRADS = ("img.qkv_w", "img.out_w", "img.fc1_w", "img.fc2_w")
+
+    def layer_grad_ranges(self, names, l_lo: int, l_hi: int) -> list[tuple[int, int]]:
+        """Flat-buffer ranges of the layers [l_lo, l_hi) of the per-layer tensors `names` (leading axis = layer)."""
+        out = []
+        for n in names:
+            per = math.prod(self.layout.shapes[n][1:])
+            o = self.layout.offsets[n]
+            out.append((o + l_lo * per, o + l_hi * per))
+        return out
+
     def forward_backward_llm(self, st: Staged, *, zero_grads: bool = True, softmax_mode: int = 0):
         """Forward of everything + backward through the loss heads, the transformer stack, the text embedding and
-        the suffix embedding.  Leaves d(prefix tokens) in `bwd.dX` for backward_vision."""
+        the suffix embedding.  Leaves d(prefix tokens) in `bwd.dX` for backward_vision.  Equivalent to
+        `forward_and_heads` -> `backward_llm_layers(depth, 0)` -> `backward_llm_tail` (the segments the data-parallel
+        trainer interleaves with gradient all-reduces)."""
+        loss = self.forward_and_heads(st, zero_grads=zero_grads, softmax_mode=softmax_mode)
+        self.backward_llm_layers(st, self.cfg.gemma.depth, 0)
+        self.backward_llm_tail(st)
+        return loss
+
+    def _bwd_dims(self, st: Staged):
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        B, Pn, A = st.B, cfg.prefix_len, cfg.action_horizon
+        hd, NH = g.head_dim, g.num_heads
+        T = Pn + A
+        return dict(B=B, Pn=Pn, A=A, L=cfg.max_token_len, C=len(cfg.image_keys), Np=cfg.num_patches, D=g.width,
+                    D1=e.width, ad=cfg.action_dim, V=cfg.vocab_size, hd=hd, NH=NH, QKV=(NH + 2) * hd, F=g.mlp_dim,
+                    F1=e.mlp_dim, T=T, Tpad=_round_up(T, 64), Mg=B * Pn, Me=B * A, R=st.R, Rq=T * NH, nm=P.n_mod(cfg))
+
+    def forward_and_heads(self, st: Staged, *, zero_grads: bool = True, softmax_mode: int = 0):
+        """Forward of everything + backward through the two loss heads (action projection, final norms, LM head).
+        Leaves d(residual streams) of the last layer in `bwd.dX` / `bwd.dXE`."""
         assert self.G is not None, "allocate model.G (flat grads) first"
         cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
         lay = self.layout
         if zero_grads:
             self.G[lay.small_begin:].zero_()  # atomically-accumulated small tensors; GEMM wgrads overwrite theirs
         loss, (XL, XEL) = self._forward_loss(st, save=True, compute_grad_seed=True, softmax_mode=softmax_mode)
-        B, Pn, A, L = st.B, cfg.prefix_len, cfg.action_horizon, cfg.max_token_len
-        C, Np = len(cfg.image_keys), cfg.num_patches
-        D, D1, ad, V = g.width, e.width, cfg.action_dim, cfg.vocab_size
-        hd, NH = g.head_dim, g.num_heads
-        QKV = (NH + 2) * hd
-        F, F1 = g.mlp_dim, e.mlp_dim
-        T = Pn + A
-        Tpad = _round_up(T, 64)
-        Mg, Me, R = B * Pn, B * A, st.R
-        Rq = T * NH
-        nm = P.n_mod(cfg)
+        d = self._bwd_dims(st)
+        B, A, D, D1, ad, V, Mg, Me, R, nm = (d[k] for k in ("B", "A", "D", "D1", "ad", "V", "Mg", "Me", "R", "nm"))
         nm3 = nm * 3 * D1
         mod = self._bufs["suf.mod"]
         dmod = self.buf("bwd.dmod", (B, nm3), zero=True)
@@ -745,7 +805,21 @@ class LAP:
         dX.zero_()
         ops.rmsnorm_bwd(dpre, XL, self.p("g.final_norm_s"), bufs["loss.rstdF"], None, dX, self.g("g.final_norm_s"),
                         R, D, row_idx=st.ce_rows)
-        # ---- transformer layers ----
+        return loss
+
+    def backward_llm_layers(self, st: Staged, l_hi: int, l_lo: int) -> None:
+        """Backward through transformer layers l_hi-1 ... l_lo (both experts + the shared attention).  When it
+        returns, the weight gradients of those layers are final (the per-layer norm scales live in the small tail)."""
+        cfg, g, e = self.cfg, self.cfg.gemma, self.cfg.expert
+        d = self._bwd_dims(st)
+        B, Pn, A, D, D1, hd, NH, QKV, F, F1, Tpad, Mg, Me, Rq, nm = (d[k] for k in (
+            "B", "Pn", "A", "D", "D1", "hd", "NH", "QKV", "F", "F1", "Tpad", "Mg", "Me", "Rq", "nm"))
+        nm3 = nm * 3 * D1
+        bufs = self._bufs
+        mod = self.buf("suf.mod", (B, nm3))
+        dmod = self.buf("bwd.dmod", (B, nm3))
+        dX = self.buf("bwd.dX", (Mg, D))
+        dXE = self.buf("bwd.dXE", (Me, D1))
         dact = self.buf("bwd.dact", (Mg, F))
         dh = self.buf("bwd.dh", (Mg, D))
         dqkv0 = self.buf("bwd.dqkv0", (Mg, QKV))
@@ -760,7 +834,7 @@ class LAP:
         dVc = self.buf("bwd.dVc", (B, Tpad, hd))
         positions = bufs["mask.pos"]
         qscale = hd ** -0.5
-        for l in reversed(range(g.depth)):
+        for l in reversed(range(l_lo, l_hi)):
             sv = lambda n: bufs[f"g.{n}.{l}"]
             # ===== MLP, prefix expert =====
             GU, h2, X1 = sv("GU"), sv("h2"), sv("X1")
@@ -825,6 +899,17 @@ class LAP:
             self._dgrad(dqkv1, self.w("e.qkv_w", l), dhE, Me, QKV, D1)
             ops.ada_rmsnorm_bwd(dhE, XE, mod.view(-1)[(2 * l) * 3 * D1:], nm3, sv("rstdE"), dXE, dXE,
                                 dmod.view(-1)[(2 * l) * 3 * D1:], nm3, B, A, D1)
+
+    def backward_llm_tail(self, st: Staged) -> None:
+        """Text-embedding scatter, adaRMS modulation Dense, time MLP and action_in_proj gradients."""
+        cfg = self.cfg
+        d = self._bwd_dims(st)
+        B, Pn, L, C, Np, D, D1, ad, Mg, Me, nm = (d[k] for k in ("B", "Pn", "L", "C", "Np", "D", "D1", "ad", "Mg", "Me", "nm"))
+        nm3 = nm * 3 * D1
+        bufs = self._bufs
+        dmod = self.buf("bwd.dmod", (B, nm3))
+        dX = self.buf("bwd.dX", (Mg, D))
+        dXE = self.buf("bwd.dXE", (Me, D1))
         # ---- text embedding (scatter-add on top of the LM-head table gradient) ----
         ops.embed_bwd(st.tokens, dX, self.g("g.embed"), B, L, C * Np, Pn, D, math.sqrt(D))
         # ---- adaRMS modulation Dense + time MLP + action_in_proj ----
@@ -845,7 +930,6 @@ class LAP:
         x_t = bufs["suf.x_t"]
         ops.sgemm(dXE, x_t, self.g("action_in_w"), D1, ad, Me, 1, D1, 1, ad, ldc=ad)
         ops.colsum(dXE, D1, self.g("action_in_b"), Me, D1)
-        return loss
 
     # ------------------------------------------------------------------------------------------
     # inference: prefix pass -> KV cache -> Euler steps  (lap.py:605-675)

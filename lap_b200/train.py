@@ -65,11 +65,14 @@ class TrainingStepRunner:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
         self.use_cuda_graph = use_cuda_graph
-        self.comm_sms = int(os.environ.get("LAPB_COMM_SMS", "16"))  # SMs left to NCCL while it overlaps compute
+        self.comm_sms = int(os.environ.get("LAPB_COMM_SMS", "8"))  # SMs left to NCCL while it overlaps compute
+        self.bwd_segments = int(os.environ.get("LAPB_BWD_SEGMENTS", "3"))  # LLM backward groups (world > 1)
+        self.vis_segments = int(os.environ.get("LAPB_VIS_SEGMENTS", "3"))  # SigLIP backward groups (world > 1)
+        self._phase_cache: dict = {}
         self._partials = None
         self._stats = None
         self._hyper_host = None
-        self._graphs: dict = {}  # (B, R_cap) -> (fwd/bwd graph, optimizer graph, loss buffer)
+        self._graphs: dict = {}  # (B, R_cap, state, model) -> (one graph per phase ..., optimizer graph)
         self._warm: dict = {}  # eager steps run per (B, R_cap): workspaces exist before capture
 
     # -- global loss normalisers (lap.py:580-589 are means over the GLOBAL batch) ------------------------------
@@ -132,68 +135,114 @@ class TrainingStepRunner:
             info.update(model._metrics(st))
         return state, info
 
+    def _phases(self, model: LAP):
+        """The step as a list of (compute, gradient ranges final after it, overlaps-communication) phases.
+
+        world == 1: [forward + whole LLM backward], [SigLIP backward].
+        world > 1 : the LLM backward is cut into `bwd_segments` groups of layers and the SigLIP backward into
+        `vis_segments`, and each group's weight-gradient ranges are all-reduced while the NEXT group computes
+        (scripts/train.py:532-537: the reference's all-reduce is scheduled by XLA inside the backward the same way).
+        Only the small tail (biases, norm scales, position table) and the last SigLIP group are reduced with nothing
+        left to hide them."""
+        lay = model.layout
+        L, Ls = model.cfg.gemma.depth, model.cfg.siglip.depth
+        nl = max(1, min(self.bwd_segments if self.world > 1 else 1, L))
+        nv = max(1, min(self.vis_segments if self.world > 1 else 1, Ls))
+        lcuts = [round(L * i / nl) for i in range(nl, -1, -1)]      # e.g. [18, 12, 6, 0]
+        vcuts = [round(Ls * i / nv) for i in range(nv, -1, -1)]     # e.g. [27, 18, 9, 0]
+        llm_rest = (lay.offsets["e.mod_w"], lay.small_begin)        # modulation Dense, action / time projections, embedding
+        phases = []
+        for i in range(nl):
+            hi, lo = lcuts[i], lcuts[i + 1]
+
+            def run(st, hi=hi, lo=lo, first=(i == 0), last=(i == nl - 1)):
+                if first:
+                    model.forward_and_heads(st)
+                model.backward_llm_layers(st, hi, lo)
+                if last:
+                    model.backward_llm_tail(st)
+
+            ranges = model.layer_grad_ranges(model.LLM_LAYER_GRADS, lo, hi) + ([llm_rest] if i == nl - 1 else [])
+            phases.append((run, ranges, i > 0))
+        for i in range(nv):
+            hi, lo = vcuts[i], vcuts[i + 1]
+
+            def runv(st, hi=hi, lo=lo):
+                model.backward_vision_segment(st, hi, lo)
+
+            ranges = model.layer_grad_ranges(model.VIS_LAYER_GRADS, lo, hi)
+            if i == 0:
+                ranges.append((lay.offsets["img.head_w"], lay.offsets["g.qkv_w"]))
+            if i == nv - 1:
+                ranges += [(lay.offsets["img.patch_w"], lay.offsets["img.qkv_w"]), (lay.small_begin, lay.total)]
+            phases.append((runv, ranges, True))
+        return phases
+
+    def _run_phase(self, fn, st, overlaps_comm: bool) -> None:
+        """With world > 1 the persistent GEMMs of a phase that runs next to an in-flight all-reduce leave `comm_sms`
+        SMs to NCCL (a 148-CTA persistent grid on fewer free SMs would run a second wave)."""
+        if self.world > 1 and overlaps_comm:
+            ops.gemm_max_ctas = max(2, (ops.num_sms() - self.comm_sms) // 2 * 2)
+        try:
+            fn(st)
+        finally:
+            ops.gemm_max_ctas = 0
+
     def step_staged(self, state: TrainState, st, step: int | None = None) -> dict:
         """One optimisation step on inputs already staged in HBM (model._stage) — no host<->device traffic except
-        the 20-byte per-step hyper-parameter vector.  After two eager steps (which allocate every workspace) the
-        three phases — forward+LLM backward, SigLIP backward, optimizer — are captured as CUDA graphs and replayed:
-        ~1700 kernel launches become three graph launches.  With world > 1 the all-reduce of the LLM gradients (88 %
-        of the bytes) is issued between the first two graphs and overlaps the SigLIP backward."""
+        the 32-byte per-step hyper-parameter vector.  After two eager steps (which allocate every workspace) the
+        phases (`_phases`) and the optimizer are captured as CUDA graphs and replayed: ~1700 kernel launches become a
+        handful of graph launches.  With world > 1 each phase's finished gradient ranges are all-reduced (NCCL,
+        asynchronously) while the next phase computes."""
         model = state.model
         step = state.step if step is None else int(step)
         self._set_hyper(state, step)
         key = (st.B, st.R, id(state), id(model))  # a graph is bound to the buffers of ONE state / model
+        phases = self._phase_cache.get(id(model))
+        if phases is None:
+            phases = self._phase_cache[id(model)] = self._phases(model)
         g = self._graphs.get(key)
         if g is None and self.use_cuda_graph and self._warm.get(key, 0) >= 2:
-            g = self._capture(state, st)
+            g = self._capture(state, st, phases)
             self._graphs[key] = g
-        lo, hi = model.llm_grad_range()
+        works = []
+        for i, (fn, ranges, overlaps) in enumerate(phases):
+            if g is None:
+                self._run_phase(fn, st, overlaps)
+            else:
+                g[i].replay()
+            for lo, hi in ranges:
+                works += self._allreduce_begin(model.G[lo:hi])
+        self._allreduce_end(works)
         if g is None:
-            loss = model.forward_backward_llm(st)
-            works = self._allreduce_begin(model.G[lo:hi])  # overlaps the SigLIP backward
-            self._backward_vision(model, st)
-            works += self._allreduce_begin(model.G[:lo]) + self._allreduce_begin(model.G[hi:])
-            self._allreduce_end(works)
             self._apply_gradients_device(state)
             self._warm[key] = self._warm.get(key, 0) + 1
         else:
-            g[0].replay()
-            works = self._allreduce_begin(model.G[lo:hi])
-            g[1].replay()
-            works += self._allreduce_begin(model.G[:lo]) + self._allreduce_begin(model.G[hi:])
-            self._allreduce_end(works)
-            g[2].replay()
-            loss = model.buf("loss.total", (1,), F32)
+            g[-1].replay()
+        loss = model.buf("loss.total", (1,), F32)
         state.step = step + 1
         # fresh scalars (the reference returns new arrays): the persistent buffers are overwritten by the next step,
         # and callers accumulate info dicts over log_interval steps.  Stream-ordered clones, no host sync.
         stats = self._stats.clone()
         return {"loss": loss[0].clone(), "grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
-    def _backward_vision(self, model, st) -> None:
-        """SigLIP backward; with world > 1 the persistent GEMMs leave `comm_sms` SMs to the concurrent all-reduce."""
-        if self.world > 1:
-            ops.gemm_max_ctas = max(2, (ops.num_sms() - self.comm_sms) // 2 * 2)
-        try:
-            model.backward_vision(st)
-        finally:
-            ops.gemm_max_ctas = 0
-
-    def _capture(self, state: TrainState, st):
+    def _capture(self, state: TrainState, st, phases):
         model = state.model
         torch.cuda.synchronize()
         pool = torch.cuda.graph_pool_handle()
-        g1 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g1, pool=pool):
-            model.forward_backward_llm(st)
-        g2 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g2, pool=pool):
-            self._backward_vision(model, st)
-        g3 = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g3, pool=pool):
+        graphs = []
+        for fn, _, overlaps in phases:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool):
+                self._run_phase(fn, st, overlaps)
+            graphs.append(g)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, pool=pool):
             self._apply_gradients_device(state)
+        graphs.append(g)
         torch.cuda.synchronize()
-        # capture does not execute: the caller replays the three graphs right away to perform this step
-        return (g1, g2, g3)
+        # capture does not execute: the caller replays the graphs right away to perform this step
+        return tuple(graphs)
 
     def _set_hyper(self, state: TrainState, step: int) -> None:
         """Per-step scalars (lr, Adam bias corrections, EMA decay) go to the device as one tiny pinned copy."""

@@ -874,3 +874,35 @@ def test_product_package_never_touches_the_oracle_or_the_reference():
     users = {f.name for f in ast.walk(tree) if isinstance(f, ast.FunctionDef)
              for n in ast.walk(f) if isinstance(n, ast.ImportFrom) and (n.module or "").split(".")[0] == "oracle"}
     assert users and all("cpu" in u or "reference" in u for u in users), users
+
+
+def test_train_phases_cover_every_gradient_exactly_once():
+    """train.py::_phases (the data-parallel schedule): the gradient ranges all-reduced after the phases tile the flat
+    buffer — every tensor exactly once, layer groups in backward order — for world 1 and world > 1."""
+    from lap_b200 import params as P
+    from lap_b200.config import get_config
+    from lap_b200.model import LAP
+    from lap_b200.train import TrainingStepRunner
+
+    for name in ("debug_tiny", "lap_libero"):
+        tc = get_config(name)
+        model = LAP.__new__(LAP)
+        model.cfg = model.config = tc.model
+        model.layout = P.FlatLayout(tc.model)
+        lay = model.layout
+        for world, segs in ((1, 3), (2, 3), (8, 2), (2, 50)):
+            r = TrainingStepRunner(tc)
+            r.world, r.bwd_segments, r.vis_segments = world, segs, segs
+            phases = r._phases(model)
+            L, Ls = tc.model.gemma.depth, tc.model.siglip.depth
+            assert len(phases) == (2 if world == 1 else min(segs, L) + min(segs, Ls))
+            assert [p[2] for p in phases][0] is False and all(p[2] for p in phases[1:])
+            covered = np.zeros(lay.total, dtype=np.int8)
+            for _, ranges, _ in phases:
+                for lo, hi in ranges:
+                    assert 0 <= lo < hi <= lay.total
+                    covered[lo:hi] += 1
+            assert covered.max() == 1
+            for n, shape in lay.shapes.items():
+                o = lay.offsets[n]
+                assert covered[o:o + int(np.prod(shape))].min() == 1, n
