@@ -283,7 +283,7 @@ class LAP:
             bb, jj = np.nonzero(lm)
             R = len(bb)
             # fixed row capacity (padding rows weigh 0) so that the captured step keeps its shapes; grows if needed
-            if R > self._R_caps.get(B, 0):
+            if B not in self._R_caps or R > self._R_caps[B]:
                 self._R_caps[B] = max(_round_up(int(R * 1.25) + 1, 128), 128)
             Rp = self._R_caps[B]
             rows = np.zeros(Rp, np.int64)
