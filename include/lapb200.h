@@ -225,12 +225,20 @@ typedef struct {
                                         (set if a barrier timed out), [2..] per-head arrival counters (LAPB_DENOISE_FOLD=1) */
   unsigned long long* prof;          /* optional [32]: ns per phase slot seen by CTA 0 (16.. = sub-phase marks); (0 prologue, 1 action_in, 2/3 P1 work /
                                         barrier, 4/5 P2, 6/7 P2b, 8/9 P3, 10/11 P4, 12/13 P5, 14 final); NULL = off */
+  int32_t packed;                    /* 1: qkv_w / o_w / gu_w / down_w, Kc ([Tpad, HD] per layer) and VcT ([HD, TpadK] per layer)
+                                        are TILE-MAJOR copies made by lapb200_pack_tiles (cluster kernel only); 0: row-major */
+  int32_t reserved_;
 } lapb_denoise_params_t;
 /* 1 if the shape is supported by the persistent kernel (B == 1, A <= 16, num_steps <= 16, head_dim <= 256 ...). */
 int lapb200_denoise_supported(int64_t B, int64_t A, int64_t ad, int64_t D1, int64_t NH, int64_t HD, int64_t F1,
                               int64_t Pn, int64_t Tpad, int64_t num_steps);
 int lapb200_denoise_grid(void);
 int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s);
+/* Tile-major copy of a [rows, cols] bf16 matrix for the weight-streaming kernels (rows % 8 == 0, cols % 32 == 0):
+ * dst[((r/8 * cols/32 + c/32) * 8 + r%8) * 32 + c%32] = src[r*row_stride + c*col_stride] (0 for c >= valid_cols), `batch`
+ * matrices `src_bs` / `dst_bs` elements apart.  A warp of the streaming kernels then reads 512 contiguous bytes per load. */
+int lapb200_pack_tiles(const void* src, void* dst, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+                       int64_t valid_cols, int64_t batch, int64_t src_bs, int64_t dst_bs, lapb_stream_t s);
 /* VcT[l][d][j] = Vc[l][j][d] for j < Pn, 0 for Pn <= j < TpadK. */
 int lapb200_transpose_v(const void* Vc, void* VcT, int64_t L, int64_t Tpad, int64_t TpadK, int64_t HD, int64_t Pn,
                         lapb_stream_t s);

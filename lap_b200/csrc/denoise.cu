@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include <stdlib.h>
+#include <algorithm>
 
 namespace lapb {
 
@@ -857,21 +858,27 @@ __host__ __device__ inline size_t dnc_smem_bytes(int D1, int HD, int OD, int F1)
 }
 
 // one n8 weight tile x K groups [kg_begin, kg_end) against the staged rows As: accumulator fragment of this warp
-// (lane (g, t): rows g and g + 8, columns 2t and 2t + 1)
-__device__ __forceinline__ void dnc_warp_tile(const bf16* As, int lda, int M, const bf16* wtile, long ldw, int kg_begin,
-                                              int kg_end, float (&acc)[4]) {
+// (lane (g, t): rows g and g + 8, columns 2t and 2t + 1).  The 16-byte fragment of lane (g, t) for K group kg sits at
+//   wtile + kg * kstride + g * gstride + 8 t
+// row-major weights [N, K]: kstride = 32, gstride = K; TILE-MAJOR packed weights (lapb200_pack_tiles): kstride = 256,
+// gstride = 32, i.e. the 32 lanes of a warp read 512 CONTIGUOUS bytes per K group and a whole n8 x K tile is one
+// contiguous 16 K-byte range (row-major makes every warp load 8 separate 64-byte row segments, which costs ~4x the
+// memory latency: 20-25 GB/s per SM instead of ~150).  U fragments are in flight per lane.
+template <int U>
+__device__ __forceinline__ void dnc_warp_tile(const bf16* As, int lda, int M, const bf16* wtile, long kstride, long gstride,
+                                              int kg_begin, int kg_end, float (&acc)[4]) {
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const bf16* xlo = As + (long)g * lda + 8 * t;
   const bf16* xhi = As + (long)(g + 8) * lda + 8 * t;
-  const bf16* wr = wtile + (long)g * ldw + 8 * t;
+  const bf16* wr = wtile + (long)g * gstride + 8 * t;
   const bool vlo = g < M, vhi = (g + 8) < M;
   const uint4 zero = make_uint4(0, 0, 0, 0);
-  for (int kg0 = kg_begin; kg0 < kg_end; kg0 += 4) {
-    uint4 b[4];
+  for (int kg0 = kg_begin; kg0 < kg_end; kg0 += U) {
+    uint4 b[U];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) b[u] = (kg0 + u < kg_end) ? dn_ld_stream(wr + (kg0 + u) * 32) : zero;
+    for (int u = 0; u < U; ++u) b[u] = (kg0 + u < kg_end) ? dn_ld_stream(wr + (long)(kg0 + u) * kstride) : zero;
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < U; ++u) {
       if (kg0 + u < kg_end) {
         const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(xlo + (kg0 + u) * 32) : zero;
         const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(xhi + (kg0 + u) * 32) : zero;
@@ -911,6 +918,10 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int rank = blockIdx.x;  // one cluster: rank == cluster_ctarank
+  // operand addressing (see dnc_warp_tile): tile-major packed weights / caches, or row-major
+  const bool pk = p.packed != 0;
+  const long ks = pk ? 256 : 32;
+  auto gs = [&](long ld) -> long { return pk ? 32 : ld; };
   const bf16* mod = reinterpret_cast<const bf16*>(p.mod);
   bf16* XE = reinterpret_cast<bf16*>(p.XE);
   bf16* XE1 = reinterpret_cast<bf16*>(p.XE1);
@@ -964,7 +975,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
     const bf16* mw = reinterpret_cast<const bf16*>(p.mod_w);
     for (int tile = tb + warp; tile < te; tile += DN_WARPS) {
       float acc[4] = {0.f, 0.f, 0.f, 0.f};
-      dnc_warp_tile(h_s, ldh, S, mw + (long)tile * 8 * D1, D1, 0, ng1, acc);
+      dnc_warp_tile<8>(h_s, ldh, S, mw + (long)tile * 8 * D1, 32, D1, 0, ng1, acc);  // mod_w stays row-major
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int m = g + (j >> 1) * 8, n = tile * 8 + 2 * t4 + (j & 1);
@@ -1020,7 +1031,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
       __syncthreads();
       for (int tile = q_tb + warp; tile < q_te; tile += DN_WARPS) {
         float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        dnc_warp_tile(h_s, ldh, A, Wqkv + (long)tile * 8 * D1, D1, 0, ng1, acc);
+        dnc_warp_tile<8>(h_s, ldh, A, Wqkv + (long)tile * 8 * D1, ks, gs(D1), 0, ng1, acc);
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
           const int m = g + (j >> 1) * 8;
@@ -1057,7 +1068,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
         // S = Q_h K^T over this CTA's prefix keys: a warp owns 8-key tiles (full K = HD)
         for (int tl = warp; tl < nk / 8; tl += DN_WARPS) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          dnc_warp_tile(q_s, ldq, A, Kc + (long)(key0 + 8 * tl) * HD, HD, 0, HD / 32, acc);
+          dnc_warp_tile<8>(q_s, ldq, A, Kc + (long)(key0 + 8 * tl) * HD, ks, gs(HD), 0, HD / 32, acc);
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int m = g + (j >> 1) * 8, kk = 8 * tl + 2 * t4 + (j & 1), key = key0 + kk;
@@ -1105,7 +1116,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
         float* po = p.part_o + (long)rank * 16 * HD;
         if (warp < HD / 8) {
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
-          dnc_warp_tile(p_s, LDP, A, VcT + (long)(warp * 8) * p.TpadK + key0, p.TpadK, 0, nk / 32, acc);
+          dnc_warp_tile<8>(p_s, LDP, A, VcT + (long)(warp * 8) * p.TpadK + (pk ? (long)(key0 / 32) * 256 : (long)key0), ks,
+                           gs(p.TpadK), 0, nk / 32, acc);
           if (at_half) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -1129,16 +1141,19 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
       tick(5);
 
       // ---------------- P3: combine the two halves of every head -> O (staged), XE1 = XE + gate_a * (O Wo^T) ----------------
-      for (int i = threadIdx.x; i < A * OD; i += DN_THREADS) {
-        const int m = i / OD, c = i - m * OD, h = c / HD, d = c - h * HD;
-        const float* ml0 = p.part_ml + ((long)(2 * h) * 16 + m) * 2;
-        const float* ml1 = p.part_ml + ((long)(2 * h + 1) * 16 + m) * 2;
-        const float m0 = __ldcg(ml0), l0 = __ldcg(ml0 + 1), m1 = __ldcg(ml1), l1 = __ldcg(ml1 + 1);
-        const float o0 = __ldcg(p.part_o + ((long)(2 * h) * 16 + m) * HD + d);
-        const float o1 = __ldcg(p.part_o + ((long)(2 * h + 1) * 16 + m) * HD + d);
-        const float mx = fmaxf(m0, m1);
-        const float w0 = __expf(m0 - mx), w1 = __expf(m1 - mx);
-        h_s[m * ldo + c] = __float2bfloat16_rn((w0 * o0 + w1 * o1) / (w0 * l0 + w1 * l1));
+      for (int i = threadIdx.x; i < A * (OD / 4); i += DN_THREADS) {
+        const int m = i / (OD / 4), c = (i - m * (OD / 4)) * 4, h = c / HD, d = c - h * HD;
+        const float2 ml0 = __ldcg(reinterpret_cast<const float2*>(p.part_ml + ((long)(2 * h) * 16 + m) * 2));
+        const float2 ml1 = __ldcg(reinterpret_cast<const float2*>(p.part_ml + ((long)(2 * h + 1) * 16 + m) * 2));
+        const float4 o0 = __ldcg(reinterpret_cast<const float4*>(p.part_o + ((long)(2 * h) * 16 + m) * HD + d));
+        const float4 o1 = __ldcg(reinterpret_cast<const float4*>(p.part_o + ((long)(2 * h + 1) * 16 + m) * HD + d));
+        const float mx = fmaxf(ml0.x, ml1.x);
+        const float w0 = __expf(ml0.x - mx), w1 = __expf(ml1.x - mx);
+        const float inv = 1.0f / (w0 * ml0.y + w1 * ml1.y);
+        uint2 u;
+        u.x = pack_bf16x2((w0 * o0.x + w1 * o1.x) * inv, (w0 * o0.y + w1 * o1.y) * inv);
+        u.y = pack_bf16x2((w0 * o0.z + w1 * o1.z) * inv, (w0 * o0.w + w1 * o1.w) * inv);
+        *reinterpret_cast<uint2*>(h_s + m * ldo + c) = u;
       }
       __syncthreads();
       tick(6);
@@ -1148,7 +1163,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           const int gq = (ngo + 3) / 4;
           if (t0 + tl < o_te)
-            dnc_warp_tile(h_s, ldo, A, Wo + (long)(t0 + tl) * 8 * OD, OD, kq * gq, min(ngo, (kq + 1) * gq), acc);
+            dnc_warp_tile<8>(h_s, ldo, A, Wo + (long)(t0 + tl) * 8 * OD, ks, gs(OD), kq * gq, min(ngo, (kq + 1) * gq), acc);
           *reinterpret_cast<float4*>(red + (((kq * 8 + tl) * 32 + lane) << 2)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
           __syncthreads();
           {
@@ -1180,8 +1195,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
       __syncthreads();
       for (int pr = f_pb + warp; pr < f_pe; pr += DN_WARPS) {
         float ag[4] = {0.f, 0.f, 0.f, 0.f}, au[4] = {0.f, 0.f, 0.f, 0.f};
-        dnc_warp_tile(h_s, ldh, A, Wgu + (long)pr * 8 * D1, D1, 0, ng1, ag);
-        dnc_warp_tile(h_s, ldh, A, Wgu + ((long)F1 + (long)pr * 8) * D1, D1, 0, ng1, au);
+        dnc_warp_tile<8>(h_s, ldh, A, Wgu + (long)pr * 8 * D1, ks, gs(D1), 0, ng1, ag);
+        dnc_warp_tile<8>(h_s, ldh, A, Wgu + ((long)F1 + (long)pr * 8) * D1, ks, gs(D1), 0, ng1, au);
 #pragma unroll
         for (int j = 0; j < 4; j += 2) {
           const int m = g + (j >> 1) * 8;
@@ -1206,7 +1221,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_cluster_kernel(const la
           float acc[4] = {0.f, 0.f, 0.f, 0.f};
           const int gq = (ngf + 3) / 4;
           if (t0 + tl < o_te)
-            dnc_warp_tile(h_s, ldf, A, Wd + (long)(t0 + tl) * 8 * F1, F1, kq * gq, min(ngf, (kq + 1) * gq), acc);
+            dnc_warp_tile<8>(h_s, ldf, A, Wd + (long)(t0 + tl) * 8 * F1, ks, gs(F1), kq * gq, min(ngf, (kq + 1) * gq), acc);
           *reinterpret_cast<float4*>(red + (((kq * 8 + tl) * 32 + lane) << 2)) = make_float4(acc[0], acc[1], acc[2], acc[3]);
           __syncthreads();
           {
@@ -1272,6 +1287,24 @@ __global__ void transpose_v_kernel(const bf16* __restrict__ Vc, bf16* __restrict
   }
 }
 
+// Tile-major packing for the weight-streaming kernels: element (r, c) of a [rows, cols] matrix (rows % 8 == 0,
+// cols % 32 == 0) moves to  ((r/8 * cols/32 + c/32) * 8 + r%8) * 32 + c%32 : every n8 x K tile is one contiguous
+// range and the 32 lanes of a warp (lane = 4 (r%8) + t, 8 elements each) read 512 contiguous bytes per K group.
+// Source element (r, c) is src[r * rs + c * cs] (cs != 1: a transposed source, e.g. V^T from the value cache), zero
+// for c >= valid_cols.  grid.y = batch (layers).
+__global__ void pack_tiles_kernel(const bf16* __restrict__ src, bf16* __restrict__ dst, long rows, long cols, long rs, long cs,
+                                  long valid_cols, long src_bs, long dst_bs) {
+  const bf16* sb = src + (long)blockIdx.y * src_bs;
+  bf16* db = dst + (long)blockIdx.y * dst_bs;
+  const long n = rows * cols;
+  for (long o = (long)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (long)gridDim.x * blockDim.x) {
+    const long e = o & 31, g = (o >> 5) & 7, blk = o >> 8;
+    const long ng = cols >> 5, kg = blk % ng, tile = blk / ng;
+    const long r = tile * 8 + g, c = kg * 32 + e;
+    db[o] = (c < valid_cols) ? sb[r * rs + c * cs] : __float2bfloat16_rn(0.f);
+  }
+}
+
 }  // namespace lapb
 
 using namespace lapb;
@@ -1298,6 +1331,18 @@ int lapb200_transpose_v(const void* Vc, void* VcT, int64_t L, int64_t Tpad, int6
   return 0;
 }
 
+int lapb200_pack_tiles(const void* src, void* dst, int64_t rows, int64_t cols, int64_t row_stride, int64_t col_stride,
+                       int64_t valid_cols, int64_t batch, int64_t src_bs, int64_t dst_bs, lapb_stream_t s) {
+  LAPB_REQUIRE(rows % 8 == 0 && cols % 32 == 0 && batch >= 1, "pack_tiles: rows %% 8, cols %% 32 (got %ld x %ld)", (long)rows,
+               (long)cols);
+  const long n = rows * cols;
+  dim3 grid((unsigned)std::min<long>((n + 255) / 256, 4096), (unsigned)batch);
+  pack_tiles_kernel<<<grid, 256, 0, STREAM(s)>>>((const bf16*)src, (bf16*)dst, rows, cols, row_stride, col_stride, valid_cols,
+                                                 src_bs, dst_bs);
+  LAPB_LAUNCH_OK("pack_tiles");
+  return 0;
+}
+
 int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
   const lapb_denoise_params_t& p = *params;
   LAPB_REQUIRE(lapb200_denoise_supported(1, p.A, p.ad, p.D1, p.NH, p.HD, p.F1, p.Pn, p.Tpad, p.num_steps),
@@ -1311,6 +1356,8 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
     const char* e = getenv("LAPB_DENOISE_MODE");
     mode = (e && e[0] == 'c') ? 1 : 0;  // default: grid (measured faster, see the K10c header)
   }
+  LAPB_REQUIRE(!p.packed || mode == 1, "denoise_loop: tile-major packed operands are read by the cluster kernel only "
+               "(LAPB_DENOISE_MODE=cluster)");
   const size_t csmem = dnc_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
   if (mode == 1 && p.NH * 2 <= DNC_CTAS && p.TpadK <= 2 * DNC_MAXK && csmem <= (size_t)227 * 1024) {
     static size_t cconf = 0;
@@ -1334,6 +1381,8 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
     const cudaError_t ce = cudaLaunchKernelEx(&ccfg, denoise_cluster_kernel, p);
     if (ce == cudaSuccess) return 0;
     (void)cudaGetLastError();  // e.g. no GPC with 16 free SMs for the cluster: use the grid kernel from now on
+    LAPB_REQUIRE(!p.packed, "denoise_loop: the cluster launch failed (%s) and the grid kernel cannot read packed operands",
+                 cudaGetErrorString(ce));
     mode = 0;
   }
   const size_t smem = dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);

@@ -13,6 +13,7 @@ parameters (lap_b200/params.py).
 from __future__ import annotations
 
 import math
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -99,6 +100,9 @@ class LAP:
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
         self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
+        # K10c: the 16-CTA cluster variant reads TILE-MAJOR packed copies of the expert weights and of the prefix cache
+        self.denoise_cluster = os.environ.get("LAPB_DENOISE_MODE", "")[:1] == "c"
+        self._packed_expert: dict | None = None
         self._infer_graphs: dict = {}
         self._infer_warm: dict = {}
         hd = cfg.gemma.head_dim
@@ -171,6 +175,21 @@ class LAP:
         """bf16 compute copy of the master params + hi/lo split of the fp32 embedding table."""
         ops.cast_f32_bf16(self.P, self.W16)
         self.refresh_embed_split()
+        self._packed_expert = None  # tile-major copies for K10c are rebuilt on their next use
+
+    def _packed_expert_weights(self) -> dict:
+        """Tile-major copies of the action expert's four per-layer weight stacks (ops.pack_tiles): what the cluster
+        variant of the denoise loop streams (512 contiguous bytes per warp load).  Serving-time only; 0.6 GB."""
+        if self._packed_expert is None:
+            out = {}
+            for name in ("e.qkv_w", "e.o_w", "e.gu_w", "e.down_w"):
+                w = self.w(name)  # [L, N, K]
+                L, N, K = w.shape
+                dst = torch.empty_like(w)
+                ops.pack_tiles(w, dst, N, K, K, 1, K, batch=L, src_bs=N * K, dst_bs=N * K)
+                out[name] = dst
+            self._packed_expert = out
+        return self._packed_expert
 
     def refresh_embed_split(self) -> None:
         ops.split_hi_lo(self.p("g.embed"), self.E_split, self.cfg.vocab_size, self.cfg.gemma.width)
@@ -1024,7 +1043,18 @@ class LAP:
         TpadK = _round_up(Pn, 64)
         nm = P.n_mod(cfg)
         VcT = self.buf("inf.VcT", (L, HD, TpadK))
-        ops.transpose_v(Vc, VcT, L, Tpad, TpadK, HD, Pn)
+        packed = self.denoise_cluster
+        if packed:
+            # tile-major copies of the prefix keys and of V^T (once per inference, like the transpose it replaces)
+            Kp = self.buf("inf.Kp", (L, Tpad, HD))
+            ops.pack_tiles(Kc, Kp, Tpad, HD, HD, 1, HD, batch=L, src_bs=Kc.shape[1] * Tpad * HD, dst_bs=Tpad * HD)
+            ops.pack_tiles(Vc, VcT, HD, TpadK, 1, HD, Pn, batch=L, src_bs=Vc.shape[1] * Tpad * HD, dst_bs=HD * TpadK)
+            Kc = Kp
+            pw = self._packed_expert_weights()
+        else:
+            ops.transpose_v(Vc, VcT, L, Tpad, TpadK, HD, Pn)
+            pw = None
+        wsel = (lambda n: pw[n][0]) if packed else (lambda n: self.w(n, 0))
         nch = TpadK // 64 + 1
         times, t = [], 1.0
         while t >= -dt / 2:  # lap.py:669-672
@@ -1033,7 +1063,7 @@ class LAP:
         assert len(times) == num_steps
         S = num_steps
         ptrs = dict(
-            qkv_w=self.w("e.qkv_w", 0), o_w=self.w("e.o_w", 0), gu_w=self.w("e.gu_w", 0), down_w=self.w("e.down_w", 0),
+            qkv_w=wsel("e.qkv_w"), o_w=wsel("e.o_w"), gu_w=wsel("e.gu_w"), down_w=wsel("e.down_w"),
             mod_w=self.w("e.mod_w"), mod_b=self.p("e.mod_b"),
             ain_w=self.p("action_in_w"), ain_b=self.p("action_in_b"), tin_w=self.p("time_in_w"), tin_b=self.p("time_in_b"),
             tout_w=self.p("time_out_w"), tout_b=self.p("time_out_b"), aout_w=self.p("action_out_w"),
@@ -1051,7 +1081,7 @@ class LAP:
 
         ops.denoise_loop(
             ints=dict(A=A, ad=ad, D1=D1, NH=NH, HD=HD, F1=F1, L=L, Pn=Pn, Tpad=Tpad, TpadK=TpadK, W32=Tpad // 32, nm=nm,
-                      num_steps=S),
+                      num_steps=S, packed=int(packed)),
             dt=dt, qscale=HD ** -0.5, times=times, ptrs=ptrs,
             strides=dict(qkv_ls=lstride("e.qkv_w"), o_ls=lstride("e.o_w"), gu_ls=lstride("e.gu_w"),
                          down_ls=lstride("e.down_w"), kc_ls=Tpad * HD, vct_ls=HD * TpadK))

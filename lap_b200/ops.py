@@ -365,6 +365,10 @@ def transpose_v(Vc, VcT, L, Tpad, TpadK, HD, Pn):
     call("transpose_v", Vc, VcT, L, Tpad, TpadK, HD, Pn)
 
 
+def pack_tiles(src, dst, rows, cols, row_stride, col_stride, valid_cols, batch=1, src_bs=0, dst_bs=0):
+    call("pack_tiles", src, dst, rows, cols, row_stride, col_stride, valid_cols, batch, src_bs, dst_bs)
+
+
 def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, strides: dict) -> None:
     """K10: every Euler step of sample_actions in one persistent cooperative kernel (csrc/denoise.cu)."""
     p = _lib.DenoiseParams()
