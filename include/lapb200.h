@@ -195,6 +195,14 @@ int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uin
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);
 
+/* K2: fused SigLIP attention forward (flax MultiHeadDotProductAttention between the QKV and output projections,
+ * OP/models/siglip.py:88-93) for head_dim in (64, 80] (So400m: 72).  qkv: bf16 [Ni*Np, 3, nh, hd] rows = (image, token), q
+ * already divided by sqrt(hd); O: bf16 [Ni*Np, nh*hd]; P (optional, Np % 8 == 0): bf16 [Ni, nh, Np, Np] softmax
+ * probabilities saved for the backward pass.  mode 0: softmax evaluated in bf16 like flax 0.10.2 (bf16 logits, e =
+ * bf16(exp(bf16(s - max))), bf16(sum), p = bf16(e / sum)); mode 1: fp32 softmax of the bf16 logits, one rounding of P. */
+int lapb200_vit_attn_fwd(const void* qkv, void* O, void* P, int64_t Ni, int64_t nh, int64_t Np, int64_t hd, int64_t mode,
+                         lapb_stream_t s);
+
 /* K10: the whole flow-matching Euler loop of LAP.sample_actions (lap.py:634-672: embed_suffix pi0.py:139-186, the
  * action-expert half of gemma.Module gemma.py:455-531 against the prefix KV cache, action_out_proj, x += dt*v) for ONE
  * sample as ONE persistent cooperative kernel (one CTA per SM, grid barriers between dependent phases, next-phase weights

@@ -98,6 +98,7 @@ class LAP:
         self._R_caps: dict[int, int] = {}  # batch size -> capacity of the language-loss row list (fixed shapes per B)
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
+        self.use_fused_vit_attention = os.environ.get("LAPB_FUSED_VIT", "1") != "0"  # K2 (SigLIP, head_dim 72)
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
         self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
         # K10c: the 16-CTA cluster variant reads TILE-MAJOR packed copies of the expert weights and of the prefix cache
@@ -354,7 +355,9 @@ class LAP:
     # ------------------------------------------------------------------------------------------
     # SigLIP tower (OP/models/siglip.py), all cameras in one pass, rows ordered (b, cam, patch)
     # ------------------------------------------------------------------------------------------
-    def _siglip_fwd(self, st: Staged, X0: torch.Tensor, rows_per_sample: int, softmax_mode: int = 0) -> None:
+    def _siglip_fwd(self, st: Staged, X0: torch.Tensor, rows_per_sample: int, softmax_mode: int = 0,
+                    save: bool = True) -> None:
+        """`save=False` (inference): the attention probabilities are not written out."""
         cfg, s = self.cfg, self.cfg.siglip
         B, C, Np, W, F, nh, hd = st.B, len(cfg.image_keys), cfg.num_patches, s.width, s.mlp_dim, s.num_heads, s.head_dim
         D = cfg.gemma.width
@@ -376,14 +379,19 @@ class LAP:
             qkv = self.buf(f"img.qkv.{l}", (Ms, 3 * W))
             ops.gemm(y0, self.w("img.qkv_w", l), qkv, M=Ms, N=3 * W, K=W, bias=self.p("img.qkv_b", l),
                      epi=ops.EPI_QSCALE, q_cols=W, q_div=q_div)
-            Pm = self.buf(f"img.P.{l}", (Ni, nh, Np, Np))
-            qf = qkv.view(-1)
-            ops.gemm(qf, qf[W:], Pm, M=Np, N=Np, K=hd, lda=3 * W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
-                     a_bs=(hd, Np * 3 * W), b_bs=(hd, Np * 3 * W), c_bs=(Np * Np, nh * Np * Np))
-            ops.vit_softmax_fwd(Pm, Ni * nh * Np, Np, Np, softmax_mode)
             o = self.buf(f"img.o.{l}", (Ms, W))
-            ops.gemm(Pm, qf[2 * W:], o, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=W, batch_i=nh, batch_o=Ni,
-                     a_bs=(Np * Np, nh * Np * Np), b_bs=(hd, Np * 3 * W), c_bs=(hd, Np * W))
+            if self.use_fused_vit_attention and 64 < hd <= 80:
+                # K2: S = QK^T -> softmax -> PV in one tcgen05 kernel; P is written out only for the backward pass
+                Pm = self.buf(f"img.P.{l}", (Ni, nh, Np, Np)) if save else None
+                ops.vit_attn_fwd(qkv, o, Pm, Ni, nh, Np, hd, softmax_mode)
+            else:
+                Pm = self.buf(f"img.P.{l}", (Ni, nh, Np, Np))
+                qf = qkv.view(-1)
+                ops.gemm(qf, qf[W:], Pm, M=Np, N=Np, K=hd, lda=3 * W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                         a_bs=(hd, Np * 3 * W), b_bs=(hd, Np * 3 * W), c_bs=(Np * Np, nh * Np * Np))
+                ops.vit_softmax_fwd(Pm, Ni * nh * Np, Np, Np, softmax_mode)
+                ops.gemm(Pm, qf[2 * W:], o, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=W, batch_i=nh,
+                         batch_o=Ni, a_bs=(Np * Np, nh * Np * Np), b_bs=(hd, Np * 3 * W), c_bs=(hd, Np * W))
             x1 = self.buf(f"img.x1.{l}", (Ms, W))
             ops.gemm(o, self.w("img.out_w", l), x1, M=Ms, N=W, K=W, bias=self.p("img.out_b", l), epi=ops.EPI_RESID,
                      resid=x)
@@ -666,7 +674,7 @@ class LAP:
         Mg, Me = B * Pn, B * A
         sv0 = "g.X.0" if save else "g.X.tmp0"
         X0 = self.buf(sv0, (Mg, D))
-        self._siglip_fwd(st, X0, Pn, softmax_mode)
+        self._siglip_fwd(st, X0, Pn, softmax_mode, save=save)
         ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
         XE0 = self.buf("g.XE.0" if save else "g.XE.tmp0", (Me, D1))
         self._suffix_embed(st, None, st.time, XE0)
@@ -994,7 +1002,7 @@ class LAP:
         x = self.buf("inf.x", (B, A * ad), F32)
         # ---- prefix pass fills the cache ----
         X0 = self.buf("inf.X0", (B * Pn, D))
-        self._siglip_fwd(st, X0, Pn)
+        self._siglip_fwd(st, X0, Pn, save=False)
         ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
         bits_p = self.buf("inf.bits_p", (B, Pn, W32), torch.int32)
         pos_p = self.buf("inf.pos_p", (B, Pn), torch.int32)
@@ -1095,16 +1103,25 @@ class LAP:
     # autoregressive decoding of lang-action tokens (lap.py:678-766), greedy
     # ------------------------------------------------------------------------------------------
     def sample_tokens(self, rng, observation: Observation, *, max_decoding_steps: int = 390,
-                      temperature: float = 0.0) -> torch.Tensor:
+                      temperature: float = 0.0, gumbel=None) -> torch.Tensor:
         """LAP.sample_tokens: prefix prefill -> KV cache -> one token per step through expert 0 alone, until every
         sample has emitted EOS or `max_decoding_steps`.  Returns int32 [B, max_decoding_steps] (zeros after the stop).
 
         The reference right-aligns the prefix (pi0_fast.left_to_right_align) and masks decode steps by slot RANGE
         (slot >= prefix_start, lap.py:737-741).  Attention does not depend on where a key is stored, so the engine keeps
         its left-aligned cache and translates the range into key positions: rolled slot i holds token (i + seqlen) mod P."""
-        if temperature > 0.0:
-            raise NotImplementedError("temperature > 0 draws from jax.random.categorical (lap.py:727-729); greedy only")
+        # temperature > 0 (lap.py:727-729): jax.random.categorical(key, z) == argmax(z + Gumbel(key)).  The Gumbel noise is
+        # either passed in (`gumbel` [B, max_decoding_steps, vocab], what the parity tests do) or drawn on the device from
+        # a torch generator seeded by `rng` — same distribution, not JAX's threefry stream.
         cfg, g = self.cfg, self.cfg.gemma
+        temperature = float(temperature)
+        gum_gen = None
+        if temperature > 0.0:
+            if gumbel is not None:
+                gumbel = (gumbel if isinstance(gumbel, torch.Tensor) else torch.from_numpy(np.asarray(gumbel))).to(
+                    self.device, torch.float32)
+            else:
+                gum_gen = torch.Generator(device=self.device).manual_seed(int(rng) if rng is not None else 0)
         st = self._stage(observation, with_loss=False)
         B, Pn, L, S = st.B, cfg.prefix_len, cfg.max_token_len, int(max_decoding_steps)
         if B > 16:
@@ -1116,7 +1133,7 @@ class LAP:
         Tpad = _round_up(Pn + cfg.action_horizon, 64)
         W32 = Tpad // 32
         X0 = self.buf("inf.X0", (B * Pn, D))
-        self._siglip_fwd(st, X0, Pn)
+        self._siglip_fwd(st, X0, Pn, save=False)
         ops.embed_fwd(st.tokens, self.p("g.embed"), X0, B, L, C * Np, Pn, D, math.sqrt(D))
         bits_p = self.buf("inf.bits_p", (B, Pn, W32), torch.int32)
         pos_p = self.buf("inf.pos_p", (B, Pn), torch.int32)
@@ -1163,7 +1180,15 @@ class LAP:
         qscale = hd ** -0.5
         step = 0
         while step < S:
-            token = torch.argmax(logits, dim=-1).to(torch.int32)       # lap.py:730 (temperature = 0)
+            if temperature > 0.0:
+                if gumbel is not None:
+                    gstep = gumbel[:, step]
+                else:  # -log(-log(u)), u in (0, 1)
+                    u = torch.rand((B, V), generator=gum_gen, device=self.device).clamp_(1e-20, 1.0 - 1e-7)
+                    gstep = -torch.log(-torch.log(u))
+                token = torch.argmax(logits / temperature + gstep, dim=-1).to(torch.int32)   # lap.py:727-729
+            else:
+                token = torch.argmax(logits, dim=-1).to(torch.int32)   # lap.py:730 (temperature = 0)
             out[:, step] = token
             eos |= token == self.EOS_TOKEN
             all_eos = bool(eos.all().item())

@@ -387,5 +387,10 @@ def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, str
     _count()
 
 
+def vit_attn_fwd(qkv, O, P, Ni, nh, Np, hd, mode=0):
+    """K2 (csrc/fa_vit.cu): fused SigLIP attention forward; P = None skips the store of the probabilities."""
+    call("vit_attn_fwd", qkv, O, P, Ni, nh, Np, hd, mode)
+
+
 def fa_gemma_fwd(Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim):
     call("fa_gemma_fwd", Q, Kc, Vc, bits, P, O0, O1, B, R, G, Tq, S_len, Tpad, W32, split_row, head_dim)

@@ -303,6 +303,26 @@ class TrainingStepRunner:
         return {"grad_norm": stats[0], "grad_norm_f32": stats[0], "param_norm": stats[3]}
 
 
+class ValidationStepRunner:
+    """scripts/train.py:422-450: `compute_loss(train=False)` on a validation batch -> the metrics dict plus `val_loss`.
+    The reference folds `state.step` into the rng (`fold_in(rng, state.step)`); explicit `noise` / `time` in the batch
+    extras take precedence, as in `TrainingStepRunner`."""
+
+    def __init__(self, config: TrainConfig):
+        self.config = config
+
+    def __call__(self, rng, state: TrainState, batch) -> dict:
+        observation, actions = batch[0], batch[1]
+        extra = batch[2] if len(batch) > 2 else {}
+        eval_rng = (int(rng) if rng is not None else 0) * 1_000_003 + int(state.step)
+        val_loss, val_metrics = state.model.compute_loss(
+            eval_rng, observation, actions, train=False, verbose_mode=self.config.model.verbose_mode,
+            noise=extra.get("noise"), time=extra.get("time"))
+        val_metrics = dict(val_metrics)
+        val_metrics["val_loss"] = val_loss
+        return val_metrics
+
+
 def train_step(config: TrainConfig, rng, state: TrainState, batch, step: int | None = None):
     return TrainingStepRunner(config)(rng, state, batch, step)
 

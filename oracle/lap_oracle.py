@@ -488,10 +488,13 @@ def left_to_right_align(x, input_mask, attn_mask):
     return (torch.roll(x, -seqlen, 0), torch.roll(input_mask, -seqlen, 0), torch.roll(attn_mask, (-seqlen, -seqlen), (0, 1)))
 
 
-def sample_tokens(p, cfg, obs, *, max_decoding_steps=390, bf16: bool, softmax_dtype="bf16", return_logits=False):
-    """LAP.sample_tokens (lap.py:678-766), greedy (temperature = 0): right-aligned prefix prefill -> KV cache -> one token
-    per step through expert 0 alone.  The decode-step mask is the reference's RANGE mask
-    (slot >= prefix_start and slot <= current), not a validity mask (lap.py:737-741)."""
+def sample_tokens(p, cfg, obs, *, max_decoding_steps=390, bf16: bool, softmax_dtype="bf16", return_logits=False,
+                  temperature: float = 0.0, gumbel=None):
+    """LAP.sample_tokens (lap.py:678-766): right-aligned prefix prefill -> KV cache -> one token per step through expert 0
+    alone.  The decode-step mask is the reference's RANGE mask (slot >= prefix_start and slot <= current), not a validity
+    mask (lap.py:737-741).  temperature = 0: greedy.  temperature > 0 (lap.py:727-729): jax.random.categorical(key, z) is
+    argmax(z + Gumbel noise drawn from key); the noise is passed in explicitly (`gumbel` [B, S, V]) because the threefry
+    stream cannot be reproduced."""
     pre_tok, pre_mask, pre_ar = embed_prefix(p, cfg, obs, bf16, softmax_dtype)
     attn = make_attn_mask(pre_mask, pre_ar)
     B, P, _ = pre_tok.shape
@@ -511,7 +514,10 @@ def sample_tokens(p, cfg, obs, *, max_decoding_steps=390, bf16: bool, softmax_dt
     logits_log = []
     step = 0
     while (not bool(eos.all())) and step < S:
-        token = last_logit.argmax(-1)  # [B, 1]
+        if temperature > 0.0:
+            token = (last_logit / temperature + gumbel[:, step : step + 1].to(last_logit.dtype)).argmax(-1)
+        else:
+            token = last_logit.argmax(-1)  # [B, 1]
         logits_log.append(last_logit[:, 0])
         out[:, step] = token[:, 0]
         eos = eos | (token[:, 0] == 1)  # EOS_TOKEN (lap.py:32)

@@ -486,3 +486,54 @@ def test_fa_pair_variant_is_bit_identical_to_the_product_kernel():
     for shape in ("train", "ragged"):
         for k in ("O0", "O1", "P", "finite"):
             assert a[shape][k] == b[shape][k], (shape, k)
+
+
+@pytest.mark.parametrize("Ni,nh,Np,mode", [(3, 16, 256, 0), (2, 2, 64, 0), (2, 2, 16, 1), (1, 16, 256, 1), (2, 4, 729, 0),
+                                           (1, 2, 200, 0)])
+def test_fused_vit_attention_matches_unfused_and_torch(Ni, nh, Np, mode):
+    """K2 (csrc/fa_vit.cu) vs the GEMM + vit_softmax + GEMM path it replaces (same rounding points: equal up to the
+    fp32 summation order of the softmax denominator) and vs a direct PyTorch statement of flax's attention with the
+    bf16 / fp32 softmax (siglip.py:88-93).  Np = 729 is the 384 px case (3 key chunks, ragged last chunk, no P output:
+    Np % 8 != 0), Np = 200 a ragged single chunk, Np = 16 / 64 the test-model sizes."""
+    hd = 72
+    W = nh * hd
+    torch.manual_seed(Np + nh)
+    qkv = (torch.randn(Ni * Np, 3 * W, device=DEV) * 0.5).bfloat16()
+    qkv[:, :W] = (qkv[:, :W].float() * 0.3).bfloat16()
+    want_p = Np % 8 == 0
+    O = torch.full((Ni * Np, W), 9.0, device=DEV, dtype=torch.bfloat16)
+    P = torch.full((Ni, nh, Np, Np), 7.0, device=DEV, dtype=torch.bfloat16) if want_p else None
+    ops.vit_attn_fwd(qkv, O, P, Ni, nh, Np, hd, mode)
+    torch.cuda.synchronize()
+    q, k, v = (qkv[:, i * W:(i + 1) * W].float().view(Ni, Np, nh, hd) for i in range(3))
+    logits = torch.einsum("nqhd,nkhd->nhqk", q, k).bfloat16().float()
+    m = logits.max(-1, keepdim=True).values
+    if mode == 0:
+        e = torch.exp((logits - m).bfloat16().float()).bfloat16().float()
+        p_ref = (e / e.sum(-1, keepdim=True).bfloat16().float()).bfloat16()
+    else:
+        p_ref = torch.softmax(logits, -1).bfloat16()
+    o_ref = torch.einsum("nhqk,nkhd->nqhd", p_ref.float(), v).reshape(Ni * Np, W)
+    assert torch.isfinite(O.float()).all()
+    assert rel_err(O, o_ref) < 4e-3, rel_err(O, o_ref)
+    if want_p:
+        assert rel_err(P, p_ref) < 3e-3
+        assert (P.float() - p_ref.float()).abs().max() <= 2 ** -8 + 1e-6
+        # unfused engine path on the same inputs
+        Pu = torch.zeros(Ni, nh, Np, Np, device=DEV, dtype=torch.bfloat16)
+        Ou = torch.zeros(Ni * Np, W, device=DEV, dtype=torch.bfloat16)
+        qf = qkv.view(-1)
+        ops.gemm(qf, qf[W:], Pu, M=Np, N=Np, K=hd, lda=3 * W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                 a_bs=(hd, Np * 3 * W), b_bs=(hd, Np * 3 * W), c_bs=(Np * Np, nh * Np * Np))
+        ops.vit_softmax_fwd(Pu, Ni * nh * Np, Np, Np, mode)
+        ops.gemm(Pu, qf[2 * W:], Ou, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=W, batch_i=nh, batch_o=Ni,
+                 a_bs=(Np * Np, nh * Np * Np), b_bs=(hd, Np * 3 * W), c_bs=(hd, Np * W))
+        torch.cuda.synchronize()
+        # identical except where bf16(sum) sits on a rounding boundary (a whole row then moves by one ulp)
+        frac_rows_equal = (P == Pu).all(-1).float().mean().item()
+        assert frac_rows_equal > 0.99, frac_rows_equal
+        assert rel_err(O, Ou) < 2e-3
+    # without P (inference) the output is the same
+    O2 = torch.zeros_like(O)
+    ops.vit_attn_fwd(qkv, O2, None, Ni, nh, Np, hd, mode)
+    assert torch.equal(O2, O)

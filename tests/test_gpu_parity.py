@@ -325,8 +325,32 @@ def test_sample_tokens_matches_oracle(name):
             else:
                 break  # after a near-tie the two decodes may legitimately diverge
     assert n_cmp >= 3
-    with pytest.raises(NotImplementedError):
-        model.sample_tokens(0, Observation.from_dict(b), max_decoding_steps=4, temperature=0.7)
+    # temperature > 0 (lap.py:727-729): categorical sampling = argmax(logits / T + Gumbel noise); with the SAME explicit
+    # noise the engine and the oracle must pick the same tokens wherever the perturbed top-2 margin is not within bf16 noise
+    gen = torch.Generator().manual_seed(5)
+    u = torch.rand((3, S, cfg.vocab_size), generator=gen).clamp_(1e-20, 1.0 - 1e-7)
+    gum = -torch.log(-torch.log(u))
+    T = 0.7
+    toks_o, logits_o = O.sample_tokens(ref, cfg, obs_for_oracle(b, langact=False), max_decoding_steps=S, bf16=True,
+                                       return_logits=True, temperature=T, gumbel=gum)
+    toks_e = model.sample_tokens(0, Observation.from_dict(b), max_decoding_steps=S, temperature=T, gumbel=gum).cpu()
+    pert = logits_o / T + gum[:, : logits_o.shape[1]]
+    top2 = pert.topk(2, dim=-1).values
+    n_cmp = 0
+    for i in range(3):
+        for s_ in range(logits_o.shape[1]):
+            if top2[i, s_, 0] - top2[i, s_, 1] > 2e-2 * logits_o[i, s_].abs().max() / T:
+                assert int(toks_e[i, s_]) == int(toks_o[i, s_]), (i, s_, toks_e[i], toks_o[i])
+                n_cmp += 1
+            else:
+                break
+    assert n_cmp >= 3
+    assert not torch.equal(toks_o, O.sample_tokens(ref, cfg, obs_for_oracle(b, langact=False), max_decoding_steps=S, bf16=True))
+    # without explicit noise the draw comes from a device generator seeded by rng: reproducible, rng-dependent
+    t1 = model.sample_tokens(3, Observation.from_dict(b), max_decoding_steps=S, temperature=5.0)
+    t2 = model.sample_tokens(3, Observation.from_dict(b), max_decoding_steps=S, temperature=5.0)
+    t3 = model.sample_tokens(4, Observation.from_dict(b), max_decoding_steps=S, temperature=5.0)
+    assert torch.equal(t1, t2) and not torch.equal(t1, t3)
 
 
 def test_edge_cases_empty_langact_dropped_camera_masked_samples():
@@ -553,3 +577,17 @@ def test_info_dict_values_are_not_aliased_by_later_steps():
         for k, v in snap.items():
             assert float(info[k]) == v, k
     assert infos[0][1]["loss"] != infos[2][1]["loss"]
+
+
+def test_validation_step_runner_returns_metrics_and_val_loss():
+    """scripts/train.py:422-450: compute_loss(train=False) + `val_loss`; does not touch the train state."""
+    from lap_b200.train import ValidationStepRunner, batch_from_dict, init_train_state
+    tc, ref, model, b = _setup("debug_tiny", 3)
+    state = init_train_state(tc, model=model)
+    p0 = model.P.clone()
+    out = ValidationStepRunner(tc)(0, state, batch_from_dict(b))
+    obs, actions, extra = batch_from_dict(b)
+    loss, m = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    assert set(out) == {"lang_loss", "action_loss", "langact_loss", "val_loss"}
+    assert float(out["val_loss"]) == float(loss) and float(out["action_loss"]) == float(m["action_loss"])
+    assert torch.equal(p0, model.P) and state.step == 0

@@ -321,3 +321,25 @@ def test_sample_tokens_equals_teacher_forced_forward(tiny):
     b["image_mask"]["left_wrist_0_rgb"][1] = False
     toks2 = O.sample_tokens(ref, cfg, obs_for_oracle(b, langact=False), max_decoding_steps=3, bf16=True)
     assert toks2.shape == (3, 3)
+
+
+def test_sample_tokens_temperature_is_gumbel_argmax(tiny):
+    """lap.py:727-729: jax.random.categorical(key, z / T) == argmax(z / T + Gumbel noise).  With zero noise the sampled
+    decode is the greedy decode; with huge noise on one token per step it emits exactly those tokens; the teacher-forcing
+    invariant keeps holding for whatever was sampled (the sampled token, not the argmax, is fed back)."""
+    tc, ref, _ = tiny
+    cfg = tc.model
+    b = synthetic_batch(cfg, 2, step=5, with_langact=False)
+    obs = obs_for_oracle(b, langact=False)
+    K = 4
+    greedy = O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False)
+    zero = torch.zeros(2, K, cfg.vocab_size)
+    assert torch.equal(O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False, temperature=0.5, gumbel=zero), greedy)
+    forced = torch.tensor([[5, 9, 11, 3], [7, 7, 2, 4]])
+    g = torch.zeros(2, K, cfg.vocab_size)
+    g.scatter_(2, forced[:, :, None], 1e9)
+    toks, logits = O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False, temperature=1.3, gumbel=g, return_logits=True)
+    assert torch.equal(toks, forced)
+    toks2, logits2 = O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False, return_logits=True)
+    assert rel_err(logits[:, 0], logits2[:, 0]) < 1e-6           # the first logits do not depend on what is sampled
+    assert rel_err(logits[:, 1], logits2[:, 1]) > 1e-3           # later ones do
