@@ -195,6 +195,21 @@ int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uin
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);
 
+/* Image side of preprocess_observation (src/lap/models/model_adapter.py:83-181), ahead of lapb200_patchify.
+ * image_resize_pad: resize_with_pad (model_adapter.py:113-116 -> OP/shared/image_tools.py:11-52) of uint8 or float32
+ *   [B, Hin, Win, 3] images into float32 [B, Hout, Wout, 3] in [-1, 1] (uint8: round, clip, then the u8/255*2-1 of
+ *   Observation.from_dict).  The separable antialiasing filter of jax.image.resize is passed as sparse rows: output row p of
+ *   the resized region [rh, rw] (placed at (ph0, pw0)) reads input rows ystart[p] .. +ytaps-1 with weights yw[p*ytaps + t].
+ * image_augment: model_adapter.py:118-151 with explicit per-sample parameters params[b] = (crop_y, crop_x, angle_deg,
+ *   brightness, contrast, saturation, skip, unused) — one bilinear resampling (crop 95 % -> resize -> rotate) + colour jitter;
+ *   definition: oracle/image_oracle.py.  src uint8 (0..255) or float32 in [-1, 1]; dst float32 in [-1, 1], dst != src. */
+int lapb200_image_resize_pad(const void* src, int64_t src_is_u8, float* dst, int64_t B, int64_t Hin, int64_t Win,
+                             int64_t Hout, int64_t Wout, int64_t rh, int64_t rw, int64_t ph0, int64_t pw0,
+                             const int32_t* ystart, const float* yw, int64_t ytaps, const int32_t* xstart, const float* xw,
+                             int64_t xtaps, lapb_stream_t s);
+int lapb200_image_augment(const void* src, int64_t src_is_u8, float* dst, int64_t B, int64_t H, int64_t W,
+                          const float* params, lapb_stream_t s);
+
 /* K2: fused SigLIP attention forward (flax MultiHeadDotProductAttention between the QKV and output projections,
  * OP/models/siglip.py:88-93) for head_dim in (64, 80] (So400m: 72).  qkv: bf16 [Ni*Np, 3, nh, hd] rows = (image, token), q
  * already divided by sqrt(hd); O: bf16 [Ni*Np, nh*hd]; P (optional, Np % 8 == 0): bf16 [Ni, nh, Np, Np] softmax

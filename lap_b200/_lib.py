@@ -16,7 +16,7 @@ from pathlib import Path
 CSRC = Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "liblapb200.so"
 INCLUDE = Path(__file__).resolve().parent.parent / "include"
-SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "loss.cu", "optimizer.cu", "skinny.cu", "fa_gemma.cu", "fa_gemma_pair.cu", "fa_vit.cu", "denoise.cu"]
+SOURCES = ["api.cu", "gemm.cu", "elementwise.cu", "attention.cu", "loss.cu", "optimizer.cu", "skinny.cu", "fa_gemma.cu", "fa_gemma_pair.cu", "fa_vit.cu", "denoise.cu", "image.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

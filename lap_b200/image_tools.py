@@ -52,3 +52,44 @@ def resize_with_pad(images, height: int, width: int, *, antialias: bool = True) 
     pw0, rem_w = divmod(width - rw, 2)
     y = np.pad(y, ((0, 0), (ph0, ph0 + rem_h), (pw0, pw0 + rem_w), (0, 0)), constant_values=pad_value)
     return y if batched else y[0]
+
+
+def resize_plan(in_h: int, in_w: int, height: int, width: int, *, antialias: bool = True) -> dict:
+    """Everything the device kernel `lapb200_image_resize_pad` needs for one (input, output) resolution pair: the size and
+    position of the resized region and the two interpolation matrices of `resize_with_pad` in sparse-row form
+    (start index + a fixed number of taps per output row, zero-padded weights)."""
+    ratio = max(in_w / width, in_h / height)
+    rh, rw = int(in_h / ratio), int(in_w / ratio)
+
+    def sparse(w: np.ndarray):
+        nz = w != 0
+        start = np.where(nz.any(1), nz.argmax(1), 0).astype(np.int32)
+        last = np.where(nz.any(1), w.shape[1] - 1 - nz[:, ::-1].argmax(1), 0)
+        taps = int((last - start + 1).max())
+        idx = start[:, None] + np.arange(taps)[None, :]
+        vals = np.where(idx < w.shape[1], np.take_along_axis(w, np.minimum(idx, w.shape[1] - 1), 1), 0.0)
+        return start, vals.astype(np.float32), taps
+
+    ys, yw, yt = sparse(_weights(in_h, rh, antialias))
+    xs, xw, xt = sparse(_weights(in_w, rw, antialias))
+    return dict(rh=rh, rw=rw, ph0=(height - rh) // 2, pw0=(width - rw) // 2, ystart=ys, yw=yw, ytaps=yt, xstart=xs, xw=xw,
+                xtaps=xt)
+
+
+AUG_CROP_FRACTION = 0.95  # model_adapter.py:130,136: RandomCrop(int(w * 0.95), int(h * 0.95))
+
+
+def draw_augmentation_params(rng: np.random.Generator, batch: int, height: int, width: int, skip=None) -> np.ndarray:
+    """Per-sample parameters of the train-time augmentation (model_adapter.py:118-151) with the reference's ranges: crop
+    window position uniform over the image, rotation in (-5, 5) degrees, brightness / contrast / saturation in
+    (-0.2, 0.2); `skip` marks VQA samples, which the reference leaves untouched.  -> float32 [batch, 8] rows
+    (crop_y, crop_x, angle_deg, brightness, contrast, saturation, skip, 0) for `lapb200_image_augment`."""
+    ch, cw = int(height * AUG_CROP_FRACTION), int(width * AUG_CROP_FRACTION)
+    p = np.zeros((batch, 8), dtype=np.float32)
+    p[:, 0] = rng.uniform(0, height - ch, batch)
+    p[:, 1] = rng.uniform(0, width - cw, batch)
+    p[:, 2] = rng.uniform(-5.0, 5.0, batch)
+    p[:, 3:6] = rng.uniform(-0.2, 0.2, (batch, 3))
+    if skip is not None:
+        p[:, 6] = np.asarray(skip, dtype=np.float32).reshape(batch)
+    return p

@@ -387,6 +387,15 @@ def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, str
     _count()
 
 
+def image_resize_pad(src, dst, B, Hin, Win, Hout, Wout, rh, rw, ph0, pw0, ystart, yw, ytaps, xstart, xw, xtaps):
+    call("image_resize_pad", src, src.dtype == torch.uint8, dst, B, Hin, Win, Hout, Wout, rh, rw, ph0, pw0, ystart, yw,
+         ytaps, xstart, xw, xtaps)
+
+
+def image_augment(src, dst, B, H, W, params):
+    call("image_augment", src, src.dtype == torch.uint8, dst, B, H, W, params)
+
+
 def vit_attn_fwd(qkv, O, P, Ni, nh, Np, hd, mode=0):
     """K2 (csrc/fa_vit.cu): fused SigLIP attention forward; P = None skips the store of the probabilities."""
     call("vit_attn_fwd", qkv, O, P, Ni, nh, Np, hd, mode)

@@ -207,11 +207,13 @@ def test_engine_matches_reference_pytorch_port(case):
     assert np.array_equal(model._bufs["mask.pos"].cpu().numpy(), g["positions"])
     v = model._bufs["loss.v"].view(B, cfg.action_horizon, -1).float().cpu()
     u = _t(inp["noise"]) - _t(inp["actions"])
-    _chk("pi05 port fp32: flow-matching error", rel_err(v - u, torch.sign(v - u) * torch.sqrt(_t(g["mse"]))), 1.5e-2)  # bf16 engine vs fp32 reference
+    # bf16 engine vs the fp32 reference run (measured on B200, round 2: 3.4e-3 / 4.2e-3; the bf16 and fp32 reference runs
+    # themselves differ by 1.2-1.6e-3 on sampled actions)
+    _chk("pi05 port fp32: flow-matching error", rel_err(v - u, torch.sign(v - u) * torch.sqrt(_t(g["mse"]))), 8e-3)
     b2 = _engine_batch(cfg, inp, "none")
     for steps, key in ((10, "sampled_actions"), (3, "sampled_actions_3")):
         a = model.sample_actions(0, Observation.from_dict(b2), num_steps=steps, noise=inp["noise"])
-        _chk(f"pi05 port fp32: {key}", rel_err(a, g[key]), 1.5e-2)
+        _chk(f"pi05 port fp32: {key}", rel_err(a, g[key]), 6e-3)  # measured 1.5e-3 ... 3.1e-3
 
 
 @pytest.mark.gpu
@@ -232,13 +234,13 @@ def test_engine_matches_reference_lap_source(case):
     ops.mask_expand(model._bufs["mask.bits"], dense, B * T, T, Tpad // 32)
     assert np.array_equal(np.packbits(dense.cpu().numpy().astype(bool), axis=-1), g["attn_mask"])
     assert np.array_equal(model._bufs["mask.pos"].cpu().numpy(), g["positions"])
-    _chk("lap.py fp32: loss", abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])), 3e-3)
+    _chk("lap.py fp32: loss", abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])), 1.5e-3)  # measured <= 6.5e-4
     for k in ("lang_loss", "langact_loss", "action_loss"):
-        _chk(f"lap.py fp32: {k}", abs(m[k].item() - float(g[k])) / abs(float(g[k])), 6e-3)
+        _chk(f"lap.py fp32: {k}", abs(m[k].item() - float(g[k])) / abs(float(g[k])), 2e-3)  # measured <= 7.5e-4
     a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, "real")), num_steps=10, noise=inp["noise"])
-    _chk("lap.py fp32: sampled_actions_eval", rel_err(a, g["sampled_actions_eval"]), 1.5e-2)
+    _chk("lap.py fp32: sampled_actions_eval", rel_err(a, g["sampled_actions_eval"]), 5e-3)  # measured <= 2.2e-3
     a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, "none")), num_steps=10, noise=inp["noise"])
-    _chk("lap.py fp32: sampled_actions_serve", rel_err(a, g["sampled_actions_serve"]), 1.5e-2)
+    _chk("lap.py fp32: sampled_actions_serve", rel_err(a, g["sampled_actions_serve"]), 5e-3)  # measured <= 1.6e-3
 
 
 @pytest.mark.gpu
@@ -256,10 +258,10 @@ def test_engine_matches_reference_sources_in_bf16(case):
     loss, m = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
     _chk("lap.py bf16: loss", abs(loss.item() - float(g["loss"])) / abs(float(g["loss"])), 1e-3)
     for k in ("lang_loss", "langact_loss", "action_loss"):
-        _chk(f"lap.py bf16: {k}", abs(m[k].item() - float(g[k])) / abs(float(g[k])), 2e-3)
+        _chk(f"lap.py bf16: {k}", abs(m[k].item() - float(g[k])) / abs(float(g[k])), 1e-3)  # measured <= 4.1e-4
     for tag, la in (("eval", "real"), ("serve", "none")):
         a = model.sample_actions(0, Observation.from_dict(_engine_batch(cfg, inp, la)), num_steps=10, noise=inp["noise"])
-        _chk(f"lap.py bf16: sampled_actions_{tag}", rel_err(a, g[f"sampled_actions_{tag}"]), 5e-3)
+        _chk(f"lap.py bf16: sampled_actions_{tag}", rel_err(a, g[f"sampled_actions_{tag}"]), 4e-3)  # measured <= 2.1e-3
 
 
 # ----------------------------------------------------------------------------------------------------------------
