@@ -19,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 import torch
 
-from . import ops
+from . import image_tools, ops
 from . import params as P
 from .config import LAPConfig
 from .observation import CoTObservation, Observation, to_numpy
@@ -95,6 +95,7 @@ class LAP:
         self._pool: dict[tuple, torch.Tensor] = {}
         self._io: dict[tuple, tuple[torch.Tensor, torch.Tensor]] = {}  # persistent (pinned host, device) input buffers
         self._io_event = None
+        self._resize_plans: dict = {}
         self._R_caps: dict[int, int] = {}  # batch size -> capacity of the language-loss row list (fixed shapes per B)
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
@@ -220,8 +221,19 @@ class LAP:
     # ------------------------------------------------------------------------------------------
     # input staging (host -> device); masks are tiny and are assembled on the host
     # ------------------------------------------------------------------------------------------
+    def _resize_plan(self, H: int, W: int) -> dict:
+        """Device-resident filter of `resize_with_pad` for one input resolution (built once, image_tools.resize_plan)."""
+        plan = self._resize_plans.get((H, W))
+        if plan is None:
+            S = self.cfg.image_size
+            plan = image_tools.resize_plan(H, W, S, S)
+            for k in ("ystart", "yw", "xstart", "xw"):
+                plan[k] = torch.from_numpy(np.ascontiguousarray(plan[k])).to(self.device)
+            self._resize_plans[(H, W)] = plan
+        return plan
+
     def _stage(self, obs: Observation, actions=None, noise=None, time=None, *, with_loss: bool,
-               global_counts: tuple[float, float] | None = None) -> Staged:
+               global_counts: tuple[float, float] | None = None, aug: dict | None = None) -> Staged:
         cfg = self.cfg
         dev = self.device
         nbytes = 0
@@ -256,10 +268,27 @@ class LAP:
             im_t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
             if im_t.dtype != torch.uint8:
                 im_t = im_t.to(torch.float32)
-            if tuple(im_t.shape[1:3]) != (cfg.image_size, cfg.image_size):
-                raise ValueError(f"image {k} has resolution {tuple(im_t.shape[1:3])}; resize_with_pad is outside the "
-                                 f"hot path (model_adapter.py:113-116) — provide {cfg.image_size}x{cfg.image_size}")
-            images.append(up(im_t, name=f"img.{k}"))
+            if im_t.ndim != 4 or im_t.shape[-1] != 3:
+                raise ValueError(f"image {k} must be [batch, height, width, 3], got {tuple(im_t.shape)}")
+            cur = up(im_t, name=f"img.{k}")
+            Bi, H, W = int(im_t.shape[0]), int(im_t.shape[1]), int(im_t.shape[2])
+            S = cfg.image_size
+            if (H, W) != (S, S):
+                # model_adapter.py:113-116: resize_with_pad, on the device (fused with the uint8 -> [-1, 1] conversion)
+                plan = self._resize_plan(H, W)
+                out = self.buf(f"img.rs.{k}", (Bi, S, S, 3), F32)
+                ops.image_resize_pad(cur, out, Bi, H, W, S, S, plan["rh"], plan["rw"], plan["ph0"], plan["pw0"],
+                                     plan["ystart"], plan["yw"], plan["ytaps"], plan["xstart"], plan["xw"], plan["xtaps"])
+                cur = out
+            if aug is not None and aug.get(k) is not None:
+                # model_adapter.py:118-151: crop / resize / rotate / colour jitter with explicit per-sample parameters
+                pa = np.zeros((Bi, 8), np.float32)
+                src = np.asarray(to_numpy(aug[k]), np.float32).reshape(Bi, -1)
+                pa[:, : src.shape[1]] = src
+                out = self.buf(f"img.aug.{k}", (Bi, S, S, 3), F32)
+                ops.image_augment(cur, out, Bi, S, S, up(pa, name=f"aug.{k}"))
+                cur = out
+            images.append(cur)
         B = images[0].shape[0]
         Np, L, C = cfg.num_patches, cfg.max_token_len, len(cfg.image_keys)
         tokens = to_numpy(obs.tokenized_prompt).astype(np.int32)
@@ -718,24 +747,38 @@ class LAP:
         m["langact_loss"] = (per_sample * st.sample_mask).sum() / st.sample_mask.sum().clamp_min(1.0)
         return m
 
+    def draw_augmentation(self, rng, observation: Observation, B: int) -> dict:
+        """Augmentation parameters for every camera (model_adapter.py:118-151 draws them with jax.random per sample and
+        camera; here numpy's generator seeded by rng).  VQA samples are skipped like the reference's `vqa_mask`."""
+        gen = np.random.default_rng((int(rng) if rng is not None else 0) + 0x5EED)
+        vqa = getattr(observation, "is_vqa_sample", None)
+        skip = None if vqa is None else to_numpy(vqa).astype(np.float32)
+        S = self.cfg.image_size
+        return {k: image_tools.draw_augmentation_params(gen, B, S, S, skip) for k in self.cfg.image_keys}
+
     def compute_loss(self, rng, observation: Observation, actions, *, train: bool = False, stage_config=None,
-                     verbose_mode=None, return_augmented_images: bool = False, noise=None, time=None):
+                     verbose_mode=None, return_augmented_images: bool = False, noise=None, time=None, aug=None):
         """lap.py:380-602.  Returns (loss, metrics) — 0-d CUDA tensors.  `noise` [B,A,ad] and `time` [B] replace the
-        reference's jax.random draws (lap.py:193-194); if omitted they are drawn from torch's generator seeded by rng."""
+        reference's jax.random draws (lap.py:193-194); if omitted they are drawn from torch's generator seeded by rng.
+        `aug` {camera: [B, 7] parameters} replaces the augmentation draws when `train` and the config enables image
+        augmentation (model_adapter.py:118-151; parameter meaning: lapb200_image_augment)."""
         cfg = self.cfg
-        if train and cfg.enable_image_augmentation:
-            raise NotImplementedError("augmax image augmentation is a 'next' row (SURVEY §8f N4); "
-                                      "lap_libero runs with enable_image_augmentation=False")
         B = to_numpy(actions).shape[0] if not isinstance(actions, torch.Tensor) else actions.shape[0]
+        if train and cfg.enable_image_augmentation and aug is None:
+            aug = self.draw_augmentation(rng, observation, B)
         if noise is None or time is None:
             gen = torch.Generator().manual_seed(int(rng) if rng is not None else 0)
             if noise is None:
                 noise = torch.randn((B, cfg.action_horizon, cfg.action_dim), generator=gen)
             if time is None:  # Beta(1.5, 1) by inverse CDF, from the same seeded generator (lap.py:194)
                 time = torch.rand((B,), generator=gen).pow(1.0 / 1.5) * 0.999 + 0.001
-        st = self._stage(observation, actions, noise, time, with_loss=True)
+        st = self._stage(observation, actions, noise, time, with_loss=True, aug=aug if train else None)
         loss, _ = self._forward_loss(st, save=False, compute_grad_seed=False)
         metrics = self._metrics(st)
+        if return_augmented_images:  # lap.py:413-420: the images the towers actually saw, for logging
+            metrics = dict(metrics, augmented_images={
+                k: (im.float() / 255.0 * 2.0 - 1.0 if im.dtype == torch.uint8 else im.clone())
+                for k, im in zip(cfg.image_keys, st.images)})
         return loss[0].clone(), metrics
 
     # ------------------------------------------------------------------------------------------

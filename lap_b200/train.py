@@ -123,8 +123,15 @@ class TrainingStepRunner:
             if time is None:
                 u = torch.rand((B,), generator=gen)
                 time = u.pow(1.0 / 1.5) * 0.999 + 0.001  # Beta(1.5, 1) by inverse CDF
+        aug = extra.get("aug")
+        if aug is None and mc.enable_image_augmentation:
+            # model_adapter.py:118-151 is on for training unless the config disables it (lap_libero does); the draw is
+            # per rank and step like the flow-matching noise
+            rank = dist.get_rank() if self.world > 1 else 0
+            aug = model.draw_augmentation(((int(rng) if rng is not None else 0) * 1_000_003 + step) * 4099 + rank,
+                                          observation, B)
         counts = self._global_counts(observation, B, model.device)
-        st = model._stage(observation, actions, noise, time, with_loss=True, global_counts=counts)
+        st = model._stage(observation, actions, noise, time, with_loss=True, global_counts=counts, aug=aug)
         info = self.step_staged(state, st, step)
         if self.world > 1:
             # each rank holds its shard's share of the global mean; the sum over ranks is the global loss
@@ -330,4 +337,4 @@ def train_step(config: TrainConfig, rng, state: TrainState, batch, step: int | N
 def batch_from_dict(d: dict):
     """Loader-format dict (data_loader.py:327) -> ((CoTObservation, actions), extras)."""
     obs = CoTObservation.from_dict(d)
-    return obs, d["actions"], {k: d[k] for k in ("noise", "time") if k in d}
+    return obs, d["actions"], {k: d[k] for k in ("noise", "time", "aug") if k in d}

@@ -537,3 +537,50 @@ def test_fused_vit_attention_matches_unfused_and_torch(Ni, nh, Np, mode):
     O2 = torch.zeros_like(O)
     ops.vit_attn_fwd(qkv, O2, None, Ni, nh, Np, hd, mode)
     assert torch.equal(O2, O)
+
+
+@pytest.mark.parametrize("H,W,u8", [(480, 640, True), (200, 300, False), (100, 150, True), (360, 224, False), (224, 224, True)])
+def test_image_resize_pad_matches_host_statement(H, W, u8):
+    """Device `resize_with_pad` (+ the uint8 -> [-1, 1] conversion) vs `lap_b200.image_tools.resize_with_pad`, the numpy
+    statement pinned against the reference's own `resize_with_pad_torch` (model_adapter.py:113-116, image_tools.py:11-52)."""
+    from lap_b200 import image_tools
+    rng = np.random.default_rng(H + W)
+    B, S = 3, 224
+    img = rng.integers(0, 256, (B, H, W, 3), dtype=np.uint8) if u8 else rng.uniform(-1, 1, (B, H, W, 3)).astype(np.float32)
+    ref = image_tools.resize_with_pad(img, S, S)
+    ref = ref.astype(np.float32) / 255.0 * 2.0 - 1.0 if u8 else ref
+    plan = image_tools.resize_plan(H, W, S, S)
+    d = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    out = torch.full((B, S, S, 3), 5.0, device=DEV)
+    ops.image_resize_pad(d(img), out, B, H, W, S, S, plan["rh"], plan["rw"], plan["ph0"], plan["pw0"], d(plan["ystart"]),
+                         d(plan["yw"]), plan["ytaps"], d(plan["xstart"]), d(plan["xw"]), plan["xtaps"])
+    got = out.cpu().numpy()
+    diff = np.abs(got - ref)
+    if u8:  # a pixel whose filtered value sits on x.5 may round the other way (fp32 summation order): one level of 255
+        assert diff.max() <= 2.0 / 255.0 + 1e-6 and (diff > 1e-6).mean() < 2e-3
+    else:
+        assert diff.max() < 2e-5
+
+
+@pytest.mark.parametrize("u8", [False, True])
+def test_image_augment_matches_numpy_statement(u8):
+    """Device augmentation (crop 95 % -> resize -> rotate as one bilinear resampling, then brightness / contrast /
+    saturation; explicit per-sample parameters) vs oracle/image_oracle.py (model_adapter.py:118-151)."""
+    from oracle import image_oracle as IO
+    rng = np.random.default_rng(3)
+    B, S = 5, 224
+    raw = rng.integers(0, 256, (B, S, S, 3), dtype=np.uint8) if u8 else rng.uniform(-1, 1, (B, S, S, 3)).astype(np.float32)
+    as_float = raw.astype(np.float32) / 255.0 * 2.0 - 1.0 if u8 else raw
+    p = IO.draw_params(rng, B, S, S, skip=[0, 0, 1, 0, 0])
+    p[0, 2], p[1, 2] = 5.0, -5.0           # extreme angles: corners sample outside the image (zero fill)
+    p[3, 3:6] = (0.2, -0.2, 0.2)
+    p[4, 3:6] = (-0.2, 0.2, -0.2)
+    ref = IO.augment(as_float, p)
+    p8 = np.zeros((B, 8), np.float32)
+    p8[:, :7] = p
+    out = torch.zeros((B, S, S, 3), device=DEV)
+    ops.image_augment(torch.from_numpy(raw).to(DEV), out, B, S, S, torch.from_numpy(p8).to(DEV))
+    got = out.cpu().numpy()
+    assert np.abs(got - ref).max() < 2e-4, np.abs(got - ref).max()     # fp32 coordinate arithmetic, 224-pixel lever arm
+    assert np.array_equal(got[2], as_float[2])                         # skipped (VQA) sample: untouched
+    assert np.abs(got[0] - as_float[0]).mean() > 0.05                  # the others really moved

@@ -591,3 +591,68 @@ def test_validation_step_runner_returns_metrics_and_val_loss():
     assert set(out) == {"lang_loss", "action_loss", "langact_loss", "val_loss"}
     assert float(out["val_loss"]) == float(loss) and float(out["action_loss"]) == float(m["action_loss"])
     assert torch.equal(p0, model.P) and state.step == 0
+
+
+def test_non_224_inputs_are_resized_on_the_device():
+    """a7 (model_adapter.py:113-116): images that are not image_size x image_size go through `resize_with_pad` on the
+    device; the loss equals the loss on the same images resized on the host."""
+    from lap_b200 import image_tools
+    from lap_b200.train import batch_from_dict
+    tc, ref, model, b = _setup("debug_small", 2)
+    S = tc.model.image_size
+    rng = np.random.default_rng(0)
+    big = {k: rng.integers(0, 256, (2, 3 * S // 2, 2 * S, 3), dtype=np.uint8) for k in b["image"]}
+    b_dev = dict(b, image=big)
+    b_host = dict(b, image={k: image_tools.resize_with_pad(v, S, S) for k, v in big.items()})
+    o1, a1, e1 = batch_from_dict(b_dev)
+    o2, a2, e2 = batch_from_dict(b_host)
+    l_dev, _ = model.compute_loss(0, o1, a1, noise=e1["noise"], time=e1["time"])
+    l_host, _ = model.compute_loss(0, o2, a2, noise=e2["noise"], time=e2["time"])
+    assert abs(l_dev.item() - l_host.item()) < 2e-3 * abs(l_host.item())   # a few pixels may round one uint8 level apart
+
+
+def test_training_with_image_augmentation():
+    """N4 (model_adapter.py:118-151; on by default in the `lap` config): with explicit augmentation parameters the loss
+    equals the loss on images augmented by the numpy statement; a whole train step with the augmentation drawn from the
+    rng runs through the CUDA-graph path, is reproducible per (rng, step) and differs from the un-augmented step."""
+    import dataclasses
+    from oracle import image_oracle as IO
+    from lap_b200.model import LAP
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+    tc0 = get_config("debug_small")
+    tc = dataclasses.replace(tc0, model=dataclasses.replace(tc0.model, enable_image_augmentation=True))
+    ref = P.init_reference_params(tc.model, 7, reference_zero_init=False)
+    model = LAP(tc.model, init=False)
+    model.load_params(ref)
+    b = synthetic_batch(tc.model, 3, step=11)
+    S = tc.model.image_size
+    rng = np.random.default_rng(1)
+    aug = {k: IO.draw_params(rng, 3, S, S) for k in b["image"]}
+    obs, actions, extra = batch_from_dict(b)
+    l_aug, m = model.compute_loss(0, obs, actions, train=True, noise=extra["noise"], time=extra["time"], aug=aug,
+                                  return_augmented_images=True)
+    for k in b["image"]:
+        assert rel_err(m["augmented_images"][k], IO.augment(b["image"][k], aug[k])) < 1e-4
+    b_pre = dict(b, image={k: IO.augment(v, aug[k]) for k, v in b["image"].items()})
+    o2, a2, e2 = batch_from_dict(b_pre)
+    l_pre, _ = model.compute_loss(0, o2, a2, noise=e2["noise"], time=e2["time"])
+    l_plain, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    assert abs(l_aug.item() - l_pre.item()) < 1e-3 * abs(l_pre.item())
+    assert abs(l_aug.item() - l_plain.item()) > 1e-4 * abs(l_plain.item())
+    # eval mode never augments
+    l_eval, _ = model.compute_loss(0, obs, actions, train=False, noise=extra["noise"], time=extra["time"], aug=aug)
+    assert l_eval.item() == l_plain.item()
+    # full train steps: augmentation drawn from (rng, step), through eager steps and the captured graphs
+    def run(seed):
+        mm = LAP(tc.model, init=False)
+        mm.load_params(ref)
+        state = init_train_state(tc, model=mm)
+        runner = TrainingStepRunner(tc)
+        out = []
+        for s in range(4):
+            state, info = runner(seed, state, batch_from_dict(synthetic_batch(tc.model, 2, step=30 + s)))
+            out.append(float(info["loss"]))
+        return out
+    r1, r2, r3 = run(0), run(0), run(1)
+    assert all(np.isfinite(r1)) and all(abs(x - y) < 1e-4 * abs(x) for x, y in zip(r1, r2))
+    assert abs(r1[0] - r3[0]) > 1e-6 * abs(r1[0])

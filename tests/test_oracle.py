@@ -343,3 +343,41 @@ def test_sample_tokens_temperature_is_gumbel_argmax(tiny):
     toks2, logits2 = O.sample_tokens(ref, cfg, obs, max_decoding_steps=K, bf16=False, return_logits=True)
     assert rel_err(logits[:, 0], logits2[:, 0]) < 1e-6           # the first logits do not depend on what is sampled
     assert rel_err(logits[:, 1], logits2[:, 1]) > 1e-3           # later ones do
+
+
+def test_image_augmentation_statement_properties():
+    """oracle/image_oracle.py (model_adapter.py:118-151 with explicit parameters): a skipped (VQA) sample is untouched; a
+    constant image stays constant under the geometric part (away from the zero-filled corners) and moves by exactly the
+    brightness / contrast formula; the output stays in [-1, 1]; a rotation by +a then reading the centre pixel is a no-op."""
+    from oracle import image_oracle as IO
+    rng = np.random.default_rng(0)
+    img = rng.uniform(-1, 1, (3, 32, 32, 3)).astype(np.float32)
+    p = IO.draw_params(rng, 3, 32, 32, skip=[0, 1, 0])
+    out = IO.augment(img, p)
+    assert out.shape == img.shape and np.array_equal(out[1], img[1]) and np.abs(out).max() <= 1.0
+    const = np.full((1, 32, 32, 3), 0.2, np.float32)
+    q = np.array([[0.5, 0.7, 3.0, 0.1, -0.1, 0.2, 0]], np.float32)
+    v = 0.2 * 0.5 + 0.5
+    v = v * (1 - 0.1) + 0.1
+    v = (v - 0.5) * (1 - 0.1) + 0.5
+    assert np.allclose(IO.augment(const, q)[0, 8:24, 8:24], v * 2 - 1, atol=1e-6)   # grey: saturation is a no-op
+    z = np.array([[0.0, 0.0, 0.0, 0, 0, 0, 0]], np.float32)                        # crop at (0, 0), no rotation / jitter
+    zo = IO.augment(img[:1], z)[0]
+    # pure zoom: output pixel (y, x) reads ((y + .5) * 30/32 - .5, ...): pixel (0, 0) reads (-1/32, -1/32) -> corner weight
+    w = 1 - 1 / 32
+    assert np.allclose(zo[0, 0], (img[0, 0, 0] * 0.5 + 0.5) * w * w * 2 - 1, atol=1e-6)
+
+
+def test_resize_plan_is_the_sparse_form_of_the_resize_matrices():
+    from lap_b200 import image_tools as it
+    for (h, w) in ((480, 640), (100, 150), (224, 300)):
+        plan = it.resize_plan(h, w, 224, 224)
+        for dense, start, vals, taps in ((it._weights(h, plan["rh"], True), plan["ystart"], plan["yw"], plan["ytaps"]),
+                                        (it._weights(w, plan["rw"], True), plan["xstart"], plan["xw"], plan["xtaps"])):
+            rec = np.zeros_like(dense)
+            for p in range(dense.shape[0]):
+                for t in range(taps):
+                    if start[p] + t < dense.shape[1]:
+                        rec[p, start[p] + t] += vals[p, t]
+            assert np.array_equal(rec, dense)
+        assert plan["ph0"] * 2 + plan["rh"] in (224, 223) and plan["pw0"] * 2 + plan["rw"] in (224, 223)
