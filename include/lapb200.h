@@ -44,7 +44,9 @@ enum {
   LAPB_EPI_GEGLU = 4,         /* dual-B: C=bf16(gelu(g)*u), C2[:, n]=g, C2[:, n+N]=u        lora.py:124-142  */
   LAPB_EPI_QSCALE = 5,        /* as NONE(+bias); columns < q_cols are divided by q_div      flax MHA q/sqrt(d) */
   LAPB_EPI_GEGLU_BWD = 6,     /* acc = dAct; C2 = [g|u] in, [dg|du] out (in place); C = act (recomputed)   lora.py:124-142 bwd */
-  LAPB_EPI_GELU_BWD = 7       /* C = bf16(acc) * gelu'(C2)                                   siglip.py:71 bwd */
+  LAPB_EPI_GELU_BWD = 7,      /* C = bf16(acc) * gelu'(C2)                                   siglip.py:71 bwd */
+  LAPB_EPI_SOFTMAX_BWD = 8    /* acc = dP; C = dS = C2 o (bf16(acc) - bias[batch*M + row]): C2 = P, bias = rowsum(dO o O)
+                                 (lapb200_rowdot), batch = batch_o index * batch_i + batch_i index      gemma.py:261 bwd */
 };
 
 typedef struct {
@@ -194,6 +196,13 @@ int lapb200_gemv_f32(const void* X, int64_t x_bf16, int64_t ldx, const float* W,
 int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* O, int64_t B,
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);
+
+/* delta[(bo*nbi + bi)*out_rows + out_off + r] = sum_d dO[bo, bi, r, d] * O[bo, bi, r, d] (bf16 in, fp32 out): the row
+ * term rowsum(P o dP) = dO . O of the softmax backward, consumed by LAPB_EPI_SOFTMAX_BWD.  Rows are `ldd` / `ldo` elements
+ * apart, the two batch levels `*_bs_i` / `*_bs_o` elements apart. */
+int lapb200_rowdot(const void* dO, const void* O, float* delta, int64_t rows, int64_t D, int64_t ldd, int64_t ldo,
+                   int64_t nbi, int64_t nbo, int64_t d_bs_i, int64_t d_bs_o, int64_t o_bs_i, int64_t o_bs_o, int64_t out_rows,
+                   int64_t out_off, lapb_stream_t s);
 
 /* Image side of preprocess_observation (src/lap/models/model_adapter.py:83-181), ahead of lapb200_patchify.
  * image_resize_pad: resize_with_pad (model_adapter.py:113-116 -> OP/shared/image_tools.py:11-52) of uint8 or float32

@@ -298,6 +298,35 @@ vit_softmax_fwd_kernel(bf16* __restrict__ S, int n, int ld, long total_rows, int
   }
 }
 
+// delta[(bo * nbi + bi) * out_rows + out_off + r] = sum_d dO[bo, bi, r, d] * O[bo, bi, r, d]   (fp32; warp per row)
+// — the row term of the softmax backward, dS = P o (dP - rowsum(P o dP)), with rowsum(P o dP) = dO . O: it lets the dP
+// GEMM's epilogue (LAPB_EPI_SOFTMAX_BWD) emit dS directly instead of a separate pass over P and dP.
+__global__ void __launch_bounds__(256)
+rowdot_kernel(const bf16* __restrict__ dO, const bf16* __restrict__ O, float* __restrict__ delta, int rows, int D, long ldd,
+              long ldo, int nbi, long d_bs_i, long d_bs_o, long o_bs_i, long o_bs_o, long out_rows, long out_off,
+              long total_rows) {
+  const long gr = (long)blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (gr >= total_rows) return;
+  const int lane = threadIdx.x & 31;
+  const int r = (int)(gr % rows);
+  const long batch = gr / rows;
+  const long bi = batch % nbi, bo = batch / nbi;
+  const bf16* a = dO + bo * d_bs_o + bi * d_bs_i + (long)r * ldd;
+  const bf16* b = O + bo * o_bs_o + bi * o_bs_i + (long)r * ldo;
+  float acc = 0.f;
+  for (int c = lane * 8; c < D; c += 256) {
+    const uint4 ua = *reinterpret_cast<const uint4*>(a + c);
+    const uint4 ub = *reinterpret_cast<const uint4*>(b + c);
+    float2 x, y;
+    x = unpack_bf16x2(ua.x); y = unpack_bf16x2(ub.x); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(ua.y); y = unpack_bf16x2(ub.y); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(ua.z); y = unpack_bf16x2(ub.z); acc += x.x * y.x + x.y * y.y;
+    x = unpack_bf16x2(ua.w); y = unpack_bf16x2(ub.w); acc += x.x * y.x + x.y * y.y;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) delta[batch * out_rows + out_off + r] = acc;
+}
+
 }  // namespace lapb
 
 using namespace lapb;
@@ -320,6 +349,19 @@ int lapb200_mask_build(const uint8_t* pm, const uint8_t* par, const uint8_t* pma
   mask_build_kernel<<<dim3((unsigned)B, (unsigned)chunks), 256, smem, STREAM(s)>>>(
       pm, par, pma, sm, sar, bits, positions, (int)P, (int)A, (int)W32, (int)row_begin, (int)infer_rows);
   LAPB_LAUNCH_OK("mask_build");
+  return 0;
+}
+
+int lapb200_rowdot(const void* dO, const void* O, float* delta, int64_t rows, int64_t D, int64_t ldd, int64_t ldo,
+                   int64_t nbi, int64_t nbo, int64_t d_bs_i, int64_t d_bs_o, int64_t o_bs_i, int64_t o_bs_o, int64_t out_rows,
+                   int64_t out_off, lapb_stream_t s) {
+  LAPB_REQUIRE(D % 8 == 0 && ldd % 8 == 0 && ldo % 8 == 0 && d_bs_i % 8 == 0 && d_bs_o % 8 == 0 && o_bs_i % 8 == 0 &&
+               o_bs_o % 8 == 0, "rowdot: D, leading dimensions and batch strides must be multiples of 8 elements");
+  const long total = rows * nbi * nbo;
+  if (total == 0) return 0;
+  rowdot_kernel<<<cdiv(total, 8), 256, 0, STREAM(s)>>>((const bf16*)dO, (const bf16*)O, delta, (int)rows, (int)D, ldd, ldo,
+                                                       (int)nbi, d_bs_i, d_bs_o, o_bs_i, o_bs_o, out_rows, out_off, total);
+  LAPB_LAUNCH_OK("rowdot");
   return 0;
 }
 

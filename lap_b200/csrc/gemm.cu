@@ -261,7 +261,7 @@ __device__ __forceinline__ void staged_load_bf16(uint8_t* stg, int lane, const _
 // One 32-row x 32-column chunk of one epilogue warp (bf16 outputs).  row0 = first row of the warp, col0 = first column.
 template <bool DUAL>
 __device__ __forceinline__ void epilogue_chunk_bf16(const GemmKArgs& a, uint8_t* stg, int lane, long row0, int col0,
-                                                    long c_boff, long r_boff, const uint32_t (&r)[32],
+                                                    long c_boff, long r_boff, long batch, const uint32_t (&r)[32],
                                                     const uint32_t (&r2)[32]) {
   const int rows_valid = (int)min(32L, (long)a.M - row0);
   const int cols_valid = min(32, a.N - col0);
@@ -290,7 +290,7 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const GemmKArgs& a, uint8_t*
   float x[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(r[j]);
-  if (a.bias) {
+  if (a.bias && a.epi != LAPB_EPI_SOFTMAX_BWD) {
     // flax Dense(dtype=bf16): y = bf16(bf16(acc) + bf16(bias))
 #pragma unroll
     for (int v = 0; v < 4; ++v) {
@@ -359,6 +359,15 @@ __device__ __forceinline__ void epilogue_chunk_bf16(const GemmKArgs& a, uint8_t*
       staged_load_bf16(stg, lane, a.C2 + c_boff + row0 * a.ldc2 + col0, a.ldc2, rows_valid, cols_valid, pre);
 #pragma unroll
       for (int j = 0; j < 32; ++j) x[j] = bf16r(x[j]) * gelu_tanh_grad(pre[j]);
+      break;
+    }
+    case LAPB_EPI_SOFTMAX_BWD: {
+      // acc = dP = dO V^T (rounded to bf16 like the stored cotangent); dS = P o (dP - delta[row]), delta = rowsum(dO o O)
+      float pp[32];
+      staged_load_bf16(stg, lane, a.C2 + c_boff + row0 * a.ldc2 + col0, a.ldc2, rows_valid, cols_valid, pp);
+      const float dl = (lane < rows_valid) ? a.bias[batch * a.M + row0 + lane] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) x[j] = pp[j] * (bf16r(x[j]) - dl);
       break;
     }
     case LAPB_EPI_GEGLU_BWD: {
@@ -581,7 +590,7 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         if (has_resid && rows_valid_w > 0 && cc + 1 < CH_PER_WARP)
           staged_prefetch(lane, a.resid + r_boff + row0w * a.ldr + col0 + 32, a.ldr, rows_valid_w, min(32, a.N - col0 - 32));
         if (!a.c_fp32) {
-          epilogue_chunk_bf16<DUAL>(a, stg, lane, row - lane, col0, c_boff, r_boff, r, r2);
+          epilogue_chunk_bf16<DUAL>(a, stg, lane, row - lane, col0, c_boff, r_boff, (long)bo * a.batch_i + bi, r, r2);
         } else if (a.k_splits > 1) {
           // split-K partial sums: transpose 32x16 fp32 halves through the staging buffer so that each
           // red.global.add.v4.f32 covers 8 rows x 64 contiguous bytes (C was zeroed by the launcher)
@@ -739,6 +748,9 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
     LAPB_REQUIRE(p->gate != nullptr && p->gate_rows > 0 && p->ldg % 8 == 0, "gemm: gated epilogue needs gate");
   if (p->epi == LAPB_EPI_GEGLU_BWD || p->epi == LAPB_EPI_GELU_BWD)
     LAPB_REQUIRE(p->C2 != nullptr && p->ldc2 % 8 == 0 && !p->c_fp32, "gemm: activation-backward epilogue needs bf16 C and C2");
+  if (p->epi == LAPB_EPI_SOFTMAX_BWD)
+    LAPB_REQUIRE(p->C2 != nullptr && p->ldc2 % 8 == 0 && !p->c_fp32 && p->bias != nullptr,
+                 "gemm: softmax-backward epilogue needs bf16 C, P in C2 and the row vector delta in bias");
 
   int bi = p->batch_i > 0 ? p->batch_i : 1, bo = p->batch_o > 0 ? p->batch_o : 1;
   int BN;

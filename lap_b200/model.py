@@ -100,6 +100,8 @@ class LAP:
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
         self.use_fused_vit_attention = os.environ.get("LAPB_FUSED_VIT", "1") != "0"  # K2 (SigLIP, head_dim 72)
+        # softmax backward folded into the dP GEMM's epilogue (row term from lapb200_rowdot); 0 = separate softmax_bwd pass
+        self.fuse_softmax_bwd = os.environ.get("LAPB_FUSED_SOFTMAX_BWD", "1") != "0"
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
         self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
         # K10c: the 16-CTA cluster variant reads TILE-MAJOR packed copies of the expert weights and of the prefix cache
@@ -503,12 +505,19 @@ class LAP:
             qf, dqf, dof = qkv.view(-1), dqkv.view(-1), do.view(-1)
             bs_qkv, bs_o, bs_p = (hd, Np * 3 * W), (hd, Np * W), (Np * Np, nh * Np * Np)
             # dP = dO V^T
-            ops.gemm(dof, qf[2 * W:], dP, M=Np, N=Np, K=hd, lda=W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
-                     a_bs=bs_o, b_bs=bs_qkv, c_bs=bs_p)
+            if self.fuse_softmax_bwd:  # dS straight from the dP GEMM's epilogue (see the Gemma backward)
+                delta = self.buf("img.delta", (Ni, nh, Np), F32)
+                ops.rowdot(do, o, delta, Np, hd, W, W, nbi=nh, nbo=Ni, d_bs=(hd, Np * W), o_bs=(hd, Np * W))
+                ops.gemm(dof, qf[2 * W:], dP, M=Np, N=Np, K=hd, lda=W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                         a_bs=bs_o, b_bs=bs_qkv, c_bs=bs_p, epi=ops.EPI_SOFTMAX_BWD, C2=Pm, ldc2=Np, bias=delta)
+            else:
+                ops.gemm(dof, qf[2 * W:], dP, M=Np, N=Np, K=hd, lda=W, ldb=3 * W, ldc=Np, batch_i=nh, batch_o=Ni,
+                         a_bs=bs_o, b_bs=bs_qkv, c_bs=bs_p)
             # dV = P^T dO
             ops.gemm(Pm, dof, dqf[2 * W:], M=Np, N=hd, K=Np, a_major=1, b_major=1, lda=Np, ldb=W, ldc=3 * W,
                      batch_i=nh, batch_o=Ni, a_bs=bs_p, b_bs=bs_o, c_bs=bs_qkv)
-            ops.softmax_bwd(Pm, dP, dP, Ni * nh * Np, Np)
+            if not self.fuse_softmax_bwd:
+                ops.softmax_bwd(Pm, dP, dP, Ni * nh * Np, Np)
             # dQ_pre = (dS K) / q_div
             ops.gemm(dP, qf[W:], dqf, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=3 * W, batch_i=nh, batch_o=Ni,
                      a_bs=bs_p, b_bs=bs_qkv, c_bs=bs_qkv, epi=ops.EPI_QSCALE, q_cols=hd, q_div=q_div)
@@ -941,11 +950,23 @@ class LAP:
             # ===== shared attention =====
             Pm, Q, Kc, Vc = sv("P"), sv("Q"), sv("Kc"), sv("Vc")
             bsR, bsT, bsP = (Rq * hd, 0), (Tpad * hd, 0), (Rq * Tpad, 0)
-            ops.gemm(dOc, Vc, dP, M=Rq, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=bsR, b_bs=bsT, c_bs=bsP)
+            if self.fuse_softmax_bwd:
+                # dS = P o (dP - rowsum(P o dP)) with rowsum(P o dP) = dO . O: the row term is one small kernel over
+                # (dO, O) and the dP GEMM's epilogue emits dS directly — no separate pass over P and dP
+                delta = self.buf("bwd.delta", (B, Rq), F32)
+                ops.rowdot(dOc, O0, delta, Pn * NH, hd, hd, hd, nbi=B, d_bs=(Rq * hd, 0), o_bs=(Pn * NH * hd, 0),
+                           out_rows=Rq, out_off=0)
+                ops.rowdot(dOc.view(-1)[Pn * NH * hd:], O1, delta, A * NH, hd, hd, hd, nbi=B, d_bs=(Rq * hd, 0),
+                           o_bs=(A * NH * hd, 0), out_rows=Rq, out_off=Pn * NH)
+                ops.gemm(dOc, Vc, dP, M=Rq, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=bsR, b_bs=bsT, c_bs=bsP,
+                         epi=ops.EPI_SOFTMAX_BWD, C2=Pm, ldc2=Tpad, bias=delta)
+            else:
+                ops.gemm(dOc, Vc, dP, M=Rq, N=Tpad, K=hd, ldc=Tpad, batch_i=B, a_bs=bsR, b_bs=bsT, c_bs=bsP)
             if not cfg.stop_action_to_vlm_grad:
                 ops.gemm(Pm, dOc, dVc, M=Tpad, N=hd, K=Rq, a_major=1, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B,
                          a_bs=bsP, b_bs=bsR, c_bs=bsT)
-            ops.softmax_bwd(Pm, dP, dP, B * Rq, Tpad)
+            if not self.fuse_softmax_bwd:
+                ops.softmax_bwd(Pm, dP, dP, B * Rq, Tpad)
             ops.gemm(dP, Kc, dQ, M=Rq, N=hd, K=Tpad, b_major=1, lda=Tpad, ldb=hd, ldc=hd, batch_i=B, a_bs=bsP,
                      b_bs=bsT, c_bs=bsR)
             if cfg.stop_action_to_vlm_grad:

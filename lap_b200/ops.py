@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmParams, check
 
-EPI_NONE, EPI_BIAS_GELU, EPI_RESID, EPI_GATED_RESID, EPI_GEGLU, EPI_QSCALE, EPI_GEGLU_BWD, EPI_GELU_BWD = range(8)
+EPI_NONE, EPI_BIAS_GELU, EPI_RESID, EPI_GATED_RESID, EPI_GEGLU, EPI_QSCALE, EPI_GEGLU_BWD, EPI_GELU_BWD, EPI_SOFTMAX_BWD = range(9)
 
 # launch counter: every C-ABI kernel entry increments this (bench.py reports it as gpu_launches)
 launch_count = 0
@@ -385,6 +385,12 @@ def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, str
         setattr(p, k, int(v))
     check(lib().lapb200_denoise_loop(ctypes.byref(p), _stream()), "denoise_loop")
     _count()
+
+
+def rowdot(dO, O, delta, rows, D, ldd, ldo, nbi=1, nbo=1, d_bs=(0, 0), o_bs=(0, 0), out_rows=None, out_off=0):
+    """delta[(bo*nbi + bi)*out_rows + out_off + r] = <dO[bo, bi, r, :D], O[bo, bi, r, :D]> (fp32)."""
+    call("rowdot", dO, O, delta, rows, D, ldd, ldo, nbi, nbo, d_bs[0], d_bs[1], o_bs[0], o_bs[1],
+         rows if out_rows is None else out_rows, out_off)
 
 
 def image_resize_pad(src, dst, B, Hin, Win, Hout, Wout, rh, rw, ph0, pw0, ystart, yw, ytaps, xstart, xw, xtaps):

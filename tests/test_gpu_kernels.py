@@ -584,3 +584,35 @@ def test_image_augment_matches_numpy_statement(u8):
     assert np.abs(got - ref).max() < 2e-4, np.abs(got - ref).max()     # fp32 coordinate arithmetic, 224-pixel lever arm
     assert np.array_equal(got[2], as_float[2])                         # skipped (VQA) sample: untouched
     assert np.abs(got[0] - as_float[0]).mean() > 0.05                  # the others really moved
+
+
+@pytest.mark.parametrize("Bn,R,T,hd", [(2, 1408, 704, 256), (3, 200, 192, 72)])
+def test_softmax_backward_fused_into_the_dp_gemm(Bn, R, T, hd):
+    """dS = P o (dP - rowsum(P o dP)), produced by the dP = dO V^T GEMM's epilogue (LAPB_EPI_SOFTMAX_BWD) with the row
+    term from lapb200_rowdot(dO, O) — against autograd through an fp32 softmax and against the separate softmax_bwd pass."""
+    torch.manual_seed(R + hd)
+    logits = torch.randn(Bn, R, T, device=DEV) * 2
+    logits[:, :, T - 7:] = -1e30                       # masked keys: P = 0 there
+    P = torch.softmax(logits, -1).bfloat16()
+    V = torch.randn(Bn, T, hd, device=DEV).bfloat16()
+    dO = (torch.randn(Bn, R, hd, device=DEV) * 0.1).bfloat16()
+    O = torch.bmm(P.float(), V.float()).bfloat16()
+    delta = torch.zeros(Bn, R, device=DEV)
+    ops.rowdot(dO, O, delta, R, hd, hd, hd, nbi=Bn, d_bs=(R * hd, 0), o_bs=(R * hd, 0))
+    assert rel_err(delta, (dO.float() * O.float()).sum(-1)) < 1e-5
+    dS = torch.zeros(Bn, R, T, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(dO, V, dS, M=R, N=T, K=hd, ldc=T, batch_i=Bn, a_bs=(R * hd, 0), b_bs=(T * hd, 0), c_bs=(R * T, 0),
+             epi=ops.EPI_SOFTMAX_BWD, C2=P, ldc2=T, bias=delta)
+    # separate pass (what the fused epilogue replaces)
+    dP = torch.zeros_like(dS)
+    ops.gemm(dO, V, dP, M=R, N=T, K=hd, ldc=T, batch_i=Bn, a_bs=(R * hd, 0), b_bs=(T * hd, 0), c_bs=(R * T, 0))
+    dS2 = torch.zeros_like(dS)
+    ops.softmax_bwd(P, dP, dS2, Bn * R, T)
+    # fp32 statement
+    dP32 = torch.bmm(dO.float(), V.float().transpose(1, 2))
+    p32 = P.float()
+    ref = p32 * (dP32 - (p32 * dP32).sum(-1, keepdim=True))
+    assert rel_err(dS, ref) < 8e-3, rel_err(dS, ref)
+    assert rel_err(dS2, ref) < 8e-3
+    assert rel_err(dS, dS2) < 8e-3
+    assert dS[:, :, T - 7:].abs().max() == 0

@@ -17,7 +17,9 @@ torch.cuda.synchronize()
 log = []
 orig = ops.gemm
 def logged(A, B, C, **kw):
-    log.append({k: kw.get(k, d) for k, d in dict(M=0, N=0, K=0, a_major=0, b_major=0, batch_i=1, batch_o=1, epi=0).items()} | {"f32": C.dtype == torch.float32})
+    log.append({k: kw.get(k, d) for k, d in dict(M=0, N=0, K=0, a_major=0, b_major=0, batch_i=1, batch_o=1, epi=0).items()}
+               | {"f32": C.dtype == torch.float32, "accumulate": bool(kw.get("accumulate", False)),
+                  "c2": kw.get("C2") is not None})
     return orig(A, B, C, **kw)
 ops.gemm = logged
 import lap_b200.model as mm
