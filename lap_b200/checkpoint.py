@@ -135,5 +135,24 @@ def load_served_params(directory, model, step: int | None = None) -> int:
     step = latest_step(directory) if step is None else int(step)
     if step is None:
         raise FileNotFoundError(f"no checkpoint under {directory}")
-    model.load_params(load_tree(directory / str(step) / "params.safetensors"))
+    d = directory / str(step)
+    if (d / "params.safetensors").exists():
+        model.load_params(load_tree(d / "params.safetensors"))
+    elif (d / "params").is_dir():
+        # a checkpoint written by the REFERENCE (Orbax `params` item, third_party/openpi/src/openpi/models/model.py:286-332)
+        from . import orbax_io
+        model.load_params(orbax_io.read_params(d / "params"))
+    else:
+        raise FileNotFoundError(f"{d} holds neither params.safetensors nor an Orbax `params` item")
     return step
+
+
+def export_orbax_params(directory, model, step: int, *, ema_flat: torch.Tensor | None = None, value_suffix: bool = True) -> Path:
+    """Write `<directory>/<step>/params` as an Orbax item in the plain-directory layout (orbax_io.write_params) so that the
+    reference's `restore_params` / `serve_policy.py` can load weights trained here.  `ema_flat` = the EMA buffer when the
+    run used EMA (`_split_params`, checkpoints.py:529-538: the served `params` item holds the EMA weights)."""
+    from . import orbax_io
+    out = Path(directory) / str(int(step)) / "params"
+    tree = model.params_reference(ema_flat if ema_flat is not None else None)
+    orbax_io.write_params(out, {k: v.numpy() for k, v in tree.items()}, value_suffix=value_suffix)
+    return out

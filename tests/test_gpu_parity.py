@@ -656,3 +656,25 @@ def test_training_with_image_augmentation():
     r1, r2, r3 = run(0), run(0), run(1)
     assert all(np.isfinite(r1)) and all(abs(x - y) < 1e-4 * abs(x) for x, y in zip(r1, r2))
     assert abs(r1[0] - r3[0]) > 1e-6 * abs(r1[0])
+
+
+def test_orbax_params_item_round_trips_through_the_engine(tmp_path):
+    """N1: weights exported as an Orbax `params` item (plain-directory layout, nnx `value` suffix like the reference's
+    training loop writes) come back bit-exactly through `load_served_params` and through the reference-style
+    `config.model.load(restore_params(dir))`; the EMA buffer is what gets served when EMA is on."""
+    from lap_b200 import checkpoint as C, orbax_io
+    from lap_b200.model import LAP
+    from lap_b200.train import init_train_state
+    tc, ref, model, _ = _setup("debug_tiny", 2)
+    state = init_train_state(tc, model=model)
+    state.ema_params.mul_(0.5)  # make the EMA distinguishable from the raw weights
+    out = C.export_orbax_params(tmp_path, model, 7, ema_flat=state.ema_params)
+    assert out == tmp_path / "7" / "params" and (out / "_METADATA").exists()
+    served = LAP(tc.model, seed=99)
+    assert C.load_served_params(tmp_path, served, step=7) == 7
+    want = model.params_reference(state.ema_params)
+    got = served.params_reference()
+    assert all(torch.equal(got[k], want[k]) for k in want)
+    m2 = tc.model.load(orbax_io.read_params(out))   # OP/models/model.py:233-241 + 286-332
+    got2 = m2.params_reference()
+    assert all(torch.equal(got2[k], want[k]) for k in want)
