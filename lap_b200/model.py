@@ -100,8 +100,11 @@ class LAP:
         self.use_cuda_graph = True
         self.use_fused_attention = True  # K1 fused tcgen05 attention forward (head_dim 256); False = GEMM+softmax+GEMM
         self.use_fused_vit_attention = os.environ.get("LAPB_FUSED_VIT", "1") != "0"  # K2 (SigLIP, head_dim 72)
-        # softmax backward folded into the dP GEMM's epilogue (row term from lapb200_rowdot); 0 = separate softmax_bwd pass
-        self.fuse_softmax_bwd = os.environ.get("LAPB_FUSED_SOFTMAX_BWD", "1") != "0"
+        # softmax backward folded into the dP GEMM's epilogue (row term from lapb200_rowdot).  Correct (tested) but measured
+        # SLOWER in the step (353.2 vs 346.4 ms, profiles/r02_softmax_bwd_fusion.md): the dP GEMM has K = head_dim (4 K
+        # blocks) and is epilogue-bound already, so the extra P tile per output tile costs more than the separate
+        # HBM-roofline pass it removes.  Off by default; LAPB_FUSED_SOFTMAX_BWD=1 enables it.
+        self.fuse_softmax_bwd = os.environ.get("LAPB_FUSED_SOFTMAX_BWD", "0") == "1"
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
         self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
         # K10c: the 16-CTA cluster variant reads TILE-MAJOR packed copies of the expert weights and of the prefix cache
