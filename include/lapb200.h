@@ -79,6 +79,9 @@ typedef struct {
   int32_t max_ctas; /* 0 = number of SMs */
   int32_t cta_group; /* 0 = auto, 1 = one CTA per tile, 2 = cta_group::2 pairs (256-row tiles) */
   int32_t k_splits;  /* 0 = auto (fp32-out, EPI_NONE only), 1 = off, n = force n K-splits (atomic fp32 adds) */
+  int32_t reserved0_;
+  int64_t split_stride; /* > 0 (with k_splits = n > 1): split s STORES its partial sums to C + s*split_stride elements
+                           (n deterministic slabs, summed in order by lapb200_resid_norm_fwd) instead of atomic adds */
 } lapb_gemm_t;
 
 int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream);
@@ -196,6 +199,14 @@ int lapb200_gemv_f32(const void* X, int64_t x_bf16, int64_t ldx, const float* W,
 int lapb200_decode_attn(const void* Q, const void* Kc, const void* Vc, const uint32_t* bits, void* O, int64_t B,
                         int64_t Tq, int64_t NH, int64_t HD, int64_t S_len, int64_t Tpad, int64_t W32,
                         lapb_stream_t s);
+
+/* Finalisation of a slab split-K GEMM (lapb_gemm_t.split_stride) fused with the following normalisation, used by the
+ * batch-1 prefix pass:  t = bf16(sum_s acc[s]); t = bf16(t + bf16(bias)) if bias; xout = bf16(resid + t) — the rounding
+ * points of LAPB_EPI_RESID — then y = LayerNorm(xout) (layernorm = 1: scale, nbias, eps 1e-6; siglip.py:87,98,161) or
+ * RMSNorm(xout) = xout*rstd*(1+scale) (gemma.py:112-131); y = NULL: finalisation only.  acc: [nsplit] slabs of [M, D] fp32. */
+int lapb200_resid_norm_fwd(const void* resid, const float* acc, int64_t nsplit, int64_t slab_stride, const float* bias,
+                           void* xout, int64_t layernorm, const float* scale, const float* nbias, void* y, float* mean,
+                           float* rstd, int64_t M, int64_t D, lapb_stream_t s);
 
 /* delta[(bo*nbi + bi)*out_rows + out_off + r] = sum_d dO[bo, bi, r, d] * O[bo, bi, r, d] (bf16 in, fp32 out): the row
  * term rowsum(P o dP) = dO . O of the softmax backward, consumed by LAPB_EPI_SOFTMAX_BWD.  Rows are `ldd` / `ldo` elements

@@ -117,6 +117,7 @@ class GemmParams(ctypes.Structure):
         ("gate", c_vp), ("ldg", c_i64), ("gate_rows", c_i32),
         ("C2", c_vp), ("ldc2", c_i64), ("q_cols", c_i32), ("q_div", c_f32),
         ("block_n", c_i32), ("max_ctas", c_i32), ("cta_group", c_i32), ("k_splits", c_i32),
+        ("reserved0_", c_i32), ("split_stride", c_i64),
     ]
 
 

@@ -50,6 +50,11 @@ __device__ __forceinline__ float gelu_tanh_grad(float x) {
   return fmaf(x * s * (1.0f - s), dy2, s);
 }
 
+// programmatic dependent launch (griddepcontrol): no-ops unless the grid was launched with the programmatic-stream-
+// serialization attribute
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------

@@ -495,6 +495,84 @@ rmsnorm_fwd_kernel(const bf16* __restrict__ x, long ldx, const long* __restrict_
   }
 }
 
+// Finalisation of a deterministic split-K GEMM fused with the following normalisation (batch-1 inference: the
+// M = 512 / 692-row down and fc2 projections have too few output tiles for 148 SMs, so they run as k_splits slabs):
+//   t  = bf16( sum_s acc[s][row, :] )                      (slabs summed in fixed order)
+//   t  = bf16( t + bf16(bias) )                            (flax Dense bias, SigLIP only)
+//   x2 = bf16( resid + t )             -> xout             (the residual add of LAPB_EPI_RESID, same rounding points)
+//   y  = LayerNorm(x2) or RMSNorm(x2)  -> y (optional)     (the next block's pre-norm; statistics in fp32)
+// One CTA of 128 threads per row, the row stays in registers (D <= 3072).
+template <bool LN>
+__global__ void __launch_bounds__(128)
+resid_norm_fwd_kernel(const bf16* __restrict__ resid, const float* __restrict__ acc, int nsplit, long slab_stride,
+                      const float* __restrict__ bias, bf16* __restrict__ xout, const float* __restrict__ scale,
+                      const float* __restrict__ nbias, bf16* __restrict__ y, float* __restrict__ mean_out,
+                      float* __restrict__ rstd_out, int D) {
+  __shared__ float red[32];
+  const long row = blockIdx.x;
+  float v[3][8];
+  float s = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int c = threadIdx.x * 8 + k * 1024;
+    if (c < D) {
+      float t[8], r[8];
+      const float* ap = acc + row * D + c;
+      ld8f(ap, t);
+      for (int sp = 1; sp < nsplit; ++sp) {
+        float u[8];
+        ld8f(ap + sp * slab_stride, u);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] += u[j];
+      }
+      ld8(resid + row * D + c, r);
+      if (bias) {
+        float b[8];
+        ld8f(bias + c, b);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) t[j] = bf16r(t[j]) + bf16r(b[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        v[k][j] = bf16r(r[j] + bf16r(t[j]));
+        s += v[k][j];
+        s2 += v[k][j] * v[k][j];
+      }
+      st8(xout + row * D + c, v[k]);
+    }
+  }
+  if (y == nullptr) return;
+  s2 = block_sum(s2, red);
+  float mean = 0.f, rstd;
+  if (LN) {
+    s = block_sum(s, red);
+    mean = s / D;
+    rstd = rsqrtf(fmaxf(s2 / D - mean * mean, 0.f) + 1e-6f);
+    if (threadIdx.x == 0 && mean_out) mean_out[row] = mean;
+  } else {
+    rstd = rsqrtf(s2 / D + 1e-6f);
+  }
+  if (threadIdx.x == 0 && rstd_out) rstd_out[row] = rstd;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    const int c = threadIdx.x * 8 + k * 1024;
+    if (c < D) {
+      float sc[8], o[8];
+      ld8f(scale + c, sc);
+      if (LN) {
+        float bi[8];
+        ld8f(nbias + c, bi);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[k][j] - mean) * (rstd * sc[j]) + bi[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o[j] = (v[k][j] * rstd) * (1.0f + sc[j]);
+      }
+      st8(y + row * D + c, o);
+    }
+  }
+}
+
 // Warp-per-row forward norms for contiguous rows of width <= 2048 (the training shapes: 22144 x 2048 RMSNorm, 16384 x 1152
 // LayerNorm).  A lane keeps its share of the row (<= 8 vectors of 16 bytes) in registers, so every element crosses HBM
 // once each way; the only synchronisation is the warp shuffle of the row statistics.  The CTA-per-row kernels above
@@ -960,6 +1038,22 @@ int lapb200_layernorm_bwd(const void* dy, const void* x, const float* scale, con
   if (M <= 0) return 0;
   if (int rc = launch_norm_bwd<true>(a, STREAM(s))) return rc;
   LAPB_LAUNCH_OK("layernorm_bwd");
+  return 0;
+}
+
+int lapb200_resid_norm_fwd(const void* resid, const float* acc, int64_t nsplit, int64_t slab_stride, const float* bias,
+                           void* xout, int64_t layernorm, const float* scale, const float* nbias, void* y, float* mean,
+                           float* rstd, int64_t M, int64_t D, lapb_stream_t s) {
+  LAPB_REQUIRE(D % 8 == 0 && D <= 3072 && nsplit >= 1, "resid_norm_fwd: D must be a multiple of 8 and <= 3072");
+  LAPB_REQUIRE(y == nullptr || (scale != nullptr && (!layernorm || nbias != nullptr)), "resid_norm_fwd: norm parameters missing");
+  if (M <= 0) return 0;
+  if (layernorm)
+    resid_norm_fwd_kernel<true><<<(unsigned)M, 128, 0, STREAM(s)>>>((const bf16*)resid, acc, (int)nsplit, slab_stride, bias,
+                                                                    (bf16*)xout, scale, nbias, (bf16*)y, mean, rstd, (int)D);
+  else
+    resid_norm_fwd_kernel<false><<<(unsigned)M, 128, 0, STREAM(s)>>>((const bf16*)resid, acc, (int)nsplit, slab_stride, bias,
+                                                                     (bf16*)xout, scale, nbias, (bf16*)y, mean, rstd, (int)D);
+  LAPB_LAUNCH_OK("resid_norm_fwd");
   return 0;
 }
 

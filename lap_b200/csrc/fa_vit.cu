@@ -11,8 +11,8 @@
 // covers dims [64, 128), of which [72, 128) are out of bounds and arrive as ZEROS from the TMA unit — the padding lives in
 // shared memory only, HBM keeps [tokens, 3, heads, 72].  S needs 5 K-steps of 16 dims (64 + 16), P V uses N = 128 columns
 // of which 72 are stored.  Keys are processed 256 at a time (the whole row for 224 px = 256 patches; 3 chunks for 384 px =
-// 729 patches); K and V of a chunk share ONE shared-memory buffer (V is fetched into it once the S MMAs have retired, while
-// the softmax warps work), so Q 32 KB + K/V 64 KB + P 64 KB fit one SM.
+// 729 patches).  P is written OVER the K chunk (K is dead once S is in TMEM), so Q 32 KB + K/P 64 KB + V 64 KB fit one SM and
+// Q, K and V are all requested at kernel start.
 //
 // Softmax: four warpgroups, thread == query row == TMEM lane, warpgroup w owns keys [64w, 64w + 64) of a chunk == one P
 // sub-tile [128 x 64] written as 128-byte swizzled rows (A operand of P V) and TMA-stored to HBM for the backward pass.
@@ -38,8 +38,9 @@ constexpr int FV_SOFT = 128 * FV_WG;
 constexpr int FV_THREADS = FV_SOFT + 96;
 constexpr int FV_Q_BYTES = FV_QT * FV_HP * 2;   // 32 KB: 2 atoms [128 rows x 128 B]
 constexpr int FV_KV_BYTES = FV_KC * FV_HP * 2;  // 64 KB: 2 atoms [256 keys x 128 B]
-constexpr int FV_P_BYTES = FV_QT * FV_KC * 2;   // 64 KB: 4 sub-tiles [128 rows x 128 B]
-constexpr int FV_SMEM = FV_Q_BYTES + FV_KV_BYTES + FV_P_BYTES + 1024 + 512 + FV_WG * 128 * 8;
+constexpr int FV_P_BYTES = FV_QT * FV_KC * 2;   // 64 KB: 4 sub-tiles [128 rows x 128 B] — aliases the K chunk
+static_assert(FV_P_BYTES <= FV_KV_BYTES, "P must fit over the K chunk");
+constexpr int FV_SMEM = FV_Q_BYTES + 2 * FV_KV_BYTES + 1024 + 512 + FV_WG * 128 * 8;
 static_assert(FV_SMEM <= 227 * 1024, "fa_vit: shared memory");
 
 struct FvArgs {
@@ -66,19 +67,22 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* Qs = smem;
-  uint8_t* KVs = Qs + FV_Q_BYTES;
-  uint8_t* Ps = KVs + FV_KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(Ps + FV_P_BYTES);
+  uint8_t* Ks = Qs + FV_Q_BYTES;
+  uint8_t* Ps = Ks;               // P overwrites the K chunk once S is in TMEM
+  uint8_t* Vs = Ks + FV_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + FV_KV_BYTES);
   uint64_t* q_full = bars;        // Q tile landed
-  uint64_t* kv_full = bars + 1;   // a K or V chunk landed in the shared K/V buffer (uses alternate parity)
-  uint64_t* kv_free = bars + 2;   // the MMAs reading the K/V buffer have retired
+  uint64_t* k_full = bars + 1;    // a K chunk landed
+  uint64_t* k_free = bars + 2;    // the last MMAs reading the K / P buffer have retired (S in pass 1, P V in pass 2)
+  uint64_t* v_full = bars + 15;   // a V chunk landed
+  uint64_t* v_free = bars + 16;   // the P V MMAs reading the V chunk have retired
   uint64_t* s_full = bars + 3;    // S of a chunk is in TMEM
   uint64_t* s_free = bars + 4;    // every softmax thread has pulled its S values
   uint64_t* p_full = bars + 5;    // [4] P sub-tile w written
   uint64_t* pv_done = bars + 9;   // P V of a chunk retired (P buffer free)
   uint64_t* st_done = bars + 10;  // [4] the TMA store of sub-tile w has read the P buffer
   uint64_t* o_full = bars + 14;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   float* stat = reinterpret_cast<float*>(bars + 64);  // [FV_WG][128][2] exchange between the warpgroups
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -95,8 +99,10 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
   if (warp == W_MMA && lane == 0) {
     mbar_init(q_full, 1);
-    mbar_init(kv_full, 1);
-    mbar_init(kv_free, 1);
+    mbar_init(k_full, 1);
+    mbar_init(k_free, 1);
+    mbar_init(v_full, 1);
+    mbar_init(v_free, 1);
     mbar_init(s_full, 1);
     mbar_init(s_free, FV_SOFT);
     for (int i = 0; i < FV_WG; ++i) {
@@ -124,30 +130,35 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
       mbar_expect_tx(q_full, FV_Q_BYTES);
       tma_load_4d(Qs, &tmQ, q_full, 0, q0, h, img);
       tma_load_4d(Qs + FV_QT * 128, &tmQ, q_full, 64, q0, h, img);  // dims [64, 128): >= 72 arrive as zeros
-      int use = 0;  // uses of the K/V buffer so far
-      auto load_kv = [&](const CUtensorMap* tm, int j) {
-        mbar_wait(kv_free, (use & 1) ^ 1);
-        mbar_expect_tx(kv_full, FV_KV_BYTES);
-        tma_load_4d(KVs, tm, kv_full, 0, j * FV_KC, h, img);
-        tma_load_4d(KVs + FV_KC * 128, tm, kv_full, 64, j * FV_KC, h, img);
-        ++use;
+      int ku = 0;  // K loads so far
+      auto load_k = [&](int j) {
+        mbar_wait(k_free, (ku & 1) ^ 1);
+        mbar_expect_tx(k_full, FV_KV_BYTES);
+        tma_load_4d(Ks, &tmK, k_full, 0, j * FV_KC, h, img);
+        tma_load_4d(Ks + FV_KC * 128, &tmK, k_full, 64, j * FV_KC, h, img);
+        ++ku;
       };
       if (two_pass)
-        for (int j = 0; j < NCH; ++j) load_kv(&tmK, j);
+        for (int j = 0; j < NCH; ++j) load_k(j);
       for (int j = 0; j < NCH; ++j) {
-        load_kv(&tmK, j);
-        load_kv(&tmV, j);
+        if (j > 0 && a.write_p)  // the TMA stores of P(j-1) must have read the buffer K(j) is about to overwrite
+          for (int w = 0; w < FV_WG; ++w) mbar_wait(&st_done[w], (j - 1) & 1);
+        load_k(j);
+        mbar_wait(v_free, (j & 1) ^ 1);
+        mbar_expect_tx(v_full, FV_KV_BYTES);
+        tma_load_4d(Vs, &tmV, v_full, 0, j * FV_KC, h, img);
+        tma_load_4d(Vs + FV_KC * 128, &tmV, v_full, 64, j * FV_KC, h, img);
       }
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer (whole warp; an elected lane issues) =====================
-    const uint32_t q_addr = smem_u32(Qs), kv_addr = smem_u32(KVs), p_addr = smem_u32(Ps);
+    const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs), p_addr = smem_u32(Ps);
     constexpr uint32_t idescPV = make_idesc_bf16(FV_QT, FV_HP, 0, 1);
     mbar_wait(q_full, 0);
-    int use = 0, s_use = 0;
-    auto issue_S = [&](int j) {
+    int ku = 0, s_use = 0;
+    auto issue_S = [&](int j, bool release_k) {
       const uint32_t idescS = make_idesc_bf16(FV_QT, chunk_keys(j), 0, 0);
-      mbar_wait(kv_full, use & 1);
+      mbar_wait(k_full, ku & 1);
       mbar_wait(s_free, (s_use & 1) ^ 1);
       tc_fence_after();
       // dims [0, 64): four 16-dim steps inside atom 0; dims [64, 80): one step inside atom 1 (72..79 are zero)
@@ -156,19 +167,19 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const uint32_t qo = (kk < 4) ? kk * 32 : FV_QT * 128;
         const uint32_t ko = (kk < 4) ? kk * 32 : FV_KC * 128;
         uint64_t da = make_smem_desc_sw128(q_addr + qo, 16, 1024);
-        uint64_t db = make_smem_desc_sw128(kv_addr + ko, 16, 1024);
+        uint64_t db = make_smem_desc_sw128(k_addr + ko, 16, 1024);
         umma_bf16_elect(tmem_base, da, db, idescS, kk != 0 ? 1u : 0u);
       }
-      umma_commit_elect(kv_free);
+      if (release_k) umma_commit_elect(k_free);  // pass 1: K is free again; pass 2: P goes there, freed after P V
       umma_commit_elect(s_full);
-      ++use;
+      ++ku;
       ++s_use;
     };
     if (two_pass)
-      for (int j = 0; j < NCH; ++j) issue_S(j);
+      for (int j = 0; j < NCH; ++j) issue_S(j, true);
     for (int j = 0; j < NCH; ++j) {
-      issue_S(j);
-      mbar_wait(kv_full, use & 1);  // V of chunk j
+      issue_S(j, false);
+      mbar_wait(v_full, j & 1);  // V of chunk j
       const int ns = (chunk_keys(j) + FV_KT - 1) / FV_KT;
       for (int s = 0; s < ns; ++s) {
         mbar_wait(&p_full[s], j & 1);
@@ -177,13 +188,13 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         for (int kk = 0; kk < ksteps; ++kk) {
           uint64_t da = make_smem_desc_sw128(p_addr + s * (FV_QT * 128) + kk * 32, 16, 1024);
           // V chunk: MN-major, 2 atoms of 64 dims ([256 keys x 128 B] = 32 KB apart), 16 keys per step = 2 KB
-          uint64_t db = make_smem_desc_sw128(kv_addr + (s * FV_KT + kk * 16) * 128, FV_KC * 128, 1024);
+          uint64_t db = make_smem_desc_sw128(v_addr + (s * FV_KT + kk * 16) * 128, FV_KC * 128, 1024);
           umma_bf16_elect(tmem_O, da, db, idescPV, (j | s | kk) != 0 ? 1u : 0u);
         }
       }
-      umma_commit_elect(kv_free);
+      umma_commit_elect(k_free);
+      umma_commit_elect(v_free);
       umma_commit_elect(pv_done);
-      ++use;
     }
     umma_commit_elect(o_full);
   } else if (warp < W_TMA) {
@@ -284,10 +295,8 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         uint32_t pk[32];
 #pragma unroll
         for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] / denom, sv[c + 1] / denom);
-        if (j > 0) {  // the P buffer is free once the P V of the previous chunk has retired and its store has read it
-          mbar_wait(pv_done, (j - 1) & 1);
-          if (a.write_p) mbar_wait(&st_done[wg], (j - 1) & 1);
-        }
+        // (P aliases K(j): the producer loaded K(j) only after P V(j-1) had retired and the stores of P(j-1) had read the
+        //  buffer, and s_full(j) says the S MMAs are done reading K(j) — the buffer is ours)
         // K-major, 128B-swizzled A sub-tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
         uint8_t* prow = Ps + wg * (FV_QT * 128) + r * 128;
 #pragma unroll
@@ -308,12 +317,13 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
       }
     }
-    // ---- epilogue: O (fp32, TMEM) -> bf16; warpgroup 0 stores the hd valid columns of its row ----
+    // ---- epilogue: O (fp32, TMEM) -> bf16 rows of hd valid columns ----
     mbar_wait(o_full, 0);
     tc_fence_after();
-    if (wg == 0) {
+    if (wg * 32 < a.hd) {  // warpgroup g stores columns [32 g, 32 g + 32) of its row
       bf16* orow = a.O + ((long)img * a.Np + qrow) * a.ldo + (long)h * a.hd;
-      for (int c0 = 0; c0 < a.hd; c0 += 32) {
+      {
+        const int c0 = wg * 32;
         uint32_t o[32];
         tmem_ld_32x32(tmem_O + lane_base + c0, o);
         tmem_ld_wait();

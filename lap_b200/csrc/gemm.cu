@@ -45,6 +45,7 @@ struct GemmKArgs {
   float q_div;
   int a_bi, a_bo, b_bi, b_bo;  // 1 if the operand really has that batch dimension, 0 = broadcast
   int k_splits, kb_per_split;  // split-K (fp32 atomic-add epilogue) for output-starved wgrads
+  long split_stride;           // > 0: split s STORES its partial sums to C + s * split_stride (deterministic slabs)
 };
 
 template <int BN, bool DUAL, int CG>
@@ -452,6 +453,11 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   if (CG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // Programmatic dependent launch (LAPB_PDL=1): the prologue above touched nothing the preceding kernel writes, so with
+  // the launch attribute set this grid is scheduled while its predecessor drains; `wait` blocks until the predecessor has
+  // completed and flushed, `launch_dependents` lets the NEXT kernel's launch begin.  Both are no-ops in a normal launch.
+  pdl_wait();
+  pdl_launch_dependents();
 
   if (warp == 0) {
     // ===================== TMA producer (every CTA stages its own A rows and its share of B) =====================
@@ -611,9 +617,13 @@ gemm_bf16_tcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const int col = col0 + hf * 16 + cq * 4;
                 if (rr < rows_valid && col < a.N) {
                   float4 v4 = *reinterpret_cast<const float4*>(stg + stg_off(rr, cq));
-                  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cbase + (long)rr * a.ldc + hf * 16 + cq * 4),
-                               "f"(v4.x), "f"(v4.y), "f"(v4.z), "f"(v4.w)
-                               : "memory");
+                  float* dst = cbase + (long)rr * a.ldc + hf * 16 + cq * 4;
+                  if (a.split_stride > 0)  // deterministic: every split owns a slab, the consumer sums them in order
+                    *reinterpret_cast<float4*>(dst + (long)(kb0 / a.kb_per_split) * a.split_stride) = v4;
+                  else
+                    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v4.x), "f"(v4.y), "f"(v4.z),
+                                 "f"(v4.w)
+                                 : "memory");
                 }
               }
               __syncwarp();
@@ -708,13 +718,18 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   cfg.blockDim = dim3(GEMM_THREADS);
   cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CG;
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled()) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
   LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, ka));
   return 0;
 }
@@ -818,6 +833,9 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
   // cut along K into units that add their partial sums atomically.
   ka.k_splits = 1;
   ka.kb_per_split = ka.num_k;
+  ka.split_stride = 0;
+  LAPB_REQUIRE(p->split_stride <= 0 || (p->c_fp32 && p->k_splits > 1 && p->epi == LAPB_EPI_NONE && !p->bias && bi * bo == 1),
+               "gemm: split_stride (slab split-K) needs fp32 C, k_splits > 1, no epilogue, no batch");
   if (p->c_fp32 && p->epi == LAPB_EPI_NONE && !p->bias && bi * bo == 1 && p->k_splits != 1) {
     const long slots = max_ctas / CG;
     int best = 1;
@@ -837,9 +855,13 @@ extern "C" int lapb200_gemm_bf16(const lapb_gemm_t* p, lapb_stream_t stream_) {
     if (best > 1) {
       ka.kb_per_split = cdiv(ka.num_k, best);
       ka.k_splits = cdiv(ka.num_k, ka.kb_per_split);
-      if (!p->accumulate)
+      if (p->split_stride > 0)
+        LAPB_REQUIRE(ka.k_splits == best && p->split_stride % 4 == 0,
+                     "gemm: split_stride needs exactly k_splits non-empty splits (K = %d, k_splits = %d)", p->K, best);
+      if (!p->accumulate && p->split_stride <= 0)
         LAPB_CUDA_OK(cudaMemset2DAsync(p->C, (size_t)p->ldc * 4, 0, (size_t)p->N * 4, (size_t)p->M, stream));
       total *= ka.k_splits;
+      ka.split_stride = p->split_stride > 0 ? p->split_stride : 0;
     }
   }
   long want = total * CG;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 namespace lapb {
 
@@ -41,5 +42,16 @@ inline int set_error(int code, const char* fmt, ...) {
 int num_sms();  // cached SM count of the current device (api.cu)
 
 inline unsigned int cdiv(long a, long b) { return (unsigned int)((a + b - 1) / b); }
+
+// LAPB_PDL=1: kernels that carry griddepcontrol.wait are launched with the programmatic-stream-serialization attribute
+// (their prologue overlaps the tail of the preceding kernel).  Read once per process.
+inline bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("LAPB_PDL");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 }  // namespace lapb

@@ -105,6 +105,8 @@ class LAP:
         # blocks) and is epilogue-bound already, so the extra P tile per output tile costs more than the separate
         # HBM-roofline pass it removes.  Off by default; LAPB_FUSED_SOFTMAX_BWD=1 enables it.
         self.fuse_softmax_bwd = os.environ.get("LAPB_FUSED_SOFTMAX_BWD", "0") == "1"
+        # batch-1 prefix pass: deterministic split-K slabs for the down / fc2 projections (tools/gemm_small_m.py)
+        self.use_small_m_split_k = os.environ.get("LAPB_SMALL_M_SPLIT_K", "1") != "0"
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
         self.use_denoise_megakernel = True  # K10 persistent Euler-loop kernel at batch 1; False = one kernel per op
         # K10c: the 16-CTA cluster variant reads TILE-MAJOR packed copies of the expert weights and of the prefix cache
@@ -226,6 +228,17 @@ class LAP:
     # ------------------------------------------------------------------------------------------
     # input staging (host -> device); masks are tiny and are assembled on the host
     # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _slab_splits(K: int, want: int) -> int:
+        """Number of K-splits (<= want) for a slab split-K GEMM such that every split owns at least one 64-wide K block
+        and no split is empty (the kernel requires exactly k_splits slabs); 0 if the problem is too shallow to split."""
+        nk = -(-K // 64)
+        for ks in range(want, 1, -1):
+            per = -(-nk // ks)
+            if per >= 8 and -(-nk // per) == ks:
+                return ks
+        return 0
+
     def _resize_plan(self, H: int, W: int) -> dict:
         """Device-resident filter of `resize_with_pad` for one input resolution (built once, image_tools.resize_plan)."""
         plan = self._resize_plans.get((H, W))
@@ -406,10 +419,21 @@ class LAP:
         ops.sgemm(patches, self.p("img.patch_w"), x, Ms, W, pk, pk, 1, pk, 1, ldc=W, bias=self.p("img.patch_b"),
                   table=self.p("img.pos"), table_rows=Np)
         q_div = _bf16_round(math.sqrt(hd))
+        # batch-1 inference: fc2 (M = 512 rows, K = 4304) has 36 output tiles for 148 SMs -> deterministic split-K slabs,
+        # summed (+ bias + residual, same rounding points) inside the NEXT LayerNorm kernel (ops.resid_norm_fwd)
+        ks2 = self._slab_splits(F, 4) if (not save and Ms <= 1024 and self.use_small_m_split_k) else 0
+        acc2 = self.buf("img.acc2", (max(ks2, 1), Ms, W), F32) if ks2 else None
+        pending = None  # (residual x1, bias) of an fc2 whose slabs still wait in acc2
         for l in range(s.depth):
             y0 = self.buf(f"img.y0.{l}", (Ms, W))
             mean0, rstd0 = self.buf(f"img.mean0.{l}", (Ms,), F32), self.buf(f"img.rstd0.{l}", (Ms,), F32)
-            ops.layernorm_fwd(x, self.p("img.ln0_s", l), self.p("img.ln0_b", l), y0, mean0, rstd0, Ms, W)
+            if pending is not None:
+                x = self.buf(f"img.x.{l}", (Ms, W))
+                ops.resid_norm_fwd(pending[0], acc2, ks2, Ms * W, pending[1], x, True, self.p("img.ln0_s", l),
+                                   self.p("img.ln0_b", l), y0, mean0, rstd0, Ms, W)
+                pending = None
+            else:
+                ops.layernorm_fwd(x, self.p("img.ln0_s", l), self.p("img.ln0_b", l), y0, mean0, rstd0, Ms, W)
             qkv = self.buf(f"img.qkv.{l}", (Ms, 3 * W))
             ops.gemm(y0, self.w("img.qkv_w", l), qkv, M=Ms, N=3 * W, K=W, bias=self.p("img.qkv_b", l),
                      epi=ops.EPI_QSCALE, q_cols=W, q_div=q_div)
@@ -435,13 +459,23 @@ class LAP:
             hpre, hact = self.buf(f"img.hpre.{l}", (Ms, F)), self.buf(f"img.hact.{l}", (Ms, F))
             ops.gemm(y1, self.w("img.fc1_w", l), hact, M=Ms, N=F, K=W, bias=self.p("img.fc1_b", l),
                      epi=ops.EPI_BIAS_GELU, C2=hpre, ldc2=F)
-            x2 = self.buf(f"img.x.{l + 1}", (Ms, W))
-            ops.gemm(hact, self.w("img.fc2_w", l), x2, M=Ms, N=W, K=F, bias=self.p("img.fc2_b", l), epi=ops.EPI_RESID,
-                     resid=x1)
-            x = x2
+            if ks2:
+                ops.gemm(hact, self.w("img.fc2_w", l), acc2, M=Ms, N=W, K=F, k_splits=ks2, split_stride=Ms * W,
+                         cta_group=1, block_n=128)
+                pending = (x1, self.p("img.fc2_b", l))
+            else:
+                x2 = self.buf(f"img.x.{l + 1}", (Ms, W))
+                ops.gemm(hact, self.w("img.fc2_w", l), x2, M=Ms, N=W, K=F, bias=self.p("img.fc2_b", l), epi=ops.EPI_RESID,
+                         resid=x1)
+                x = x2
         yenc = self.buf("img.yenc", (Ms, W))
-        ops.layernorm_fwd(x, self.p("img.enc_s"), self.p("img.enc_b"), yenc, self.buf("img.mean_e", (Ms,), F32),
-                          self.buf("img.rstd_e", (Ms,), F32), Ms, W)
+        if pending is not None:
+            ops.resid_norm_fwd(pending[0], acc2, ks2, Ms * W, pending[1], self.buf(f"img.x.{s.depth}", (Ms, W)), True,
+                               self.p("img.enc_s"), self.p("img.enc_b"), yenc, self.buf("img.mean_e", (Ms,), F32),
+                               self.buf("img.rstd_e", (Ms,), F32), Ms, W)
+        else:
+            ops.layernorm_fwd(x, self.p("img.enc_s"), self.p("img.enc_b"), yenc, self.buf("img.mean_e", (Ms,), F32),
+                              self.buf("img.rstd_e", (Ms,), F32), Ms, W)
         # head Dense -> image tokens written straight into the prefix rows [b, cam*Np + t]
         ops.gemm(yenc, self.w("img.head_w"), X0, M=Np, N=D, K=W, bias=self.p("img.head_b"), batch_i=C, batch_o=B,
                  a_bs=(Np * W, C * Np * W), c_bs=(Np * D, rows_per_sample * D), ldc=D)
@@ -1297,11 +1331,22 @@ class LAP:
         Mg = B * Pn
         R = Pn * NH
         qscale = hd ** -0.5
+        # batch 1: the down projection (M = 692 rows, K = 16384) as deterministic split-K slabs over 2-CTA tiles, summed
+        # (+ residual, same rounding points) inside the next layer's RMSNorm kernel (ops.resid_norm_fwd)
+        ksd = self._slab_splits(F, 3) if (Mg <= 1024 and F >= 4096 and self.use_small_m_split_k) else 0
+        accd = self.buf("inf.accd", (max(ksd, 1), Mg, D), F32) if ksd else None
+        pending = None  # residual X1 of a down projection whose slabs still wait in accd
         for l in range(g.depth):
             Kc, Vc = cache[0][l], cache[1][l]
             h = self.buf("inf.h", (Mg, D))
             rstd = self.buf("inf.rstdp", (Mg,), F32)
-            ops.rmsnorm_fwd(X, h, rstd, Mg, D, scale=self.p("g.attn_norm_s", l))
+            if pending is not None:
+                X = self.buf(f"inf.Xp{l % 2}", (Mg, D))
+                ops.resid_norm_fwd(pending, accd, ksd, Mg * D, None, X, False, self.p("g.attn_norm_s", l), None, h, None,
+                                   rstd, Mg, D)
+                pending = None
+            else:
+                ops.rmsnorm_fwd(X, h, rstd, Mg, D, scale=self.p("g.attn_norm_s", l))
             qkv0 = self.buf("inf.qkv0", (Mg, QKV))
             ops.gemm(h, self.w("g.qkv_w", l), qkv0, M=Mg, N=QKV, K=D)
             Q = self.buf("inf.Qp", (B, Pn, NH, hd))
@@ -1327,7 +1372,15 @@ class LAP:
             ops.rmsnorm_fwd(X1, h2, rstd, Mg, D, scale=self.p("g.ffn_norm_s", l))
             act = self.buf("inf.act", (Mg, F))
             ops.gemm(h2, self.w("g.gu_w", l), act, M=Mg, N=F, K=D, epi=ops.EPI_GEGLU, C2=None)
-            X2 = self.buf(f"inf.Xp{l % 2}", (Mg, D))
-            ops.gemm(act, self.w("g.down_w", l), X2, M=Mg, N=D, K=F, epi=ops.EPI_RESID, resid=X1)
-            X = X2
+            if ksd:
+                ops.gemm(act, self.w("g.down_w", l), accd, M=Mg, N=D, K=F, k_splits=ksd, split_stride=Mg * D, cta_group=2,
+                         block_n=256)
+                pending = X1
+            else:
+                X2 = self.buf(f"inf.Xp{(l + 1) % 2}", (Mg, D))
+                ops.gemm(act, self.w("g.down_w", l), X2, M=Mg, N=D, K=F, epi=ops.EPI_RESID, resid=X1)
+                X = X2
+        if pending is not None:  # the caller wants the last layer's output: finalise without a norm
+            X = self.buf(f"inf.Xp{g.depth % 2}", (Mg, D))
+            ops.resid_norm_fwd(pending, accd, ksd, Mg * D, None, X, False, None, None, None, None, None, Mg, D)
         return X

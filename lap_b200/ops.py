@@ -82,6 +82,7 @@ def gemm(
     max_ctas: int = 0,
     cta_group: int = 0,
     k_splits: int = 0,
+    split_stride: int = 0,
 ) -> torch.Tensor:
     """C[b] = epi(A[b] @ B[b]^T). Strides are in elements; pointers are taken at the tensors' data_ptr()."""
     assert A.dtype == torch.bfloat16 and B.dtype == torch.bfloat16
@@ -118,6 +119,7 @@ def gemm(
     p.max_ctas = max_ctas if max_ctas else gemm_max_ctas
     p.cta_group = cta_group
     p.k_splits = k_splits
+    p.split_stride = split_stride
     prof = _gemm_prof
     if prof is not None:
         e0 = torch.cuda.Event(enable_timing=True)
@@ -385,6 +387,10 @@ def denoise_loop(*, ints: dict, dt: float, qscale: float, times, ptrs: dict, str
         setattr(p, k, int(v))
     check(lib().lapb200_denoise_loop(ctypes.byref(p), _stream()), "denoise_loop")
     _count()
+
+
+def resid_norm_fwd(resid, acc, nsplit, slab_stride, bias, xout, layernorm, scale, nbias, y, mean, rstd, M, D):
+    call("resid_norm_fwd", resid, acc, nsplit, slab_stride, bias, xout, bool(layernorm), scale, nbias, y, mean, rstd, M, D)
 
 
 def rowdot(dO, O, delta, rows, D, ldd, ldo, nbi=1, nbo=1, d_bs=(0, 0), o_bs=(0, 0), out_rows=None, out_off=0):

@@ -616,3 +616,49 @@ def test_softmax_backward_fused_into_the_dp_gemm(Bn, R, T, hd):
     assert rel_err(dS2, ref) < 8e-3
     assert rel_err(dS, dS2) < 8e-3
     assert dS[:, :, T - 7:].abs().max() == 0
+
+
+@pytest.mark.parametrize("M,N,K,ks,ln,cg,bn", [(692, 2048, 16384, 3, False, 2, 256), (512, 1152, 4304, 4, True, 1, 128),
+                                               (100, 256, 1024, 2, False, 1, 128)])
+def test_slab_split_k_with_fused_residual_norm(M, N, K, ks, ln, cg, bn):
+    """Batch-1 prefix pass: a small-M / long-K projection as `ks` deterministic split-K slabs (plain stores, no atomics)
+    whose sum + bias + residual + the next block's norm happen in ONE kernel (lapb200_resid_norm_fwd) — against the
+    single-pass GEMM with the residual epilogue followed by the stand-alone norm kernel (same rounding points: equal up to
+    the fp32 summation order), and bit-identical from run to run."""
+    torch.manual_seed(M + K)
+    A = (torch.randn(M, K, device=DEV) * 0.1).bfloat16()
+    W = (torch.randn(N, K, device=DEV) * 0.05).bfloat16()
+    R = torch.randn(M, N, device=DEV).bfloat16()
+    bias = torch.randn(N, device=DEV) * 0.1 if ln else None
+    scale = torch.randn(N, device=DEV) * 0.2
+    nb = torch.randn(N, device=DEV) * 0.1
+    # reference path
+    X2 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+    ops.gemm(A, W, X2, M=M, N=N, K=K, epi=ops.EPI_RESID, resid=R, bias=bias)
+    Y = torch.zeros_like(X2)
+    rstd = torch.zeros(M, device=DEV)
+    mean = torch.zeros(M, device=DEV)
+    if ln:
+        ops.layernorm_fwd(X2, scale, nb, Y, mean, rstd, M, N)
+    else:
+        ops.rmsnorm_fwd(X2, Y, rstd, M, N, scale=scale)
+    # slab path
+    def run():
+        acc = torch.full((ks, M, N), 7.0, device=DEV)          # stale contents must not matter: slabs are overwritten
+        ops.gemm(A, W, acc, M=M, N=N, K=K, k_splits=ks, split_stride=M * N, cta_group=cg, block_n=bn)
+        x2 = torch.zeros(M, N, device=DEV, dtype=torch.bfloat16)
+        y = torch.zeros_like(x2)
+        r2, m2 = torch.zeros(M, device=DEV), torch.zeros(M, device=DEV)
+        ops.resid_norm_fwd(R, acc, ks, M * N, bias, x2, ln, scale, nb if ln else None, y, m2 if ln else None, r2, M, N)
+        return acc, x2, y, r2
+    acc, x2, y, r2 = run()
+    ref32 = A.float() @ W.float().T
+    assert rel_err(acc.sum(0), ref32) < 1e-5
+    assert (x2 != X2).float().mean().item() < 2e-3          # a different fp32 summation order flips a rare bf16 rounding
+    assert rel_err(x2, X2) < 1e-3 and rel_err(y, Y) < 2e-3 and rel_err(r2, rstd) < 1e-4
+    acc_b, x2_b, y_b, _ = run()
+    assert torch.equal(acc, acc_b) and torch.equal(x2, x2_b) and torch.equal(y, y_b)
+    # finalisation only (y = None)
+    x3 = torch.zeros_like(x2)
+    ops.resid_norm_fwd(R, acc, ks, M * N, bias, x3, ln, None, None, None, None, None, M, N)
+    assert torch.equal(x3, x2)
