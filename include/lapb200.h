@@ -138,7 +138,7 @@ int lapb200_rope_bwd(const void* dQ, const void* dK, const void* dV, const int32
                      int64_t NH, int64_t HD, float qscale, lapb_stream_t s);
 
 /* GeGLU backward in place (lora.py:124-142); GELU backward (siglip.py:71); swish (pi0.py:165-167). */
-int lapb200_geglu_bwd(void* dact, void* gu, int64_t M, int64_t F, lapb_stream_t s);
+int lapb200_geglu_bwd(void* dact, void* gu, int64_t M, int64_t F, int64_t write_act, lapb_stream_t s);
 int lapb200_gelu_bwd(void* dh, const void* pre, int64_t n, lapb_stream_t s);
 int lapb200_swish_fwd(const float* z, float* y, void* y_bf16, int64_t n, lapb_stream_t s);
 int lapb200_swish_bwd(const float* z, const float* dy, const void* dy_bf16, float* dz, int64_t n, lapb_stream_t s);

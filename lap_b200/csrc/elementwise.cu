@@ -807,7 +807,9 @@ rope_bwd_kernel(const bf16* __restrict__ dQ, const bf16* __restrict__ dK, const 
 
 // ------------------------------------------------------------------------------------------------
 // GeGLU backward (lora.py:124-142), in place:  in  dact=[dAct], gu=[g|u]   out  dact=[act], gu=[dg|du]
+// WRITE_ACT = false: the caller kept `act` from the forward pass (one sixth of this kernel's HBM traffic saved)
 // ------------------------------------------------------------------------------------------------
+template <bool WRITE_ACT>
 __global__ void geglu_bwd_kernel(bf16* __restrict__ dact, bf16* __restrict__ gu, long M, long F) {
   long nvec = M * (F / 8);
   for (long v = (long)blockIdx.x * blockDim.x + threadIdx.x; v < nvec; v += (long)gridDim.x * blockDim.x) {
@@ -823,7 +825,7 @@ __global__ void geglu_bwd_kernel(bf16* __restrict__ dact, bf16* __restrict__ gu,
       du[j] = d[j] * ge;
       dg[j] = d[j] * u[j] * gelu_tanh_grad(g[j]);
     }
-    st8(dact + r * F + c, act);
+    if (WRITE_ACT) st8(dact + r * F + c, act);
     st8(gu + r * 2 * F + c, dg);
     st8(gu + r * 2 * F + F + c, du);
   }
@@ -1136,9 +1138,10 @@ int lapb200_rope_bwd(const void* dQ, const void* dK, const void* dV, const int32
   return 0;
 }
 
-int lapb200_geglu_bwd(void* dact, void* gu, int64_t M, int64_t F, lapb_stream_t s) {
+int lapb200_geglu_bwd(void* dact, void* gu, int64_t M, int64_t F, int64_t write_act, lapb_stream_t s) {
   LAPB_REQUIRE(F % 8 == 0, "geglu_bwd: F %% 8 != 0");
-  geglu_bwd_kernel<<<grid_for(M * F / 8, 256), 256, 0, STREAM(s)>>>((bf16*)dact, (bf16*)gu, M, F);
+  if (write_act) geglu_bwd_kernel<true><<<grid_for(M * F / 8, 256), 256, 0, STREAM(s)>>>((bf16*)dact, (bf16*)gu, M, F);
+  else geglu_bwd_kernel<false><<<grid_for(M * F / 8, 256), 256, 0, STREAM(s)>>>((bf16*)dact, (bf16*)gu, M, F);
   LAPB_LAUNCH_OK("geglu_bwd");
   return 0;
 }

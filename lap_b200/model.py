@@ -105,6 +105,7 @@ class LAP:
         # blocks) and is epilogue-bound already, so the extra P tile per output tile costs more than the separate
         # HBM-roofline pass it removes.  Off by default; LAPB_FUSED_SOFTMAX_BWD=1 enables it.
         self.fuse_softmax_bwd = os.environ.get("LAPB_FUSED_SOFTMAX_BWD", "0") == "1"
+        self.save_mlp_act = os.environ.get("LAPB_SAVE_MLP_ACT", "1") != "0"  # keep gelu(g)*u of every layer for the backward
         # batch-1 prefix pass: deterministic split-K slabs for the down / fc2 projections (tools/gemm_small_m.py)
         self.use_small_m_split_k = os.environ.get("LAPB_SMALL_M_SPLIT_K", "1") != "0"
         self.denoise_profile = False  # accumulate per-phase ns of K10 into buf "dn.prof" (tools/denoise_prof.py)
@@ -701,7 +702,9 @@ class LAP:
                 h2 = self.buf(sv("h2", l), (Mg, D))
                 rstd2 = self.buf(sv("rstd2", l), (Mg,), F32)
                 ops.rmsnorm_fwd(X1, h2, rstd2, Mg, D, scale=self.p("g.ffn_norm_s", l))
-                act = self.buf(f"{tag}.act", (Mg, F))
+                # `act` is kept per layer when the backward follows: geglu_bwd then need not rewrite it (one sixth of its
+                # HBM traffic), at 0.7 GB per layer of the 180 GB
+                act = self.buf(sv("act", l) if (save and self.save_mlp_act) else f"{tag}.act", (Mg, F))
                 GU = self.buf(sv("GU", l), (Mg, 2 * F))
                 ops.gemm(h2, self.w("g.gu_w", l), act, M=Mg, N=F, K=D, epi=ops.EPI_GEGLU, C2=GU, ldc2=2 * F)
                 X2 = self.buf(sv("X", l + 1), (Mg, D))
@@ -957,8 +960,12 @@ class LAP:
             # (fusing geglu_bwd into this GEMM's epilogue — EPI_GEGLU_BWD — measured slower: the epilogue becomes the
             #  bottleneck; the streaming kernel runs at the HBM roofline instead)
             self._dgrad(dX, self.w("g.down_w", l), dact, Mg, D, F)
-            ops.geglu_bwd(dact, GU, Mg, F)  # dact <- act, GU <- [dg|du]
-            self._wgrad(dX, dact, self.g("g.down_w", l), Mg, D, F)
+            if self.save_mlp_act:
+                ops.geglu_bwd(dact, GU, Mg, F, write_act=False)  # GU <- [dg|du]; act was kept by the forward
+                self._wgrad(dX, sv("act"), self.g("g.down_w", l), Mg, D, F)
+            else:
+                ops.geglu_bwd(dact, GU, Mg, F)  # dact <- act, GU <- [dg|du]
+                self._wgrad(dX, dact, self.g("g.down_w", l), Mg, D, F)
             self._wgrad(GU, h2, self.g("g.gu_w", l), Mg, 2 * F, D)
             self._dgrad(GU, self.w("g.gu_w", l), dh, Mg, 2 * F, D)
             ops.rmsnorm_bwd(dh, X1, self.p("g.ffn_norm_s", l), sv("rstd2"), dX, dX, self.g("g.ffn_norm_s", l), Mg, D)

@@ -243,8 +243,9 @@ def rope_bwd(dQ, dK, dV, positions, timescale, dqkv0, dqkv1, B, P, A, Tpad, NH, 
     call("rope_bwd", dQ, dK, dV, positions, timescale, dqkv0, dqkv1, B, P, A, Tpad, NH, HD, float(qscale))
 
 
-def geglu_bwd(dact, gu, M, F):
-    call("geglu_bwd", dact, gu, M, F)
+def geglu_bwd(dact, gu, M, F, write_act=True):
+    """dact <- act (only if write_act: the caller may have kept act from the forward), gu <- [dg | du], in place."""
+    call("geglu_bwd", dact, gu, M, F, bool(write_act))
 
 
 def gelu_bwd(dh, pre, n):
