@@ -20,7 +20,18 @@ Q = (torch.randn(B, T, NH, HD, device=dev) * 0.2).bfloat16(); Kc = torch.randn(B
 bits = torch.full((B, T, Tpad // 32), -1, dtype=torch.int32, device=dev)
 P = torch.empty(B, T * NH, Tpad, device=dev, dtype=torch.bfloat16); O0 = torch.empty(B * 692 * NH, HD, device=dev, dtype=torch.bfloat16); O1 = torch.empty(B * 10 * NH, HD, device=dev, dtype=torch.bfloat16)
 dP = torch.randn(B, T * NH, Tpad, device=dev).bfloat16()
+# round 2: K2 (fused SigLIP attention) at the training shape (64 images), the image kernels, the batch-1 finaliser
+Ni, nh, Np, hdv = 64, 16, 256, 72
+qkv_v = (torch.randn(Ni * Np, 3 * nh * hdv, device=dev) * 0.3).bfloat16()
+Ov = torch.empty(Ni * Np, nh * hdv, device=dev, dtype=torch.bfloat16); Pv = torch.empty(Ni, nh, Np, Np, device=dev, dtype=torch.bfloat16)
+img8 = torch.randint(0, 256, (32, 224, 224, 3), device=dev, dtype=torch.uint8); imgf = torch.empty(32, 224, 224, 3, device=dev)
+augp = torch.zeros(32, 8, device=dev); augp[:, 2] = 3.0; augp[:, 3] = 0.1
+acc3 = torch.randn(3, 692, 2048, device=dev); r692 = torch.randn(692, 2048, device=dev).bfloat16(); x692 = torch.empty_like(r692); y692 = torch.empty_like(r692); rs692 = torch.empty(692, device=dev)
 for _ in range(2):
+    ops.vit_attn_fwd(qkv_v, Ov, Pv, Ni, nh, Np, hdv, 0)
+    ops.vit_attn_fwd(qkv_v, Ov, None, Ni, nh, Np, hdv, 0)
+    ops.image_augment(img8, imgf, 32, 224, 224, augp)
+    ops.resid_norm_fwd(r692, acc3, 3, 692 * 2048, None, x692, False, scale, None, y692, None, rs692, 692, 2048)
     ops.rmsnorm_fwd(x, y, rstd, M, D, scale=scale)
     ops.rmsnorm_bwd(dy, x, scale, rstd, dres, dx, dsc, M, D)
     ops.geglu_bwd(dact, gu, M, F)
