@@ -23,6 +23,7 @@
 #include "../../include/lapb200.h"
 #include "common.cuh"
 #include "host_util.h"
+#include <stdlib.h>
 
 namespace lapb {
 
@@ -352,6 +353,224 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Single-chunk variant (Np <= 256: the 224 px tower): ONE CTA = one (image, head) = BOTH 128-row query tiles, so K and V are
+// fetched once per head and the two tiles are pipelined through the roles — while the softmax warps work on tile 1 the
+// tensor core runs P V of tile 0, and the epilogue of tile 0 overlaps P V of tile 1.  (The one-tile-per-CTA kernel above is
+// latency-bound: ncu shows 30 % issue utilisation with the CTA's phases strictly serial, profiles/r02_k2.md.)
+//   shared memory: Q0 | Q1 (2 x 32 KB), K (64 KB), V (64 KB).  P(0) overwrites K, P(1) overwrites Q0|Q1: both are dead once
+//   the two S MMAs have retired.  TMEM: S0 [0, 256), S1 [256, 512); O(t) reuses the first 128 columns of S(t).
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int FVP_SMEM = 2 * FV_Q_BYTES + 2 * FV_KV_BYTES + 1024 + 512 + FV_WG * 128 * 8;
+static_assert(FVP_SMEM <= 227 * 1024, "fa_vit pair: shared memory");
+
+__global__ void __launch_bounds__(FV_THREADS, 1)
+fa_vit_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmP, const FvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* Qs = smem;                       // [2 tiles][2 atoms][128 rows x 128 B]
+  uint8_t* Ks = Qs + 2 * FV_Q_BYTES;
+  uint8_t* Vs = Ks + FV_KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(Vs + FV_KV_BYTES);
+  uint64_t* qk_full = bars;        // Q0, Q1 and K landed
+  uint64_t* v_full = bars + 1;
+  uint64_t* s_full = bars + 2;     // [2] S(t) in TMEM (implies every S MMA issued before it has retired)
+  uint64_t* s_read = bars + 4;     // [2] every softmax thread has pulled its S(t) values: O(t) may overwrite the columns
+  uint64_t* p_full = bars + 6;     // [2][4] P sub-tile w of tile t written
+  uint64_t* o_full = bars + 14;    // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 16);
+  float* stat = reinterpret_cast<float*>(bars + 64);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, img = blockIdx.y;
+  const int NT = a.Np > FV_QT ? 2 : 1;                      // query tiles of this head
+  const int nkeys = (a.Np + 15) & ~15;                      // MMA N / K extent (multiple of 16, <= 256)
+  constexpr int W_TMA = 4 * FV_WG, W_MMA = W_TMA + 1, W_ALLOC = W_TMA + 2;
+  uint8_t* const Pbuf[2] = {Ks, Qs};
+
+  if (warp == W_TMA && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+  }
+  if (warp == W_MMA && lane == 0) {
+    mbar_init(qk_full, 1);
+    mbar_init(v_full, 1);
+    for (int t = 0; t < 2; ++t) {
+      mbar_init(&s_full[t], 1);
+      mbar_init(&s_read[t], FV_SOFT);
+      mbar_init(&o_full[t], 1);
+      for (int w = 0; w < FV_WG; ++w) mbar_init(&p_full[t * 4 + w], 1);
+    }
+    fence_barrier_init();
+    fence_proxy_async();
+  }
+  if (warp == W_ALLOC) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == W_TMA) {
+    if (lane == 0) {
+      mbar_expect_tx(qk_full, NT * FV_Q_BYTES + FV_KV_BYTES);
+      for (int t = 0; t < NT; ++t) {
+        tma_load_4d(Qs + t * FV_Q_BYTES, &tmQ, qk_full, 0, t * FV_QT, h, img);
+        tma_load_4d(Qs + t * FV_Q_BYTES + FV_QT * 128, &tmQ, qk_full, 64, t * FV_QT, h, img);
+      }
+      tma_load_4d(Ks, &tmK, qk_full, 0, 0, h, img);
+      tma_load_4d(Ks + FV_KC * 128, &tmK, qk_full, 64, 0, h, img);
+      mbar_expect_tx(v_full, FV_KV_BYTES);
+      tma_load_4d(Vs, &tmV, v_full, 0, 0, h, img);
+      tma_load_4d(Vs + FV_KC * 128, &tmV, v_full, 64, 0, h, img);
+    }
+  } else if (warp == W_MMA) {
+    const uint32_t q_addr = smem_u32(Qs), k_addr = smem_u32(Ks), v_addr = smem_u32(Vs);
+    constexpr uint32_t idescPV = make_idesc_bf16(FV_QT, FV_HP, 0, 1);
+    const uint32_t idescS = make_idesc_bf16(FV_QT, nkeys, 0, 0);
+    mbar_wait(qk_full, 0);
+    tc_fence_after();
+    for (int t = 0; t < NT; ++t) {
+#pragma unroll
+      for (int kk = 0; kk < 5; ++kk) {
+        const uint32_t qo = t * FV_Q_BYTES + ((kk < 4) ? kk * 32 : FV_QT * 128);
+        const uint32_t ko = (kk < 4) ? kk * 32 : FV_KC * 128;
+        uint64_t da = make_smem_desc_sw128(q_addr + qo, 16, 1024);
+        uint64_t db = make_smem_desc_sw128(k_addr + ko, 16, 1024);
+        umma_bf16_elect(tmem_base + t * 256, da, db, idescS, kk != 0 ? 1u : 0u);
+      }
+      // the commit of S(NT-1) covers the MMAs of S(0) too: only then are Q and K dead (P may overwrite them)
+      if (t == NT - 1)
+        for (int u = 0; u < NT; ++u) umma_commit_elect(&s_full[u]);
+    }
+    mbar_wait(v_full, 0);
+    const int ns = (nkeys + FV_KT - 1) / FV_KT;
+    for (int t = 0; t < NT; ++t) {
+      const uint32_t p_addr = smem_u32(Pbuf[t]);
+      mbar_wait(&s_read[t], 0);  // O(t) lives in the first 128 columns of S(t)
+      for (int s2 = 0; s2 < ns; ++s2) {
+        mbar_wait(&p_full[t * 4 + s2], 0);
+        tc_fence_after();
+        const int ksteps = min(FV_KT, nkeys - s2 * FV_KT) / 16;
+        for (int kk = 0; kk < ksteps; ++kk) {
+          uint64_t da = make_smem_desc_sw128(p_addr + s2 * (FV_QT * 128) + kk * 32, 16, 1024);
+          uint64_t db = make_smem_desc_sw128(v_addr + (s2 * FV_KT + kk * 16) * 128, FV_KC * 128, 1024);
+          umma_bf16_elect(tmem_base + t * 256, da, db, idescPV, (s2 | kk) != 0 ? 1u : 0u);
+        }
+      }
+      umma_commit_elect(&o_full[t]);
+    }
+  } else if (warp < W_TMA) {
+    const int wg = warp >> 2;
+    const int r = (warp & 3) * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const bool bf16_softmax = a.mode == 0;
+    const bool leader = (warp & 3) == 0 && lane == 0;
+    const bool active = wg * FV_KT < nkeys;
+    auto expv = [&](float x) { return bf16_softmax ? bf16r(__expf(bf16r(x))) : __expf(x); };
+    auto exchange = [&](float mine, bool is_max) -> float {
+      stat[(wg * 128 + r) * 2] = mine;
+      fv_softmax_bar();
+      float v = stat[r * 2];
+#pragma unroll
+      for (int o = 1; o < FV_WG; ++o) v = is_max ? fmaxf(v, stat[(o * 128 + r) * 2]) : v + stat[(o * 128 + r) * 2];
+      fv_softmax_bar();
+      return v;
+    };
+    auto epilogue = [&](int t) {  // O(t) (fp32, TMEM) -> bf16 rows; warpgroup g stores columns [32 g, 32 g + 32)
+      mbar_wait(&o_full[t], 0);
+      tc_fence_after();
+      const int qrow = t * FV_QT + r;
+      if (wg * 32 < a.hd) {
+        bf16* orow = a.O + ((long)img * a.Np + qrow) * a.ldo + (long)h * a.hd;
+        const int c0 = wg * 32;
+        uint32_t o[32];
+        tmem_ld_32x32(tmem_base + t * 256 + lane_base + c0, o);
+        tmem_ld_wait();
+        if (qrow < a.Np) {
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            if (c0 + v * 8 < a.hd) {
+              uint4 u;
+              u.x = pack_bf16x2(__uint_as_float(o[8 * v + 0]), __uint_as_float(o[8 * v + 1]));
+              u.y = pack_bf16x2(__uint_as_float(o[8 * v + 2]), __uint_as_float(o[8 * v + 3]));
+              u.z = pack_bf16x2(__uint_as_float(o[8 * v + 4]), __uint_as_float(o[8 * v + 5]));
+              u.w = pack_bf16x2(__uint_as_float(o[8 * v + 6]), __uint_as_float(o[8 * v + 7]));
+              *reinterpret_cast<uint4*>(orow + c0 + v * 8) = u;
+            }
+          }
+        }
+      }
+    };
+    for (int t = 0; t < NT; ++t) {
+      mbar_wait(&s_full[t], 0);
+      tc_fence_after();
+      float sv[64];
+      if (active) {
+        const int k0 = wg * FV_KT;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          uint32_t tt[32];
+          tmem_ld_32x32(tmem_base + t * 256 + lane_base + wg * FV_KT + hf * 32, tt);
+          tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            sv[hf * 32 + c] = (k0 + hf * 32 + c < a.Np) ? bf16r(__uint_as_float(tt[c])) : FV_NEG_INF;
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 64; ++c) sv[c] = FV_NEG_INF;
+      }
+      tc_fence_before();
+      mbar_arrive_relaxed(&s_read[t]);
+      float tmax = -3.4e38f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) tmax = fmaxf(tmax, sv[c]);
+      const float m = exchange(tmax, true);
+      float sum = 0.f;
+#pragma unroll
+      for (int c = 0; c < 64; ++c) {
+        sv[c] = expv(sv[c] - m);
+        sum += sv[c];
+      }
+      const float l = exchange(sum, false);
+      const float denom = bf16_softmax ? bf16r(l) : l;
+      if (active) {
+        uint32_t pk[32];
+#pragma unroll
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] / denom, sv[c + 1] / denom);
+        uint8_t* sub = Pbuf[t] + wg * (FV_QT * 128);
+        uint8_t* prow = sub + r * 128;
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(prow + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        fence_proxy_async();
+        fv_wg_bar(wg);
+        if (leader) {
+          if (a.write_p) {
+            fv_tma_store_4d(&tmP, sub, wg * FV_KT, t * FV_QT, h, img);
+            fv_store_commit();
+          }
+          mbar_arrive(&p_full[t * 4 + wg]);
+        }
+      }
+      if (t == 1) epilogue(0);  // O(0) has been accumulating while tile 1 went through the softmax
+    }
+    epilogue(NT - 1);
+    if (leader && a.write_p) fv_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == W_ALLOC) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 int make_tmap_bf16_4d(CUtensorMap* m, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t d3, int64_t s1,
                       int64_t s2, int64_t s3, uint32_t box0, uint32_t box1);  // gemm.cu
 
@@ -385,7 +604,19 @@ extern "C" int lapb200_vit_attn_fwd(const void* qkv, void* O, void* P, int64_t N
   static bool configured = false;
   if (!configured) {
     LAPB_CUDA_OK(cudaFuncSetAttribute(fa_vit_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FV_SMEM));
+    LAPB_CUDA_OK(cudaFuncSetAttribute(fa_vit_fwd_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FVP_SMEM));
     configured = true;
+  }
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("LAPB_VIT_PAIR");
+    pair_env = (e && e[0] == '0') ? 0 : 1;  // 0: always the one-tile-per-CTA kernel
+  }
+  if (pair_env && Np <= FV_KC) {  // the whole row in one key chunk: one CTA per head, both query tiles pipelined
+    dim3 grid((unsigned)nh, (unsigned)Ni);
+    fa_vit_fwd_pair_kernel<<<grid, FV_THREADS, FVP_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
+    LAPB_LAUNCH_OK("vit_attn_fwd (pair)");
+    return 0;
   }
   dim3 grid((unsigned)cdiv(Np, FV_QT), (unsigned)nh, (unsigned)Ni);
   fa_vit_fwd_kernel<<<grid, FV_THREADS, FV_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
