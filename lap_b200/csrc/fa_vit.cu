@@ -291,11 +291,11 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
         for (int c = 0; c < 64; ++c) sv[c] = expv(sv[c] - m);
       }
-      const float denom = bf16_softmax ? bf16r(l) : l;
+      const float inv = 1.0f / (bf16_softmax ? bf16r(l) : l);  // see the pair kernel
       if (active) {
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] / denom, sv[c + 1] / denom);
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] * inv, sv[c + 1] * inv);
         // (P aliases K(j): the producer loaded K(j) only after P V(j-1) had retired and the stores of P(j-1) had read the
         //  buffer, and s_full(j) says the S MMAs are done reading K(j) — the buffer is ours)
         // K-major, 128B-swizzled A sub-tile: row r is 128 B (64 keys); 16-byte chunk c sits at chunk position c ^ (r & 7)
@@ -361,7 +361,7 @@ fa_vit_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 //   shared memory: Q0 | Q1 (2 x 32 KB), K (64 KB), V (64 KB).  P(0) overwrites K, P(1) overwrites Q0|Q1: both are dead once
 //   the two S MMAs have retired.  TMEM: S0 [0, 256), S1 [256, 512); O(t) reuses the first 128 columns of S(t).
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int FVP_SMEM = 2 * FV_Q_BYTES + 2 * FV_KV_BYTES + 1024 + 512 + FV_WG * 128 * 8;
+constexpr int FVP_SMEM = 2 * FV_Q_BYTES + 2 * FV_KV_BYTES + 1024 + 512 + 4 * FV_WG * 128 * 4;  // 4 exchange slots
 static_assert(FVP_SMEM <= 227 * 1024, "fa_vit pair: shared memory");
 
 __global__ void __launch_bounds__(FV_THREADS, 1)
@@ -472,13 +472,15 @@ fa_vit_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
     const bool leader = (warp & 3) == 0 && lane == 0;
     const bool active = wg * FV_KT < nkeys;
     auto expv = [&](float x) { return bf16_softmax ? bf16r(__expf(bf16r(x))) : __expf(x); };
-    auto exchange = [&](float mine, bool is_max) -> float {
-      stat[(wg * 128 + r) * 2] = mine;
+    // combine one value per warpgroup across the four of them; every (tile, quantity) has its own slot, so ONE barrier
+    // per exchange is enough (nothing is ever overwritten)
+    auto exchange = [&](float mine, bool is_max, int slot) -> float {
+      float* st = stat + slot * (FV_WG * 128);
+      st[wg * 128 + r] = mine;
       fv_softmax_bar();
-      float v = stat[r * 2];
+      float v = st[r];
 #pragma unroll
-      for (int o = 1; o < FV_WG; ++o) v = is_max ? fmaxf(v, stat[(o * 128 + r) * 2]) : v + stat[(o * 128 + r) * 2];
-      fv_softmax_bar();
+      for (int o = 1; o < FV_WG; ++o) v = is_max ? fmaxf(v, st[o * 128 + r]) : v + st[o * 128 + r];
       return v;
     };
     auto epilogue = [&](int t) {  // O(t) (fp32, TMEM) -> bf16 rows; warpgroup g stores columns [32 g, 32 g + 32)
@@ -530,19 +532,21 @@ fa_vit_fwd_pair_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_con
       float tmax = -3.4e38f;
 #pragma unroll
       for (int c = 0; c < 64; ++c) tmax = fmaxf(tmax, sv[c]);
-      const float m = exchange(tmax, true);
+      const float m = exchange(tmax, true, 2 * t);
       float sum = 0.f;
 #pragma unroll
       for (int c = 0; c < 64; ++c) {
         sv[c] = expv(sv[c] - m);
         sum += sv[c];
       }
-      const float l = exchange(sum, false);
-      const float denom = bf16_softmax ? bf16r(l) : l;
+      const float l = exchange(sum, false, 2 * t + 1);
+      // one IEEE reciprocal per row, then a multiply per element (K1 does the same): e * (1/l) differs from e / l by at
+      // most one fp32 ulp, i.e. it moves a bf16 rounding with probability ~3e-5 per element
+      const float inv = 1.0f / (bf16_softmax ? bf16r(l) : l);
       if (active) {
         uint32_t pk[32];
 #pragma unroll
-        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] / denom, sv[c + 1] / denom);
+        for (int c = 0; c < 64; c += 2) pk[c >> 1] = pack_bf16x2(sv[c] * inv, sv[c + 1] * inv);
         uint8_t* sub = Pbuf[t] + wg * (FV_QT * 128);
         uint8_t* prow = sub + r * 128;
 #pragma unroll

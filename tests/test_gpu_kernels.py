@@ -529,9 +529,10 @@ def test_fused_vit_attention_matches_unfused_and_torch(Ni, nh, Np, mode):
         ops.gemm(Pu, qf[2 * W:], Ou, M=Np, N=hd, K=Np, b_major=1, lda=Np, ldb=3 * W, ldc=W, batch_i=nh, batch_o=Ni,
                  a_bs=(Np * Np, nh * Np * Np), b_bs=(hd, Np * 3 * W), c_bs=(hd, Np * W))
         torch.cuda.synchronize()
-        # identical except where bf16(sum) sits on a rounding boundary (a whole row then moves by one ulp)
-        frac_rows_equal = (P == Pu).all(-1).float().mean().item()
-        assert frac_rows_equal > 0.99, frac_rows_equal
+        # identical except where bf16(sum) sits on a rounding boundary (a whole row then moves by one ulp) and where
+        # e * (1 / sum) and e / sum differ in the last fp32 bit right at a bf16 boundary (~3e-5 of the elements)
+        assert (P != Pu).float().mean().item() < 2e-3
+        assert (P.float() - Pu.float()).abs().max() <= 2 ** -8 + 1e-6
         assert rel_err(O, Ou) < 2e-3
     # without P (inference) the output is the same
     O2 = torch.zeros_like(O)
