@@ -616,7 +616,10 @@ extern "C" int lapb200_vit_attn_fwd(const void* qkv, void* O, void* P, int64_t N
     const char* e = getenv("LAPB_VIT_PAIR");
     pair_env = (e && e[0] == '0') ? 0 : 1;  // 0: always the one-tile-per-CTA kernel
   }
-  if (pair_env && Np <= FV_KC) {  // the whole row in one key chunk: one CTA per head, both query tiles pipelined
+  // the whole row in one key chunk AND more query tiles than two waves of CTAs: one CTA per head, both query tiles pipelined
+  // (measured, tools/k2_time.py: 173 vs 209 us at 64 images; at 2 images — 64 tiles, the serving case — one tile per CTA is
+  //  the faster shape, 17 vs 28 us)
+  if (pair_env && Np <= FV_KC && nh * Ni * (long)cdiv(Np, FV_QT) > 2L * num_sms()) {
     dim3 grid((unsigned)nh, (unsigned)Ni);
     fa_vit_fwd_pair_kernel<<<grid, FV_THREADS, FVP_SMEM, stream>>>(tmQ, tmK, tmV, tmP, a);
     LAPB_LAUNCH_OK("vit_attn_fwd (pair)");
