@@ -119,21 +119,43 @@ sgemm_kernel(const TA* __restrict__ A, const TB* __restrict__ B, void* __restric
   int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
   int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
   float acc[4][4] = {};
-  for (int k0 = 0; k0 < K; k0 += TK) {
-    for (int i = threadIdx.x; i < TM * TK; i += 256) {
-      // pick the faster-varying index by stride so global loads coalesce where possible
+  // software pipeline: the global loads of K block k+1 are in flight (registers) while block k is multiplied out of
+  // shared memory — these GEMMs are tiny (M <= 64 rows x K = 1024, or K = 588) and were bound by the exposed load latency
+  // of every K block (~3 us each)
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + q * 256;
       int mm, kk;
+      // pick the faster-varying index by stride so global loads coalesce where possible
       if (sak == 1) { kk = i % TK; mm = i / TK; } else { mm = i % TM; kk = i / TM; }
       int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < M && k < K) ? (float)A[m * sam + k * sak] : 0.f;
-    }
-    for (int i = threadIdx.x; i < TN * TK; i += 256) {
-      int nn, kk;
+      ra[q] = (m < M && k < K) ? (float)A[m * sam + k * sak] : 0.f;
+      int nn;
       if (sbk == 1) { kk = i % TK; nn = i / TK; } else { nn = i % TN; kk = i / TN; }
-      int n = n0 + nn, k = k0 + kk;
-      Bs[kk][nn] = (n < N && k < K) ? (float)B[n * sbn + k * sbk] : 0.f;
+      int n = n0 + nn;
+      k = k0 + kk;
+      rb[q] = (n < N && k < K) ? (float)B[n * sbn + k * sbk] : 0.f;
     }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int i = threadIdx.x + q * 256;
+      int mm, kk;
+      if (sak == 1) { kk = i % TK; mm = i / TK; } else { mm = i % TM; kk = i / TM; }
+      As[kk][mm] = ra[q];
+      int nn;
+      if (sbk == 1) { kk = i % TK; nn = i / TK; } else { nn = i % TN; kk = i / TN; }
+      Bs[kk][nn] = rb[q];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += TK) {
+    stash();
     __syncthreads();
+    if (k0 + TK < K) fetch(k0 + TK);
 #pragma unroll
     for (int kk = 0; kk < TK; ++kk) {
       float a[4], b[4];
