@@ -260,7 +260,7 @@ def run_train(args) -> None:
     def max_over_ranks(ms: float) -> float:
         if world == 1:
             return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms], dtype=torch.float32, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 

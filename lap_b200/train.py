@@ -81,7 +81,7 @@ class TrainingStepRunner:
         n_active = float(to_numpy(sm).astype(bool).sum()) if sm is not None else float(B)
         n_action = float(B)
         if self.world > 1:
-            t = torch.tensor([n_active, n_action], dtype=torch.float64, device=device)
+            t = torch.tensor([n_active, n_action], dtype=torch.float32, device=device)  # counts <= 2^24: exact in fp32
             dist.all_reduce(t, op=dist.ReduceOp.SUM)
             n_active, n_action = (float(x) for x in t.tolist())
         return n_active, n_action
