@@ -237,10 +237,10 @@ def run_train(args) -> None:
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # the gradient all-reduce is spread over the whole backward (train.py::_phases): 8 NCCL channels next to the 8 SMs
-        # the persistent GEMMs leave free are enough to move 13.4 GB in the ~200 ms of backward
-        os.environ.setdefault("NCCL_MAX_NCHANNELS", "8")
-        os.environ.setdefault("LAPB_COMM_SMS", "8")
+        # the all-reduce of the LLM gradients overlaps the SigLIP backward: 16 NCCL channels (N = 2: the p2p ring needs them;
+        # N = 8: NVLS runs 16 CTAs regardless) next to the 16 SMs the persistent GEMMs leave free
+        os.environ.setdefault("NCCL_MAX_NCHANNELS", "16")
+        os.environ.setdefault("LAPB_COMM_SMS", "16")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     tc = get_config("lap_libero")

@@ -65,9 +65,13 @@ class TrainingStepRunner:
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.bucket_bytes = bucket_bytes
         self.use_cuda_graph = use_cuda_graph
-        self.comm_sms = int(os.environ.get("LAPB_COMM_SMS", "8"))  # SMs left to NCCL while it overlaps compute
-        self.bwd_segments = int(os.environ.get("LAPB_BWD_SEGMENTS", "3"))  # LLM backward groups (world > 1)
-        self.vis_segments = int(os.environ.get("LAPB_VIS_SEGMENTS", "3"))  # SigLIP backward groups (world > 1)
+        # Defaults = the measured best at N = 2 and N = 8 (profiles/r02_overlap_sweep.md): ONE LLM group + ONE SigLIP group
+        # (the LLM gradients are reduced under the SigLIP backward) and 16 SMs left to NCCL (NVLS runs 16 CTAs whatever
+        # NCCL_MAX_NCHANNELS says).  Finer groups hide more of the all-reduce but put the SM carve-out on more GEMMs: equal
+        # within noise at N = 8 (373.9 vs 374.9 ms), slower at N = 2.
+        self.comm_sms = int(os.environ.get("LAPB_COMM_SMS", "16"))  # SMs left to NCCL while it overlaps compute
+        self.bwd_segments = int(os.environ.get("LAPB_BWD_SEGMENTS", "1"))  # LLM backward groups (world > 1)
+        self.vis_segments = int(os.environ.get("LAPB_VIS_SEGMENTS", "1"))  # SigLIP backward groups (world > 1)
         self._phase_cache: dict = {}
         self._partials = None
         self._stats = None
