@@ -226,6 +226,20 @@ class LAP:
         self._bufs[name] = t
         return t
 
+    def release_workspaces(self) -> None:
+        """Drop every pooled workspace, staging buffer and captured inference graph (parameters stay).  Workspaces are
+        never freed implicitly — a captured graph may point at them — so a long-lived process that has cycled through many
+        batch shapes calls this at a quiet point; trainers drop their own graphs first (`TrainingStepRunner.reset`)."""
+        torch.cuda.synchronize(self.device)
+        self._infer_graphs.clear()
+        self._infer_warm.clear()
+        self._bufs.clear()
+        self._pool.clear()
+        self._io.clear()
+        self._io_event = None
+        self._resize_plans.clear()
+        torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------------------------------
     # input staging (host -> device); masks are tiny and are assembled on the host
     # ------------------------------------------------------------------------------------------

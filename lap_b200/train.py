@@ -79,6 +79,13 @@ class TrainingStepRunner:
         self._graphs: dict = {}  # (B, R_cap, state, model) -> (one graph per phase ..., optimizer graph)
         self._warm: dict = {}  # eager steps run per (B, R_cap): workspaces exist before capture
 
+    def reset(self) -> None:
+        """Forget the captured step graphs (call before `LAP.release_workspaces`, or after replacing the train state)."""
+        torch.cuda.synchronize()
+        self._graphs.clear()
+        self._warm.clear()
+        self._phase_cache.clear()
+
     # -- global loss normalisers (lap.py:580-589 are means over the GLOBAL batch) ------------------------------
     def _global_counts(self, observation, B: int, device) -> tuple[float, float]:
         sm = getattr(observation, "sample_mask", None)

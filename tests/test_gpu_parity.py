@@ -678,3 +678,30 @@ def test_orbax_params_item_round_trips_through_the_engine(tmp_path):
     m2 = tc.model.load(orbax_io.read_params(out))   # OP/models/model.py:233-241 + 286-332
     got2 = m2.params_reference()
     assert all(torch.equal(got2[k], want[k]) for k in want)
+
+
+def test_release_workspaces_then_continue():
+    """Workspaces are pooled for the life of the model; `release_workspaces` (after `runner.reset`) gives them back and the
+    next calls rebuild what they need with identical results."""
+    from lap_b200.observation import Observation
+    from lap_b200.train import TrainingStepRunner, batch_from_dict, init_train_state
+    tc, ref, model, b = _setup("debug_tiny", 2)
+    b1 = synthetic_batch(tc.model, 1, step=3, with_langact=False)
+    o1 = Observation.from_dict(b1)
+    a = [model.sample_actions(0, o1, num_steps=10, noise=b1["noise"]) for _ in range(3)]
+    obs, actions, extra = batch_from_dict(b)
+    l0, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    n_before = len(model._pool)
+    model.release_workspaces()
+    assert len(model._pool) == 0 and not model._infer_graphs and n_before > 0
+    a2 = model.sample_actions(0, o1, num_steps=10, noise=b1["noise"])
+    l1, _ = model.compute_loss(0, obs, actions, noise=extra["noise"], time=extra["time"])
+    assert torch.equal(a2, a[0]) and l1.item() == l0.item()
+    state = init_train_state(tc, model=model)
+    runner = TrainingStepRunner(tc)
+    for s_ in range(4):
+        state, info = runner(0, state, batch_from_dict(synthetic_batch(tc.model, 2, step=50 + s_)))
+    runner.reset()
+    model.release_workspaces()
+    state, info2 = runner(0, state, batch_from_dict(synthetic_batch(tc.model, 2, step=60)))
+    assert np.isfinite(float(info2["loss"]))
