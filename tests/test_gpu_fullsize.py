@@ -165,10 +165,10 @@ def test_full_size_gradients_match_oracle(full):
             r = rel_err(g_eng[k], g_o)
             worst = max(worst, r)
             n_cmp += 1
-            assert r < 6e-2, (k, r)               # bf16 cotangents through 45 layers vs fp32 autograd of the bf16 forward
+            assert r < 4e-2, (k, r)               # bf16 cotangents through 45 layers vs fp32 autograd (measured: 1.6e-2)
         v.grad = None
     tot = float(torch.sqrt(sum((v.double() ** 2).sum() for v in g_eng.values())))
-    _report(f"worst per-tensor gradient error over {n_cmp} tensors", worst, 6e-2)
+    _report(f"worst per-tensor gradient error over {n_cmp} tensors", worst, 4e-2)
     _report("global gradient norm", abs(tot - gnorm) / gnorm, 1e-2)
     assert abs(tot - gnorm) < 1e-2 * gnorm
 
