@@ -489,12 +489,13 @@ def test_fa_pair_variant_is_bit_identical_to_the_product_kernel():
 
 
 @pytest.mark.parametrize("Ni,nh,Np,mode", [(3, 16, 256, 0), (2, 2, 64, 0), (2, 2, 16, 1), (1, 16, 256, 1), (2, 4, 729, 0),
-                                           (1, 2, 200, 0)])
+                                           (1, 2, 200, 0), (12, 16, 256, 0), (12, 16, 200, 1), (40, 16, 96, 0)])
 def test_fused_vit_attention_matches_unfused_and_torch(Ni, nh, Np, mode):
     """K2 (csrc/fa_vit.cu) vs the GEMM + vit_softmax + GEMM path it replaces (same rounding points: equal up to the
     fp32 summation order of the softmax denominator) and vs a direct PyTorch statement of flax's attention with the
     bf16 / fp32 softmax (siglip.py:88-93).  Np = 729 is the 384 px case (3 key chunks, ragged last chunk, no P output:
-    Np % 8 != 0), Np = 200 a ragged single chunk, Np = 16 / 64 the test-model sizes."""
+    Np % 8 != 0), Np = 200 a ragged single chunk, Np = 16 / 64 the test-model sizes; the cases with more than two waves of
+    query tiles (12 x 16 heads x 2 tiles, 40 x 16 x 1) run the one-CTA-per-head pair kernel (both tiles / a single tile)."""
     hd = 72
     W = nh * hd
     torch.manual_seed(Np + nh)
