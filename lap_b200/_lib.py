@@ -135,7 +135,7 @@ class DenoiseParams(ctypes.Structure):
         ("cond16", c_vp), ("mod", c_vp),
         *[(n, c_vp) for n in ("XE", "XE1", "qkv", "O", "act")],
         ("part_o", c_vp), ("part_ml", c_vp), ("sync", c_vp), ("prof", c_vp),
-        ("packed", c_i32), ("reserved_", c_i32),
+        ("packed", c_i32), ("flags", c_i32),
     ]
 
 

@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       {  // L2 prefetch of this CTA's weight slices of the NEXT layer (next step's layer 0 after the last one): the HBM
          // traffic of a layer is spread over the whole previous layer instead of arriving as one burst per phase
         const int ln = (l + 1 < L) ? l + 1 : 0;
-        if (l + 1 < L || step + 1 < S) {
+        if ((l + 1 < L || step + 1 < S) && !(p.flags & 1)) {
           const bf16* nq = reinterpret_cast<const bf16*>(p.qkv_w) + (long)ln * p.qkv_ls;
           const bf16* no = reinterpret_cast<const bf16*>(p.o_w) + (long)ln * p.o_ls;
           const bf16* ng = reinterpret_cast<const bf16*>(p.gu_w) + (long)ln * p.gu_ls;

@@ -1211,7 +1211,7 @@ class LAP:
 
         ops.denoise_loop(
             ints=dict(A=A, ad=ad, D1=D1, NH=NH, HD=HD, F1=F1, L=L, Pn=Pn, Tpad=Tpad, TpadK=TpadK, W32=Tpad // 32, nm=nm,
-                      num_steps=S, packed=int(packed)),
+                      num_steps=S, packed=int(packed), flags=int(os.environ.get("LAPB_DENOISE_FLAGS", "0"))),
             dt=dt, qscale=HD ** -0.5, times=times, ptrs=ptrs,
             strides=dict(qkv_ls=lstride("e.qkv_w"), o_ls=lstride("e.o_w"), gu_ls=lstride("e.gu_w"),
                          down_ls=lstride("e.down_w"), kc_ls=Tpad * HD, vct_ls=HD * TpadK))
