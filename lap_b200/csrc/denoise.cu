@@ -31,6 +31,7 @@
 #include "common.cuh"
 #include "host_util.h"
 #include <stdlib.h>
+#include <string.h>
 #include <algorithm>
 
 namespace lapb {
@@ -86,18 +87,40 @@ struct GridBarrier {
   unsigned* error;
   unsigned target;
   unsigned nblocks;
-  __device__ __forceinline__ void sync() {
+  // light: release-RMW arrive + relaxed polling (MEMBAR.ALL.GPU, no CCTL.IVALL).  The strong form (fence.sc + ld.acquire)
+  // invalidates the SM's L1 on both sides of every barrier, which turns each register-spill reload and each cached
+  // parameter read after the barrier into an L2 round trip.  The light form is sufficient HERE because every value that one
+  // CTA writes and another reads inside the loop travels through L2-only accesses (cp.async.cg / ld.global.cg), never L1.
+  bool light;
+  // arrive() / wait() split the barrier so that loads issued between the two (weights of the next phase) are not ahead of
+  // the releasing fence in thread 0's program order
+  __device__ __forceinline__ void arrive() {
     __syncthreads();
     if (threadIdx.x == 0) {
       target += nblocks;
-      __threadfence();
-      asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+      if (light) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+      } else {
+        __threadfence();
+        asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+      }
+    }
+  }
+  __device__ __forceinline__ void sync() {
+    arrive();
+    wait();
+  }
+  __device__ __forceinline__ void wait() {
+    if (threadIdx.x == 0) {
       unsigned v, spins = 0;
       do {
-        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        if (light)
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        else
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         if ((++spins & 1023u) == 0) {  // a barrier that cannot complete must not hang the GPU: flag it and fall through
           unsigned e;
-          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(error) : "memory");
+          asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(e) : "l"(error) : "memory");
           if (e != 0 || spins > (1u << 21)) {
             atomicExch(error, 1u);
             break;
@@ -300,20 +323,25 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t4 = lane & 3;
   const int tslot = warp >> 3, kpart = warp & 7;
-  GridBarrier bar{p.sync, p.sync + 1, 0u, gridDim.x};
+  GridBarrier bar{p.sync, p.sync + 1, 0u, gridDim.x, false};
   __shared__ int fold_last;
-  // optional phase profile (CTA 0, thread 0): nanoseconds accumulated per phase slot
+  // optional phase profile (thread 0 of EVERY CTA; row blockIdx.x of p.prof[grid][32]): nanoseconds per phase slot,
+  // accumulated in shared memory (a global read-modify-write per tick would stall the in-order warp ~0.5 us each time)
+  __shared__ unsigned long long prof_s[32];
   unsigned long long prof_last = 0;
-  const bool prof_on = p.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  const bool prof_on = p.prof != nullptr && threadIdx.x == 0;
+  if (prof_on)
+    for (int i = 0; i < 32; ++i) prof_s[i] = 0;
   auto tick = [&](int slot) {
     if (prof_on) {
       unsigned long long now;
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-      if (slot >= 0) p.prof[slot] += now - prof_last;
+      if (slot >= 0) prof_s[slot] += now - prof_last;
       prof_last = now;
     }
   };
   tick(-1);
+  const bool split = (p.flags & 2) == 0, spread = (p.flags & 4) != 0;  // flags 0 = measured best
   const bf16* mod = reinterpret_cast<const bf16*>(p.mod);
   bf16* XE = reinterpret_cast<bf16*>(p.XE);
   bf16* XE1 = reinterpret_cast<bf16*>(p.XE1);
@@ -425,15 +453,20 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       const bf16* mod_a = mod_sm;           // [scale | shift | gate] of the attention norm
       const bf16* mod_f = mod_sm + 3 * D1;  // ... of the ffn norm
 
+      // Optional L2 prefetch of this CTA's weight slices of the NEXT layer (next step's layer 0 after the last one).  flags
+      // bit 0: all four matrices at the top of P1 (one 34.6 MB burst per layer: measured 6 % slower than no prefetch, the small
+      // dependent loads queue behind it); bit 2 (`spread`): each phase prefetches its own matrix of the next layer once its
+      // staging loads have landed (neutral).  Both off by default (profiles/r02_denoise_loop.md).
+      const int ln = (l + 1 < L) ? l + 1 : 0;
+      const bool have_next = (l + 1 < L || step + 1 < S);
+      const bf16* nq = reinterpret_cast<const bf16*>(p.qkv_w) + (long)ln * p.qkv_ls;
+      const bf16* no = reinterpret_cast<const bf16*>(p.o_w) + (long)ln * p.o_ls;
+      const bf16* ng = reinterpret_cast<const bf16*>(p.gu_w) + (long)ln * p.gu_ls;
+      const bf16* nd = reinterpret_cast<const bf16*>(p.down_w) + (long)ln * p.down_ls;
+
       // ---------------- P1: h = adaRMS(XE); qkv = h Wqkv^T ----------------
-      {  // L2 prefetch of this CTA's weight slices of the NEXT layer (next step's layer 0 after the last one): the HBM
-         // traffic of a layer is spread over the whole previous layer instead of arriving as one burst per phase
-        const int ln = (l + 1 < L) ? l + 1 : 0;
-        if ((l + 1 < L || step + 1 < S) && !(p.flags & 1)) {
-          const bf16* nq = reinterpret_cast<const bf16*>(p.qkv_w) + (long)ln * p.qkv_ls;
-          const bf16* no = reinterpret_cast<const bf16*>(p.o_w) + (long)ln * p.o_ls;
-          const bf16* ng = reinterpret_cast<const bf16*>(p.gu_w) + (long)ln * p.gu_ls;
-          const bf16* nd = reinterpret_cast<const bf16*>(p.down_w) + (long)ln * p.down_ls;
+      {
+        if (have_next && (p.flags & 1)) {
           if (q_te > q_tb) dn_prefetch_l2(nq + (long)q_tb * 8 * D1, (long)(q_te - q_tb) * 8 * D1 * 2, 0);
           if (o_te > o_tb) dn_prefetch_l2(no + (long)o_tb * 8 * OD, (long)(o_te - o_tb) * 8 * OD * 2, 8);
           if (f_pe > f_pb) {
@@ -447,6 +480,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       dn_stage(mod_s + (long)(2 * l) * 3 * D1, 0, mod_sm, 0, 1, 6 * D1);
       dn_cp_wait_all();
       __syncthreads();
+      if (spread && have_next && q_te > q_tb) dn_prefetch_l2(nq + (long)q_tb * 8 * D1, (long)(q_te - q_tb) * 8 * D1 * 2, 0);
       tick(16);
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_a);
       __syncthreads();
@@ -484,11 +518,13 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
                        ? *reinterpret_cast<const uint4*>(VcT + (long)(warp * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32)
                        : zero4;
       };
+      if (split) bar.arrive();
       if (item0_prefix) load_kv((item0 % NCH) * DN_CK);
       tick(20);
       tick(2);
-      bar.sync();
+      if (split) bar.wait(); else bar.sync();
       tick(3);
+      if (spread && have_next && o_te > o_tb) dn_prefetch_l2(no + (long)o_tb * 8 * OD, (long)(o_te - o_tb) * 8 * OD * 2, 0);
 
       // ---------------- P2: attention partials, item = (head, key chunk) ----------------
       for (int item = blockIdx.x; item < NH * NCH; item += gridDim.x) {
@@ -681,10 +717,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       // P3's weights (one n8 tile of Wo per CTA, K split over all 32 warps): in flight across the barrier
       uint4 w3[2];
       const bf16* wt3 = o_te > o_tb ? Wo + (long)o_tb * 8 * OD : nullptr;
+      if (split) bar.arrive();
       dn_load_w<2>(w3, wt3, OD, ngo, warp, DN_WARPS);
       tick(22);
       tick(6);
-      bar.sync();
+      if (split) bar.wait(); else bar.sync();
       tick(7);
 
       // ---------------- P3: XE1 = XE + gate_a * (O Wo^T) ----------------
@@ -700,7 +737,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           if (t0 + 1 < o_te) {
             wt3 = Wo + (long)(t0 + 1) * 8 * OD;
             dn_load_w<2>(w3, wt3, OD, ngo, warp, DN_WARPS);
-          } else {
+          } else if (!split) {
             dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);  // P4's first pass
           }
           if (threadIdx.x < 16 * 8) {
@@ -715,17 +752,27 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
           }
           __syncthreads();
         }
-      } else {
+      } else if (!split) {
         dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);
       }
       tick(8);
-      bar.sync();
+      if (split) {
+        bar.arrive();
+        dn_load_w<4>(w4, wt4, D1, ng1, kpart, 8);
+        bar.wait();
+      } else {
+        bar.sync();
+      }
       tick(9);
 
       // ---------------- P4: h = adaRMS(XE1); act = gelu(h Wg^T) * (h Wu^T) ----------------
       dn_stage(XE1, D1, xe_s, D1, A, D1);
       dn_cp_wait_all();
       __syncthreads();
+      if (spread && have_next && f_pe > f_pb) {
+        dn_prefetch_l2(ng + (long)f_pb * 8 * D1, (long)(f_pe - f_pb) * 8 * D1 * 2, 0);
+        dn_prefetch_l2(ng + ((long)F1 + (long)f_pb * 8) * D1, (long)(f_pe - f_pb) * 8 * D1 * 2, 8);
+      }
       tick(28);
       dn_ada_norm(xe_s, h_s, ldh, A, D1, mod_f);
       __syncthreads();
@@ -750,9 +797,10 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
       // P5's tile of Wd (K split over all 32 warps): in flight across the barrier
       uint4 w5[4];
       const bf16* wt5 = o_te > o_tb ? Wd + (long)o_tb * 8 * F1 : nullptr;
+      if (split) bar.arrive();
       dn_load_w<4>(w5, wt5, F1, ngf, warp, DN_WARPS);
       tick(10);
-      bar.sync();
+      if (split) bar.wait(); else bar.sync();
       tick(11);
 
       // ---------------- P5: XE = XE1 + gate_f * (act Wd^T) ----------------
@@ -760,6 +808,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
         dn_stage(act, F1, h_s, ldf, A, F1);
         dn_cp_wait_all();
         __syncthreads();
+        if (spread && have_next) dn_prefetch_l2(nd + (long)o_tb * 8 * F1, (long)(o_te - o_tb) * 8 * F1 * 2, 0);
         for (int t0 = o_tb; t0 < o_te; ++t0) {
           dn_mma_warp<4>(h_s, ldf, A, ngf, warp, DN_WARPS, w5, wt5, F1, red);
           __syncthreads();
@@ -781,12 +830,13 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
         }
       }
       // next layer's qkv tiles: in flight across the barrier (the next step's layer 0 is loaded in the final phase)
+      if (split) bar.arrive();
       if (l + 1 < L) {
         wt1 = qkv_tile(Wqkv + p.qkv_ls, q_tb);
         dn_load_w<4>(w1, wt1, D1, ng1, kpart, 8);
       }
       tick(12);
-      bar.sync();
+      if (split) bar.wait(); else bar.sync();
       tick(13);
     }
 
@@ -814,6 +864,756 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop_kernel(const lapb_
   }
   if (blockIdx.x == 0)
     for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) p.x[i] = x_s[i];
+  if (prof_on)
+    for (int i = 0; i < 32; ++i) p.prof[(long)blockIdx.x * 32 + i] += prof_s[i];
+}
+
+// ======================================================================================================================
+// K10 v2 — the same grid-wide Euler loop, restructured after the per-CTA phase profile of round 2
+// (profiles/r02_denoise_loop.md §4).  What the profile showed about the kernel above:
+//   * 1024 threads cap the kernel at 64 registers, so the weight fragments "preloaded into registers across the barrier"
+//     were spilled: the thread waited for the HBM load to land in order to store it to local memory — the latency the
+//     preload was meant to hide sat on the critical path of every phase (1.6-3.5 us at five sites per layer);
+//   * fence.sc + ld.acquire invalidate the L1 on both sides of every barrier, so each spill reload / parameter read after
+//     a barrier was an L2 round trip;
+//   * the chunk combine walked 12 chunks x 3 dependent L2 loads per output (3 us); the adaRMS norms used 10 of 32 warps.
+// Changes (arithmetic and rounding points unchanged, only fp32 summation orders of the norm statistic / chunk combine /
+// action_out_proj differ):
+//   * weights and K/V fragments travel global -> shared with cp.async into per-THREAD private 16-byte slots (`wbuf`:
+//     [warp][4][lane]): nothing is held in registers, the copy is issued right after the slot's last read and waited for
+//     with the staging loads of the phase that consumes it; both gate/up passes of P4 are in flight at once (second
+//     buffer in the idle part of `big`);
+//   * light grid barrier (red.release + relaxed polling: no L1 invalidation), arrive/wait split, copies issued between;
+//   * chunk combine: 4 lanes per 4 outputs, chunks strided over the lanes (one L2 latency, 5 live warps); the suffix
+//     chunk of a head (CUDA cores, the straggler of P2) is split by query rows over the CTAs without a prefix chunk;
+//   * adaRMS norm on 2 warps per row; action_in_proj with a thread per column; activations staged with A rows
+//     (not 16) and 64-byte row padding (conflict-free A-fragment reads).
+// p.flags (experiments): bit 1 strong barrier (fence.sc + ld.acquire).
+constexpr int DN2_PAD = 32;                                    // bf16 elements: rows 64 B apart modulo 128 B
+constexpr size_t DN2_WBUF = (size_t)DN_WARPS * 4 * 32 * 16;    // 64 KB: [warp][slot 0..3][lane] uint4
+
+__host__ __device__ inline size_t dn2_h_bytes(int rows, int D1) { return dn_align16((size_t)rows * (D1 + DN2_PAD) * 2); }
+// region holding, in turn: normalised rows h (+ the second weight buffer behind them: P4, modulation GEMM), attention
+// scratch (P2), staged O (P3), staged act (P5)
+__host__ __device__ inline size_t dn2_big_bytes(int A, int D1, int HD, int OD, int F1) {
+  size_t b = dn2_h_bytes(A, D1) + DN2_WBUF;
+  const size_t a = dn_attn_bytes(HD), o = (size_t)A * (OD + DN2_PAD) * 2, f = (size_t)A * (F1 + DN2_PAD) * 2;
+  b = b > a ? b : a;
+  b = b > o ? b : o;
+  b = b > f ? b : f;
+  return dn_align16(b);
+}
+__host__ __device__ inline size_t dn2_xe_bytes(int A, int D1) { return dn_align16((size_t)A * D1 * 2); }  // [A][D1] bf16
+// xe_s | big; the prologue lays its own buffers over both: fp32 [S][D1] time embedding (T1, T2), then the staged cond16
+// rows [S][D1+PAD] followed by the second weight buffer (T3)
+__host__ __device__ inline size_t dn2_act_bytes(int A, int S, int D1, int HD, int OD, int F1) {
+  size_t act = dn2_xe_bytes(A, D1) + dn2_big_bytes(A, D1, HD, OD, F1);
+  const size_t pro = dn_align16((size_t)S * D1 * 4), t3 = dn2_h_bytes(S, D1) + DN2_WBUF;
+  act = act > pro ? act : pro;
+  act = act > t3 ? act : t3;
+  return act;
+}
+__host__ __device__ inline size_t dn2_smem_bytes(int A, int S, int D1, int HD, int OD, int F1) {
+  // xe_s | big | wbuf | red | x_s | rope table | mod rows (attn + ffn) | mask bits
+  const size_t act = dn2_act_bytes(A, S, D1, HD, OD, F1);
+  return act + DN2_WBUF + (size_t)8 * 4 * 32 * 4 * 4 + (size_t)16 * 32 * 4 + (size_t)16 * (HD / 2) * 8 + (size_t)6 * D1 * 2 +
+         (size_t)16 * 32 * 4 + 16;
+}
+
+__device__ __forceinline__ void dn2_cp16_zfill(void* smem_dst, const void* gsrc, bool ok) {
+  if (ok)
+    dn_cp16(smem_dst, gsrc);
+  else
+    *reinterpret_cast<uint4*>(smem_dst) = make_uint4(0, 0, 0, 0);
+}
+// this thread's U fragments of one n8 weight tile (K groups kg_first + kg_stride * u) -> its private slots wme[u * 32]
+template <int U>
+__device__ __forceinline__ void dn2_issue_w(uint4* wme, const bf16* wtile, long ldw, int ngroups, int kg_first,
+                                            int kg_stride) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    const int kg = kg_first + kg_stride * u;
+    const bool ok = wtile != nullptr && kg < ngroups;
+    dn2_cp16_zfill(wme + u * 32, ok ? wtile + (long)g * ldw + 8 * t + kg * 32 : nullptr, ok);
+  }
+}
+// as dn_mma_warp, B fragments from the thread's slots (the caller has waited for the copies of the first K batch)
+template <int U>
+__device__ __forceinline__ void dn2_mma_warp(const bf16* As, int lda, int M, int ngroups, int kg_first, int kg_stride,
+                                             uint4* wme, const bf16* wtile, long ldw, float* red) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const bf16* xlo = As + (long)g * lda + 8 * t;
+  const bf16* xhi = As + (long)(g + 8) * lda + 8 * t;
+  const bool vlo = g < M, vhi = (g + 8) < M;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  for (int base = kg_first; base < ngroups; base += kg_stride * U) {
+    if (base != kg_first) {  // K longer than one batch (not the case at LAP-3B sizes): refill the slots and wait
+      dn2_issue_w<U>(wme, wtile, ldw, ngroups, base, kg_stride);
+      dn_cp_wait_all();
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int kg = base + kg_stride * u;
+      if (kg < ngroups) {
+        const uint4 b = wme[u * 32];
+        const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(xlo + kg * 32) : zero;
+        const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(xhi + kg * 32) : zero;
+        dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, b.x, b.y);
+        dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, b.z, b.w);
+      }
+    }
+  }
+  *reinterpret_cast<float4*>(red + ((((warp & 7) * 4 + (warp >> 3)) * 32 + lane) << 2)) =
+      make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// adaptive RMSNorm (see dn_ada_norm) on 2 warps per row: warp = (row m = warp >> 1, column half warp & 1); `scratch` holds
+// the 2A partial sums of squares.  Contains one __syncthreads().
+__device__ __forceinline__ void dn2_ada_norm(const bf16* xe_s, bf16* h_s, int ldh, int A, int D1, const bf16* mod_row,
+                                             float* scratch) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m = warp >> 1, c0 = (warp & 1) * (D1 >> 1), c1 = c0 + (D1 >> 1);
+  float s2 = 0.f;
+  if (m < A) {
+    for (int c = c0 + lane * 8; c < c1; c += 256) {
+      float v[8];
+      dn_unpack8(*reinterpret_cast<const uint4*>(xe_s + (long)m * D1 + c), v);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s2 += v[j] * v[j];
+    }
+  }
+  s2 = warp_sum(s2);
+  if (lane == 0) scratch[warp] = s2;
+  __syncthreads();
+  if (m < A) {
+    const float rstd = rsqrtf((scratch[2 * m] + scratch[2 * m + 1]) / D1 + 1e-6f);
+    for (int c = c0 + lane * 8; c < c1; c += 256) {
+      float v[8], sc[8], sh[8], o[8];
+      dn_unpack8(*reinterpret_cast<const uint4*>(xe_s + (long)m * D1 + c), v);
+      dn_unpack8(*reinterpret_cast<const uint4*>(mod_row + c), sc);
+      dn_unpack8(*reinterpret_cast<const uint4*>(mod_row + D1 + c), sh);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o[j] = (v[j] * rstd) * bf16r(1.0f + sc[j]) + sh[j];
+      *reinterpret_cast<uint4*>(h_s + (long)m * ldh + c) = dn_pack8(o);
+    }
+  }
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb_denoise_params_t p) {
+  extern __shared__ __align__(16) unsigned char dn_smem[];
+  const int A = p.A, ad = p.ad, D1 = p.D1, NH = p.NH, HD = p.HD, F1 = p.F1, L = p.L, Pn = p.Pn, W32 = p.W32;
+  const int QKV = (NH + 2) * HD, OD = NH * HD, nm3 = p.nm * 3 * D1, S = p.num_steps;
+  const int ldh = D1 + DN2_PAD, ldo = OD + DN2_PAD, ldf = F1 + DN2_PAD, ldq = HD + 8, ldp = DN_CK + 8, half = HD / 2;
+  // ---- shared memory ----
+  bf16* xe_s = reinterpret_cast<bf16*>(dn_smem);                                     // [A][D1] residual stream copy
+  unsigned char* big = dn_smem + dn2_xe_bytes(A, D1);
+  bf16* h_s = reinterpret_cast<bf16*>(big);                                           // [A][D1+PAD] / staged O / staged act
+  unsigned char* wbuf_b = dn_smem + dn2_act_bytes(A, S, D1, HD, OD, F1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  uint4* wme = reinterpret_cast<uint4*>(wbuf_b) + warp * 128 + lane;                                   // slots wme[u * 32]
+  uint4* wme2 = reinterpret_cast<uint4*>(big + dn2_h_bytes(A, D1)) + warp * 128 + lane;                // second buffer
+  float* red = reinterpret_cast<float*>(wbuf_b + DN2_WBUF);                           // [8][4][32][4]
+  float* x_s = red + 8 * 4 * 32 * 4;                                                  // [16*32] x_t
+  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);                          // [16][HD/2] (cos, sin)
+  bf16* mod_sm = reinterpret_cast<bf16*>(rope_s + 16 * half);                         // [2][3*D1]: attn-norm, ffn-norm rows
+  uint32_t* bits_s = reinterpret_cast<uint32_t*>(mod_sm + 6 * D1);                    // [16][32]
+  float* te_s = reinterpret_cast<float*>(dn_smem);                                    // prologue only
+  // attention scratch (inside `big`)
+  bf16* q_s = reinterpret_cast<bf16*>(big);                                           // [16][HD+8]
+  float* s_s = reinterpret_cast<float*>(q_s + 16 * ldq);                              // [16][64]
+  bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * DN_CK);                              // [16][72]
+  float* ks_s = reinterpret_cast<float*>(p_s + 16 * ldp);                             // [16][HD]
+  bf16* qraw = reinterpret_cast<bf16*>(ks_s + 16 * HD);                               // [16][HD] x3
+  bf16* kraw = qraw + 16 * HD;
+  bf16* vraw = kraw + 16 * HD;
+  float* sp_s = reinterpret_cast<float*>(vraw + 16 * HD);                             // [4][16][64] S partials (K quarters)
+
+  const int g = lane >> 2, t4 = lane & 3;
+  const int tslot = warp >> 3, kpart = warp & 7;
+  GridBarrier bar{p.sync, p.sync + 1, 0u, gridDim.x, (p.flags & 2) == 0};
+  // (the next phase's copies are issued AFTER the arrive: issued before it, by the warps that do not hold the releasing
+  //  thread, the loop is 4 % slower — the releasing MEMBAR also drains the copies in flight)
+  // optional phase profile: thread 0 of every CTA, row blockIdx.x of p.prof[grid][32], accumulated in shared memory
+  __shared__ unsigned long long prof_s[32];
+  unsigned long long prof_last = 0;
+  const bool prof_on = PROF && p.prof != nullptr && threadIdx.x == 0;
+  if (PROF && prof_on)
+    for (int i = 0; i < 32; ++i) prof_s[i] = 0;
+  auto tick = [&](int slot) {
+    if (PROF && prof_on) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (slot >= 0) prof_s[slot] += now - prof_last;
+      prof_last = now;
+    }
+  };
+  tick(-1);
+  const bf16* mod = reinterpret_cast<const bf16*>(p.mod);
+  bf16* XE = reinterpret_cast<bf16*>(p.XE);
+  bf16* XE1 = reinterpret_cast<bf16*>(p.XE1);
+  bf16* qkv = reinterpret_cast<bf16*>(p.qkv);
+  bf16* Obuf = reinterpret_cast<bf16*>(p.O);
+  bf16* act = reinterpret_cast<bf16*>(p.act);
+  const int NCHP = (Pn + DN_CK - 1) / DN_CK, NCH = NCHP + 1;
+  const int nprefix = NH * NCHP;
+  int sfx_rows, sfx_blocks;  // suffix chunk of a head: sfx_blocks items of sfx_rows query rows
+  {
+    int r = ((int)gridDim.x > nprefix) ? ((int)gridDim.x - nprefix) / NH : 1;
+    r = r < 1 ? 1 : (r > A ? A : r);
+    sfx_rows = (A + r - 1) / r;
+    sfx_blocks = (A + sfx_rows - 1) / sfx_rows;
+  }
+  const uint4 zero4 = make_uint4(0, 0, 0, 0);
+  const int ng1 = D1 >> 5, ngo = OD >> 5, ngf = F1 >> 5;
+
+  // this CTA's share of every phase (contiguous n8 tiles / GeGLU pairs / attention item)
+  int q_tb, q_te, o_tb, o_te, f_pb, f_pe;
+  dn_range(QKV / 8, q_tb, q_te);
+  dn_range(D1 / 8, o_tb, o_te);
+  dn_range(F1 / 8, f_pb, f_pe);
+  // this warp's weight tile in a tile-mode pass
+  auto qkv_tile = [&](const bf16* W, int t0) { return (t0 + tslot < q_te) ? W + (long)(t0 + tslot) * 8 * D1 : nullptr; };
+  auto gu_tile = [&](const bf16* W, int p0) {  // slots: gate p0, up p0, gate p0+1, up p0+1
+    const int pr = p0 + (tslot >> 1);
+    return (pr < f_pe) ? W + ((long)(tslot & 1) * F1 + (long)pr * 8) * D1 : nullptr;
+  };
+  // K / V^T fragments of a 64-key prefix chunk -> slots 0,1 (S tile: warp = (key tile kpart, head-dim quarter tslot)) and
+  // 2,3 (P V: warp = n8 tile of the head dims).  (cp.async with an L2 evict_last cache hint for these 13 MB faults with
+  // "illegal instruction" on sm_100a under CUDA 12.9 — plain copies.)
+  auto issue_kv = [&](const bf16* Kc, const bf16* VcT, int key0) {
+    const bf16* kr = Kc + (long)(key0 + 8 * kpart + g) * HD + 8 * t4;
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int kg = tslot + 4 * u;
+      if (kg < HD / 32) {
+        dn_cp16(wme + u * 32, kr + kg * 32);
+      } else {
+        wme[u * 32] = zero4;
+      }
+    }
+#pragma unroll
+    for (int kg = 0; kg < 2; ++kg) {
+      if (warp < HD / 8) {
+        const bf16* vr = VcT + (long)(warp * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32;
+        dn_cp16(wme + (2 + kg) * 32, vr);
+      } else {
+        wme[(2 + kg) * 32] = zero4;
+      }
+    }
+  };
+
+  // =========================== prologue: time conditioning of every step ===========================
+  {
+    // T1: time_emb (pi0.py:47-63) for all steps, then s1 = swish(time_mlp_in(time_emb))
+    const int halfw = D1 / 2;
+    for (int i = threadIdx.x; i < S * halfw; i += DN_THREADS) {
+      const int r = i / halfw, c = i % halfw;
+      const float fraction = (halfw > 1) ? (float)c / (float)(halfw - 1) : 0.f;
+      const float period = 4e-3f * powf(4.0f / 4e-3f, fraction);
+      const float inp = p.times[r] * (1.0f / period * 2.0f * 3.14159265358979323846f);
+      float sn, cs;
+      sincosf(inp, &sn, &cs);
+      te_s[r * D1 + c] = sn;
+      te_s[r * D1 + halfw + c] = cs;
+    }
+    __syncthreads();
+    dn_time_mlp(te_s, S, D1, p.tin_w, p.tin_b, p.s1, nullptr);
+    bar.sync();
+    // T2: cond = swish(time_mlp_out(s1)) -> cond16
+    for (int i = threadIdx.x; i < S * D1; i += DN_THREADS) te_s[i] = __ldcg(p.s1 + i);
+    __syncthreads();
+    dn_time_mlp(te_s, S, D1, p.tout_w, p.tout_b, nullptr, reinterpret_cast<bf16*>(p.cond16));
+    bar.sync();
+    // T3: mod = cond16 @ mod_w^T + mod_b  (rows = steps); passes alternate between the two weight buffers, two in flight
+    bf16* h3 = reinterpret_cast<bf16*>(dn_smem);                                      // [S][D1+PAD] staged cond16
+    uint4* wme3 = reinterpret_cast<uint4*>(dn_smem + dn2_h_bytes(S, D1)) + warp * 128 + lane;
+    dn_stage(reinterpret_cast<const bf16*>(p.cond16), D1, h3, ldh, S, D1);
+    int tb, te;
+    dn_range(nm3 / 8, tb, te);
+    const bf16* mw = reinterpret_cast<const bf16*>(p.mod_w);
+    auto mod_tile = [&](int t0) { return (t0 + tslot < te) ? mw + (long)(t0 + tslot) * 8 * D1 : nullptr; };
+    if (tb < te) dn2_issue_w<4>(wme, mod_tile(tb), D1, ng1, kpart, 8);
+    if (tb + 4 < te) dn2_issue_w<4>(wme3, mod_tile(tb + 4), D1, ng1, kpart, 8);
+    dn_cp_wait_all();
+    __syncthreads();
+    int pass = 0;
+    for (int t0 = tb; t0 < te; t0 += 4, ++pass) {
+      uint4* wb = (pass & 1) ? wme3 : wme;
+      dn2_mma_warp<4>(h3, ldh, S, ng1, kpart, 8, wb, mod_tile(t0), D1, red);
+      if (t0 + 8 < te) dn2_issue_w<4>(wb, mod_tile(t0 + 8), D1, ng1, kpart, 8);  // refill: consumed two passes from now
+      __syncthreads();
+      if (threadIdx.x < 16 * 32) {
+        const int e = threadIdx.x, m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
+        if (m < S && t0 + tile < te) {
+          const int n = (t0 + tile) * 8 + cc;
+          const float v = bf16r(dn_tile_val(red, tile, m, cc, false)) + bf16r(p.mod_b[n]);
+          reinterpret_cast<bf16*>(p.mod)[(long)m * nm3 + n] = __float2bfloat16_rn(v);
+        }
+      }
+      // the next pass's weights were issued one pass ago; cp.async completes in order, so allow the refill just issued
+      // to stay in flight: wait_group needs commit groups, so simply wait for everything except when a refill was issued
+      if (t0 + 8 < te) {
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+      } else {
+        dn_cp_wait_all();
+      }
+      __syncthreads();
+    }
+    // x_t <- noise; (cos, sin) of the suffix positions and the mask words (constant over steps and layers)
+    for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) x_s[i] = p.x[i];
+    for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+      const int m = i / half, d = i % half;
+      float sn, cs;
+      sincosf((float)p.pos[m] / p.timescale[d], &sn, &cs);
+      rope_s[i] = make_float2(cs, sn);
+    }
+    for (int i = threadIdx.x; i < A * W32; i += DN_THREADS) bits_s[(i / W32) * 32 + (i % W32)] = p.bits[i];
+    bar.arrive();
+    // Wqkv tiles of layer 0: in flight across the barrier and action_in_proj
+    dn2_issue_w<4>(wme, qkv_tile(reinterpret_cast<const bf16*>(p.qkv_w), q_tb), D1, ng1, kpart, 8);
+    bar.wait();
+    tick(0);
+  }
+
+  // =========================== Euler loop ===========================
+  for (int step = 0; step < S; ++step) {
+    const bf16* mod_s = mod + (long)step * nm3;
+    // XE = bf16(action_in_proj(x_t)) (pi0.py:159), every CTA holds the full copy; thread = output column
+    for (int n = threadIdx.x; n < D1; n += DN_THREADS) {
+      float acc[16];
+#pragma unroll
+      for (int m = 0; m < 16; ++m) acc[m] = 0.f;
+      for (int j0 = 0; j0 < ad; j0 += 8) {  // (the L1 is ~6 KB next to 222 KB of shared memory: these are L2 reads)
+        float wv[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) wv[jj] = (j0 + jj < ad) ? __ldg(p.ain_w + (long)n * ad + j0 + jj) : 0.f;
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+          if (j0 + jj < ad) {
+#pragma unroll
+            for (int m = 0; m < 16; ++m)
+              if (m < A) acc[m] += x_s[m * ad + j0 + jj] * wv[jj];
+          }
+        }
+      }
+      const float bv = __ldg(p.ain_b + n);
+#pragma unroll
+      for (int m = 0; m < 16; ++m)
+        if (m < A) xe_s[m * D1 + n] = __float2bfloat16_rn(acc[m] + bv);
+    }
+    __syncthreads();
+    tick(1);
+
+    for (int l = 0; l < L; ++l) {
+      const bf16* Wqkv = reinterpret_cast<const bf16*>(p.qkv_w) + (long)l * p.qkv_ls;
+      const bf16* mod_a = mod_sm;           // [scale | shift | gate] of the attention norm
+      const bf16* mod_f = mod_sm + 3 * D1;  // ... of the ffn norm
+
+      // ---------------- P1: h = adaRMS(XE); qkv = h Wqkv^T ----------------
+      if (l > 0) dn_stage(XE, D1, xe_s, D1, A, D1);
+      dn_stage(mod_s + (long)(2 * l) * 3 * D1, 0, mod_sm, 0, 1, 6 * D1);
+      dn_cp_wait_all();  // + this CTA's Wqkv fragments, issued before the previous barrier
+      __syncthreads();
+      tick(16);
+      dn2_ada_norm(xe_s, h_s, ldh, A, D1, mod_a, red);
+      __syncthreads();
+      tick(17);
+      for (int t0 = q_tb; t0 < q_te; t0 += 4) {
+        dn2_mma_warp<4>(h_s, ldh, A, ng1, kpart, 8, wme, qkv_tile(Wqkv, t0), D1, red);
+        const bool more = t0 + 4 < q_te;
+        if (more) dn2_issue_w<4>(wme, qkv_tile(Wqkv, t0 + 4), D1, ng1, kpart, 8);
+        __syncthreads();
+        tick(18);
+        if (threadIdx.x < 16 * 32) {
+          const int e = threadIdx.x, m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
+          if (m < A && t0 + tile < q_te)
+            qkv[(long)m * QKV + (t0 + tile) * 8 + cc] = __float2bfloat16_rn(dn_tile_val(red, tile, m, cc, false));
+        }
+        if (more) {
+          dn_cp_wait_all();
+          __syncthreads();
+        }
+      }
+      tick(19);
+      // this CTA's attention item: the K / V^T fragments of its key chunk do not depend on this step -> copy them now.
+      // Items: (head, prefix chunk) for item < nprefix, then (head, block of query rows) of the suffix keys — the suffix
+      // chunk runs on CUDA cores and would be the straggler of the phase as ONE item per head; its rows are independent
+      // (per-row softmax statistics), so it is split over the CTAs the prefix chunks leave idle.
+      const int item0 = blockIdx.x;
+      const bool item0_prefix = item0 < nprefix;
+      {
+        const bf16* Kc = reinterpret_cast<const bf16*>(p.Kc) + (long)l * p.kc_ls;
+        const bf16* VcT = reinterpret_cast<const bf16*>(p.VcT) + (long)l * p.vct_ls;
+        bar.arrive();
+        if (item0_prefix) issue_kv(Kc, VcT, (item0 % NCHP) * DN_CK);
+        tick(20);
+        tick(2);
+        bar.wait();
+        tick(3);
+      }
+
+      // ---------------- P2: attention partials, item = (head, key chunk) ----------------
+      for (int item = blockIdx.x; item < nprefix + NH * sfx_blocks; item += gridDim.x) {
+        const bool prefix = item < nprefix;
+        const int h = prefix ? item / NCHP : (item - nprefix) / sfx_blocks, c = prefix ? item % NCHP : NCHP;
+        const int r0 = prefix ? 0 : ((item - nprefix) % sfx_blocks) * sfx_rows;  // suffix item: query rows [r0, r1)
+        const int r1 = prefix ? A : min(A, r0 + sfx_rows);
+        __syncthreads();
+        dn_stage(qkv + h * HD, QKV, qraw, HD, A, HD);
+        if (!prefix) {
+          dn_stage(qkv + NH * HD, QKV, kraw, HD, A, HD);
+          dn_stage(qkv + (NH + 1) * HD, QKV, vraw, HD, A, HD);
+        } else if (item != item0) {  // (only when there are more items than CTAs)
+          issue_kv(reinterpret_cast<const bf16*>(p.Kc) + (long)l * p.kc_ls,
+                   reinterpret_cast<const bf16*>(p.VcT) + (long)l * p.vct_ls, c * DN_CK);
+        }
+        dn_cp_wait_all();
+        __syncthreads();
+        tick(24);
+        // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ) (gemma.py:215-218, 548-564); suffix item: ks_s <- bf16(rope(k))
+        for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
+          const int m = i / half, d = i % half;
+          const float cs = rope_s[i].x, sn = rope_s[i].y;
+          const float x1 = __bfloat162float(qraw[m * HD + d]), x2 = __bfloat162float(qraw[m * HD + half + d]);
+          q_s[m * ldq + d] = __float2bfloat16_rn(bf16r(x1 * cs - x2 * sn) * p.qscale);
+          q_s[m * ldq + half + d] = __float2bfloat16_rn(bf16r(x2 * cs + x1 * sn) * p.qscale);
+          if (!prefix) {
+            const float k1 = __bfloat162float(kraw[m * HD + d]), k2 = __bfloat162float(kraw[m * HD + half + d]);
+            ks_s[m * HD + d] = bf16r(k1 * cs - k2 * sn);
+            ks_s[m * HD + half + d] = bf16r(k2 * cs + k1 * sn);
+          }
+        }
+        __syncthreads();
+        tick(25);
+        float* po = p.part_o + (long)(h * NCH + c) * 16 * HD;
+        float* pml = p.part_ml + (long)(h * NCH + c) * 16 * 2;
+        if (prefix) {
+          // ---- prefix chunk: keys [key0, key0 + 64) of the cache, tensor cores ----
+          const int key0 = c * DN_CK;
+          {  // S partial tile: warp (kpart, tslot) -> keys key0 + 8*kpart .. + 8, head-dim groups tslot, tslot + 4
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+            const bool vlo = g < A, vhi = (g + 8) < A;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              const int kg = tslot + 4 * u;
+              if (kg < HD / 32) {
+                const uint4 kf = wme[u * 32];
+                const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(q_s + g * ldq + kg * 32 + 8 * t4) : zero4;
+                const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(q_s + (g + 8) * ldq + kg * 32 + 8 * t4) : zero4;
+                dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, kf.x, kf.y);
+                dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, kf.z, kf.w);
+              }
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = g + (j >> 1) * 8, kk = 8 * kpart + 2 * t4 + (j & 1);
+              sp_s[(tslot * 16 + m) * DN_CK + kk] = acc[j];
+            }
+          }
+          __syncthreads();
+          tick(26);
+          // chunk-local softmax: warp m -> row m; lane -> keys lane, lane+32 (sum of the 4 K-quarter partials, mask)
+          if (warp < A) {
+            const int m = warp;
+            float v0 = 0.f, v1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              v0 += sp_s[(q * 16 + m) * DN_CK + lane];
+              v1 += sp_s[(q * 16 + m) * DN_CK + 32 + lane];
+            }
+            const int k0 = key0 + lane, k1 = key0 + 32 + lane;
+            const bool ok0 = k0 < Pn && ((bits_s[m * 32 + (k0 >> 5)] >> (k0 & 31)) & 1u);
+            const bool ok1 = k1 < Pn && ((bits_s[m * 32 + (k1 >> 5)] >> (k1 & 31)) & 1u);
+            v0 = ok0 ? v0 : DN_BIG_NEG;
+            v1 = ok1 ? v1 : DN_BIG_NEG;
+            const float mx = warp_max(fmaxf(v0, v1));
+            const float e0 = __expf(v0 - mx), e1 = __expf(v1 - mx);
+            const float sum = warp_sum(e0 + e1);
+            p_s[m * ldp + lane] = __float2bfloat16_rn(e0);
+            p_s[m * ldp + 32 + lane] = __float2bfloat16_rn(e1);
+            if (lane == 0) {
+              pml[m * 2] = mx;
+              pml[m * 2 + 1] = sum;
+            }
+          }
+          __syncthreads();
+          tick(27);
+          // O_c = P V : warp w -> n8 tile w of the head dims; K = 64 keys (2 groups)
+          if (warp < HD / 8) {
+            const bool vlo = g < A, vhi = (g + 8) < A;
+            float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int kg = 0; kg < 2; ++kg) {
+              const uint4 vf = wme[(2 + kg) * 32];
+              const uint4 alo = vlo ? *reinterpret_cast<const uint4*>(p_s + g * ldp + kg * 32 + 8 * t4) : zero4;
+              const uint4 ahi = vhi ? *reinterpret_cast<const uint4*>(p_s + (g + 8) * ldp + kg * 32 + 8 * t4) : zero4;
+              dn_mma(acc, alo.x, ahi.x, alo.y, ahi.y, vf.x, vf.y);
+              dn_mma(acc, alo.z, ahi.z, alo.w, ahi.w, vf.z, vf.w);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int m = g + (j >> 1) * 8, d = warp * 8 + 2 * t4 + (j & 1);
+              if (m < A) po[m * HD + d] = acc[j];
+            }
+          }
+        } else {
+          // ---- suffix keys (this step's own A tokens): CUDA cores on shared memory ----
+          for (int pr = warp; pr < (r1 - r0) * A; pr += DN_WARPS) {  // logits: warp per (query a, key a2)
+            const int a = r0 + pr / A, a2 = pr % A;
+            float sacc = 0.f;
+            for (int d = lane; d < HD; d += 32) sacc += __bfloat162float(q_s[a * ldq + d]) * ks_s[a2 * HD + d];
+            sacc = warp_sum(sacc);
+            if (lane == 0) {
+              const int key = Pn + a2;
+              const bool ok = (bits_s[a * 32 + (key >> 5)] >> (key & 31)) & 1u;
+              s_s[a * DN_CK + a2] = ok ? sacc : DN_BIG_NEG;
+            }
+          }
+          __syncthreads();
+          if (warp < r1 - r0) {  // warp -> row a; lane a2 -> key a2 (A <= 16)
+            const int a = r0 + warp;
+            const float v = (lane < A) ? s_s[a * DN_CK + lane] : -3.4e38f;
+            const float mx = warp_max(v);
+            const float e = (lane < A) ? __expf(v - mx) : 0.f;
+            const float sum = warp_sum(e);
+            if (lane < A) s_s[a * DN_CK + lane] = bf16r(e);
+            if (lane == 0) {
+              pml[a * 2] = mx;
+              pml[a * 2 + 1] = sum;
+            }
+          }
+          __syncthreads();
+          for (int i = threadIdx.x; i < (r1 - r0) * HD; i += DN_THREADS) {
+            const int a = r0 + i / HD, d = i % HD;
+            float o = 0.f;
+            for (int a2 = 0; a2 < A; ++a2) o += s_s[a * DN_CK + a2] * __bfloat162float(vraw[a2 * HD + d]);
+            po[a * HD + d] = o;
+          }
+        }
+      }
+      tick(4);
+      // Wo tile of P3 (one n8 tile per CTA, K split over all 32 warps) -> slots 0,1: the K/V fragments are consumed
+      {
+        const bf16* Wo = reinterpret_cast<const bf16*>(p.o_w) + (long)l * p.o_ls;
+        const bf16* wt3 = o_te > o_tb ? Wo + (long)o_tb * 8 * OD : nullptr;
+        bar.arrive();
+        dn2_issue_w<2>(wme, wt3, OD, ngo, warp, DN_WARPS);
+        bar.wait();
+      }
+      tick(5);
+
+      // ---------------- P2b: combine the chunks -> O [A, NH*HD]: 4 lanes per 4 outputs, chunks strided over the lanes ----
+      {
+        const int units = A * (OD >> 2);
+        const int per_cta = (units + gridDim.x - 1) / gridDim.x;
+        const int quad = threadIdx.x >> 2, sub = threadIdx.x & 3;  // with 32 resident warps issue slots, not latency, are
+        for (int u0 = 0; u0 < per_cta; u0 += DN_THREADS / 4) {     // the cost: few threads, 3-5 chunks each
+          if (u0 + (warp << 3) >= per_cta) break;                  // (warp-uniform) no live quad in this warp
+          const int ui = u0 + quad, unit = blockIdx.x * per_cta + ui;
+          const bool valid = ui < per_cta && unit < units;
+          const int uu = valid ? unit : 0;
+          const int m = uu / (OD >> 2), col = (uu % (OD >> 2)) * 4, h = col / HD, d = col % HD;
+          const float* ml = p.part_ml + ((long)h * NCH * 16 + m) * 2;
+          const float* oc = p.part_o + ((long)h * NCH * 16 + m) * HD + d;
+          float2 mlv[5];
+          float4 ov[5];
+          float mx = -3.4e38f;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {  // chunks sub, sub + 4, ... (NCH <= 17 since Tpad <= 1024)
+            const int c = sub + 4 * j;
+            mlv[j] = make_float2(-3.4e38f, 0.f);
+            ov[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (c < NCH) {
+              mlv[j] = __ldcg(reinterpret_cast<const float2*>(ml + (long)c * 32));
+              ov[j] = __ldcg(reinterpret_cast<const float4*>(oc + (long)c * 16 * HD));
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) mx = fmaxf(mx, mlv[j].x);
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+          float den = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            if (sub + 4 * j < NCH) {
+              const float w = __expf(mlv[j].x - mx);
+              den += w * mlv[j].y;
+              n0 += w * ov[j].x;
+              n1 += w * ov[j].y;
+              n2 += w * ov[j].z;
+              n3 += w * ov[j].w;
+            }
+          }
+#pragma unroll
+          for (int o = 1; o <= 2; o <<= 1) {
+            den += __shfl_xor_sync(0xffffffffu, den, o);
+            n0 += __shfl_xor_sync(0xffffffffu, n0, o);
+            n1 += __shfl_xor_sync(0xffffffffu, n1, o);
+            n2 += __shfl_xor_sync(0xffffffffu, n2, o);
+            n3 += __shfl_xor_sync(0xffffffffu, n3, o);
+          }
+          if (valid && sub == 0) {
+            uint2 o2;
+            o2.x = pack_bf16x2(n0 / den, n1 / den);
+            o2.y = pack_bf16x2(n2 / den, n3 / den);
+            *reinterpret_cast<uint2*>(Obuf + (long)m * OD + col) = o2;
+          }
+        }
+      }
+      tick(21);
+      tick(22);
+      tick(6);
+      bar.sync();
+      tick(7);
+
+      // ---------------- P3: XE1 = XE + gate_a * (O Wo^T) ----------------
+      const bf16* Wgu = reinterpret_cast<const bf16*>(p.gu_w) + (long)l * p.gu_ls;
+      {
+        const bf16* Wo = reinterpret_cast<const bf16*>(p.o_w) + (long)l * p.o_ls;
+        if (o_te > o_tb) {
+          dn_stage(Obuf, OD, h_s, ldo, A, OD);
+          dn_cp_wait_all();
+          __syncthreads();
+          for (int t0 = o_tb; t0 < o_te; ++t0) {
+            dn2_mma_warp<2>(h_s, ldo, A, ngo, warp, DN_WARPS, wme, Wo + (long)t0 * 8 * OD, OD, red);
+            const bool more = t0 + 1 < o_te;
+            if (more) dn2_issue_w<2>(wme, Wo + (long)(t0 + 1) * 8 * OD, OD, ngo, warp, DN_WARPS);
+            __syncthreads();
+            if (threadIdx.x < 16 * 8) {
+              const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
+              if (m < A) {
+                const int n = t0 * 8 + cc;
+                const float y = bf16r(dn_tile_val(red, 0, m, cc, true));
+                const float gt = __bfloat162float(mod_a[2 * D1 + n]);
+                const float r = __bfloat162float(xe_s[m * D1 + n]);
+                XE1[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
+              }
+            }
+            if (more) {
+              dn_cp_wait_all();
+              __syncthreads();
+            }
+          }
+        }
+        tick(8);
+        bar.arrive();  // (every warp is done with the staged O: the second weight buffer, behind h, may be filled)
+        dn2_issue_w<4>(wme, gu_tile(Wgu, f_pb), D1, ng1, kpart, 8);  // both gate/up passes of P4
+        dn2_issue_w<4>(wme2, gu_tile(Wgu, f_pb + 2), D1, ng1, kpart, 8);
+        bar.wait();
+        tick(9);
+      }
+
+      // ---------------- P4: h = adaRMS(XE1); act = gelu(h Wg^T) * (h Wu^T) ----------------
+      dn_stage(XE1, D1, xe_s, D1, A, D1);
+      dn_cp_wait_all();
+      __syncthreads();
+      tick(28);
+      dn2_ada_norm(xe_s, h_s, ldh, A, D1, mod_f, red);
+      __syncthreads();
+      tick(29);
+      {
+        int pass = 0;
+        for (int p0 = f_pb; p0 < f_pe; p0 += 2, ++pass) {
+          uint4* wb = (pass & 1) ? wme2 : wme;
+          dn2_mma_warp<4>(h_s, ldh, A, ng1, kpart, 8, wb, gu_tile(Wgu, p0), D1, red);
+          const bool refill = p0 + 4 < f_pe;  // (more than two passes: not at LAP-3B sizes on a full grid)
+          if (refill) dn2_issue_w<4>(wb, gu_tile(Wgu, p0 + 4), D1, ng1, kpart, 8);
+          __syncthreads();
+          if (threadIdx.x < 256) {
+            const int e = threadIdx.x;  // 16 rows x 2 pairs x 8 columns = 256 outputs
+            const int m = e >> 4, pi = (e >> 3) & 1, cc = e & 7;
+            if (m < A && p0 + pi < f_pe) {
+              const float gv = bf16r(dn_tile_val(red, 2 * pi, m, cc, false));
+              const float uv = bf16r(dn_tile_val(red, 2 * pi + 1, m, cc, false));
+              act[(long)m * F1 + (p0 + pi) * 8 + cc] = __float2bfloat16_rn(bf16r(gelu_tanh(gv)) * uv);
+            }
+          }
+          if (p0 + 2 < f_pe) {
+            dn_cp_wait_all();  // (nothing pending unless a refill was issued)
+            __syncthreads();
+          }
+        }
+      }
+      tick(30);
+      // P5's tile of Wd (K split over all 32 warps) -> slots 0..3
+      {
+        const bf16* Wd = reinterpret_cast<const bf16*>(p.down_w) + (long)l * p.down_ls;
+        const bf16* wt5 = o_te > o_tb ? Wd + (long)o_tb * 8 * F1 : nullptr;
+        bar.arrive();
+        dn2_issue_w<4>(wme, wt5, F1, ngf, warp, DN_WARPS);
+        tick(10);
+        bar.wait();
+        tick(11);
+
+        // ---------------- P5: XE = XE1 + gate_f * (act Wd^T) ----------------
+        const bool next_w1 = l + 1 < L;  // (the next step's layer 0 is issued in the final phase)
+        if (o_te > o_tb) {
+          dn_stage(act, F1, h_s, ldf, A, F1);
+          dn_cp_wait_all();
+          __syncthreads();
+          for (int t0 = o_tb; t0 < o_te; ++t0) {
+            dn2_mma_warp<4>(h_s, ldf, A, ngf, warp, DN_WARPS, wme, Wd + (long)t0 * 8 * F1, F1, red);
+            const bool more = t0 + 1 < o_te;
+            if (more) dn2_issue_w<4>(wme, Wd + (long)(t0 + 1) * 8 * F1, F1, ngf, warp, DN_WARPS);
+            __syncthreads();
+            if (threadIdx.x < 16 * 8) {
+              const int m = threadIdx.x >> 3, cc = threadIdx.x & 7;
+              if (m < A) {
+                const int n = t0 * 8 + cc;
+                const float y = bf16r(dn_tile_val(red, 0, m, cc, true));
+                const float gt = __bfloat162float(mod_f[2 * D1 + n]);
+                const float r = __bfloat162float(xe_s[m * D1 + n]);
+                XE[(long)m * D1 + n] = __float2bfloat16_rn(r + bf16r(y * gt));
+              }
+            }
+            if (more) {
+              dn_cp_wait_all();
+              __syncthreads();
+            }
+          }
+        }
+        tick(12);
+        bar.arrive();
+        if (next_w1) dn2_issue_w<4>(wme, qkv_tile(Wqkv + p.qkv_ls, q_tb), D1, ng1, kpart, 8);
+        bar.wait();
+        tick(13);
+      }
+    }
+
+    // ---------------- final: v = action_out_proj(adaRMS(XE)); x += dt * v (lap.py:665-667) ----------------
+    dn_stage(XE, D1, xe_s, D1, A, D1);
+    dn_stage(mod_s + (long)(p.nm - 1) * 3 * D1, 0, mod_sm, 0, 1, 2 * D1);
+    dn_cp_wait_all();
+    __syncthreads();
+    // the next step's layer-0 Wqkv fragments fly during the final phase and action_in_proj
+    if (step + 1 < S) dn2_issue_w<4>(wme, qkv_tile(reinterpret_cast<const bf16*>(p.qkv_w), q_tb), D1, ng1, kpart, 8);
+    dn2_ada_norm(xe_s, h_s, ldh, A, D1, mod_sm, red);
+    __syncthreads();
+    for (int o = warp; o < A * ad; o += DN_WARPS) {
+      const int m = o / ad, j = o % ad;
+      float acc = 0.f;
+#pragma unroll 8
+      for (int k = lane * 4; k < D1; k += 128) {
+        const float4 wv = __ldg(reinterpret_cast<const float4*>(p.aout_w + (long)j * D1 + k));
+        const uint2 hv = *reinterpret_cast<const uint2*>(h_s + m * ldh + k);
+        const float2 h01 = unpack_bf16x2(hv.x), h23 = unpack_bf16x2(hv.y);
+        acc += wv.x * h01.x + wv.y * h01.y + wv.z * h23.x + wv.w * h23.y;
+      }
+      acc = warp_sum(acc);
+      if (lane == 0) x_s[o] += p.dt * (acc + __ldg(p.aout_b + j));
+    }
+    __syncthreads();
+    tick(14);
+  }
+  if (blockIdx.x == 0)
+    for (int i = threadIdx.x; i < A * ad; i += DN_THREADS) p.x[i] = x_s[i];
+  if (PROF && prof_on)
+    for (int i = 0; i < 32; ++i) p.prof[(long)blockIdx.x * 32 + i] += prof_s[i];
 }
 
 // ======================================================================================================================
@@ -1317,7 +2117,8 @@ int lapb200_denoise_supported(int64_t B, int64_t A, int64_t ad, int64_t D1, int6
   return B == 1 && A >= 1 && A <= 16 && ad >= 1 && ad <= 32 && num_steps >= 1 && num_steps <= 16 && D1 % 32 == 0 &&
          D1 >= 64 && D1 <= 2048 && HD % 32 == 0 && HD >= 32 && HD <= 256 && F1 % 32 == 0 && (NH * HD) % 32 == 0 &&
          NH >= 1 && Pn >= 1 && Tpad >= ((Pn + DN_CK - 1) / DN_CK) * DN_CK && Tpad % 32 == 0 && Tpad <= 1024 &&
-         dn_smem_bytes((int)D1, (int)HD, (int)(NH * HD), (int)F1) <= (size_t)227 * 1024;
+         (dn_smem_bytes((int)D1, (int)HD, (int)(NH * HD), (int)F1) <= (size_t)227 * 1024 ||
+          dn2_smem_bytes((int)A, (int)num_steps, (int)D1, (int)HD, (int)(NH * HD), (int)F1) <= (size_t)227 * 1024);
 }
 
 int lapb200_denoise_grid(void) { return num_sms(); }
@@ -1351,10 +2152,10 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
   LAPB_REQUIRE(p.TpadK == ((p.Pn + DN_CK - 1) / DN_CK) * DN_CK, "denoise_loop: TpadK must be round_up(Pn, 64)");
   // Two partitionings of the same loop: "cluster" = one 16-CTA thread-block cluster (hardware cluster barriers; needs
   // 8 query heads so that (head, key half) maps onto the 16 CTAs), "grid" = one CTA per SM with grid barriers.
-  static int mode = -1;  // 0 grid, 1 cluster
+  static int mode = -1;  // 0 grid v2 (v1 when its shared memory does not fit), 1 cluster, 2 grid v1
   if (mode < 0) {
     const char* e = getenv("LAPB_DENOISE_MODE");
-    mode = (e && e[0] == 'c') ? 1 : 0;  // default: grid (measured faster, see the K10c header)
+    mode = (e && e[0] == 'c') ? 1 : (e && strcmp(e, "grid1") == 0) ? 2 : 0;  // default: grid (measured faster than K10c)
   }
   LAPB_REQUIRE(!p.packed || mode == 1, "denoise_loop: tile-major packed operands are read by the cluster kernel only "
                "(LAPB_DENOISE_MODE=cluster)");
@@ -1385,15 +2186,20 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
                  cudaGetErrorString(ce));
     mode = 0;
   }
-  const size_t smem = dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
+  const size_t smem2 = dn2_smem_bytes(p.A, p.num_steps, p.D1, p.HD, p.NH * p.HD, p.F1);
+  const bool v2 = mode != 2 && smem2 <= (size_t)227 * 1024;
+  const size_t smem = v2 ? smem2 : dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
   LAPB_REQUIRE(smem <= 227 * 1024, "denoise_loop: needs %zu bytes of shared memory (> 227 KB)", smem);
-  static size_t configured = 0;
-  if (smem > configured) {
-    LAPB_CUDA_OK(cudaFuncSetAttribute(denoise_loop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
+  const void* kern = v2 ? (p.prof ? (const void*)denoise_loop2_kernel<true> : (const void*)denoise_loop2_kernel<false>)
+                        : (const void*)denoise_loop_kernel;
+  static size_t configured[3] = {0, 0, 0};
+  const int ki = v2 ? (p.prof ? 2 : 1) : 0;
+  if (smem > configured[ki]) {
+    LAPB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured[ki] = smem;
   }
   int per_sm = 0;
-  LAPB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, denoise_loop_kernel, DN_THREADS, smem));
+  LAPB_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, DN_THREADS, smem));
   LAPB_REQUIRE(per_sm >= 1, "denoise_loop: kernel does not fit on an SM (smem %zu)", smem);
   LAPB_CUDA_OK(cudaMemsetAsync(p.sync, 0, LAPB_DENOISE_SYNC_WORDS * sizeof(uint32_t), STREAM(s)));
   cudaLaunchConfig_t cfg = {};
@@ -1418,7 +2224,12 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
     const char* e = getenv("LAPB_DENOISE_FOLD");
     fold_env = (e && atoi(e) != 0 && p.NH <= LAPB_DENOISE_SYNC_WORDS - 2) ? 1 : 0;
   }
-  LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, denoise_loop_kernel, p, fold_env));
+  if (v2) {
+    void* args[] = {(void*)&p};
+    LAPB_CUDA_OK(cudaLaunchKernelExC(&cfg, kern, args));
+  } else {
+    LAPB_CUDA_OK(cudaLaunchKernelEx(&cfg, denoise_loop_kernel, p, fold_env));
+  }
   return 0;
 }
 

@@ -1204,7 +1204,7 @@ class LAP:
             part_o=self.buf("dn.part_o", (NH * nch, 16, HD), F32), part_ml=self.buf("dn.part_ml", (NH * nch, 16, 2), F32),
             sync=self.buf("dn.sync", (32,), torch.int32, zero=True))  # LAPB_DENOISE_SYNC_WORDS
         if self.denoise_profile:
-            ptrs["prof"] = self.buf("dn.prof", (32,), torch.int64, zero=True)
+            ptrs["prof"] = self.buf("dn.prof", (256 * 32,), torch.int64, zero=True)  # [CTA][slot]
 
         def lstride(name):
             return self.w(name, 1).data_ptr() - self.w(name, 0).data_ptr() >> 1 if L > 1 else 0
