@@ -920,28 +920,25 @@ __host__ __device__ inline size_t dn2_smem_bytes(int A, int S, int D1, int HD, i
          (size_t)16 * 32 * 4 + 16;
 }
 
-__device__ __forceinline__ void dn2_cp16_zfill(void* smem_dst, const void* gsrc, bool ok) {
-  if (ok)
-    dn_cp16(smem_dst, gsrc);
-  else
-    *reinterpret_cast<uint4*>(smem_dst) = make_uint4(0, 0, 0, 0);
-}
-// this thread's U fragments of one n8 weight tile (K groups kg_first + kg_stride * u) -> its private slots wme[u * 32]
+// this thread's U fragments of one n8 weight tile (K groups kg_first + kg_stride * u) -> its private slots wme[u * 32].
+// wtile == nullptr: the warp's tile slot lies beyond the CTA's share — nothing is copied, dn2_mma_warp skips the warp and
+// the epilogues never read that slot of `red`.
 template <int U>
 __device__ __forceinline__ void dn2_issue_w(uint4* wme, const bf16* wtile, long ldw, int ngroups, int kg_first,
                                             int kg_stride) {
+  if (wtile == nullptr) return;
   const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
 #pragma unroll
   for (int u = 0; u < U; ++u) {
     const int kg = kg_first + kg_stride * u;
-    const bool ok = wtile != nullptr && kg < ngroups;
-    dn2_cp16_zfill(wme + u * 32, ok ? wtile + (long)g * ldw + 8 * t + kg * 32 : nullptr, ok);
+    if (kg < ngroups) dn_cp16(wme + u * 32, wtile + (long)g * ldw + 8 * t + kg * 32);
   }
 }
 // as dn_mma_warp, B fragments from the thread's slots (the caller has waited for the copies of the first K batch)
 template <int U>
 __device__ __forceinline__ void dn2_mma_warp(const bf16* As, int lda, int M, int ngroups, int kg_first, int kg_stride,
                                              uint4* wme, const bf16* wtile, long ldw, float* red) {
+  if (wtile == nullptr) return;  // (warp-uniform) no tile in this slot: saves its share of the shared-memory bandwidth
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -1089,20 +1086,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const int kg = tslot + 4 * u;
-      if (kg < HD / 32) {
-        dn_cp16(wme + u * 32, kr + kg * 32);
-      } else {
-        wme[u * 32] = zero4;
-      }
+      if (kg < HD / 32) dn_cp16(wme + u * 32, kr + kg * 32);
     }
 #pragma unroll
     for (int kg = 0; kg < 2; ++kg) {
-      if (warp < HD / 8) {
-        const bf16* vr = VcT + (long)(warp * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32;
-        dn_cp16(wme + (2 + kg) * 32, vr);
-      } else {
-        wme[(2 + kg) * 32] = zero4;
-      }
+      if (warp < HD / 8) dn_cp16(wme + (2 + kg) * 32, VcT + (long)(warp * 8 + g) * p.TpadK + key0 + 8 * t4 + kg * 32);
     }
   };
 
@@ -1264,31 +1252,37 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
         const int r0 = prefix ? 0 : ((item - nprefix) % sfx_blocks) * sfx_rows;  // suffix item: query rows [r0, r1)
         const int r1 = prefix ? A : min(A, r0 + sfx_rows);
         __syncthreads();
-        dn_stage(qkv + h * HD, QKV, qraw, HD, A, HD);
         if (!prefix) {
-          dn_stage(qkv + NH * HD, QKV, kraw, HD, A, HD);
           dn_stage(qkv + (NH + 1) * HD, QKV, vraw, HD, A, HD);
         } else if (item != item0) {  // (only when there are more items than CTAs)
           issue_kv(reinterpret_cast<const bf16*>(p.Kc) + (long)l * p.kc_ls,
                    reinterpret_cast<const bf16*>(p.VcT) + (long)l * p.vct_ls, c * DN_CK);
         }
-        dn_cp_wait_all();
-        __syncthreads();
-        tick(24);
-        // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ) (gemma.py:215-218, 548-564); suffix item: ks_s <- bf16(rope(k))
-        for (int i = threadIdx.x; i < A * half; i += DN_THREADS) {
-          const int m = i / half, d = i % half;
-          const float cs = rope_s[i].x, sn = rope_s[i].y;
-          const float x1 = __bfloat162float(qraw[m * HD + d]), x2 = __bfloat162float(qraw[m * HD + half + d]);
-          q_s[m * ldq + d] = __float2bfloat16_rn(bf16r(x1 * cs - x2 * sn) * p.qscale);
-          q_s[m * ldq + half + d] = __float2bfloat16_rn(bf16r(x2 * cs + x1 * sn) * p.qscale);
+        // q_s <- bf16( bf16(rope(q_h)) * hd^-0.5 ) (gemma.py:215-218, 548-564); suffix item: ks_s <- bf16(rope(k)).  The rows
+        // come straight from L2 (two adjacent head dims per thread), RoPE applied on the way
+        for (int i = threadIdx.x; i < A * (half >> 1); i += DN_THREADS) {
+          const int m = i / (half >> 1), d = (i % (half >> 1)) * 2;
+          const float2 c0 = rope_s[m * half + d], c1 = rope_s[m * half + d + 1];  // (cos, sin)
+          const bf16* qrow = qkv + (long)m * QKV + h * HD;
+          const float2 x1 = unpack_bf16x2(__ldcg(reinterpret_cast<const uint32_t*>(qrow + d)));
+          const float2 x2 = unpack_bf16x2(__ldcg(reinterpret_cast<const uint32_t*>(qrow + half + d)));
+          *reinterpret_cast<uint32_t*>(q_s + m * ldq + d) =
+              pack_bf16x2(bf16r(x1.x * c0.x - x2.x * c0.y) * p.qscale, bf16r(x1.y * c1.x - x2.y * c1.y) * p.qscale);
+          *reinterpret_cast<uint32_t*>(q_s + m * ldq + half + d) =
+              pack_bf16x2(bf16r(x2.x * c0.x + x1.x * c0.y) * p.qscale, bf16r(x2.y * c1.x + x1.y * c1.y) * p.qscale);
           if (!prefix) {
-            const float k1 = __bfloat162float(kraw[m * HD + d]), k2 = __bfloat162float(kraw[m * HD + half + d]);
-            ks_s[m * HD + d] = bf16r(k1 * cs - k2 * sn);
-            ks_s[m * HD + half + d] = bf16r(k2 * cs + k1 * sn);
+            const bf16* krow = qkv + (long)m * QKV + NH * HD;
+            const float2 k1 = unpack_bf16x2(__ldcg(reinterpret_cast<const uint32_t*>(krow + d)));
+            const float2 k2 = unpack_bf16x2(__ldcg(reinterpret_cast<const uint32_t*>(krow + half + d)));
+            ks_s[m * HD + d] = bf16r(k1.x * c0.x - k2.x * c0.y);
+            ks_s[m * HD + d + 1] = bf16r(k1.y * c1.x - k2.y * c1.y);
+            ks_s[m * HD + half + d] = bf16r(k2.x * c0.x + k1.x * c0.y);
+            ks_s[m * HD + half + d + 1] = bf16r(k2.y * c1.x + k1.y * c1.y);
           }
         }
+        dn_cp_wait_all();  // K / V^T fragments (or the staged suffix v rows)
         __syncthreads();
+        tick(24);
         tick(25);
         float* po = p.part_o + (long)(h * NCH + c) * 16 * HD;
         float* pml = p.part_ml + (long)(h * NCH + c) * 16 * 2;

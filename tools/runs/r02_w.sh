@@ -1,0 +1,14 @@
+#!/bin/bash
+# K10 v2, third iteration: invalid tile slots skipped
+mkdir -p gpurun_out
+T="python -m pytest tests/test_gpu_parity.py tests/test_gpu_kernels.py -q -p no:cacheprovider -k"
+timeout 300 $T "fused_denoise or batch1_sampling or denoise" 2>&1 | tail -15 > gpurun_out/r02w_pytest_v2.log; tail -3 gpurun_out/r02w_pytest_v2.log
+for v in "LAPB_DENOISE_CTAS=40"; do
+  env $v timeout 300 $T "fused_denoise" 2>&1 | tail -3 | sed "s/^/$v: /"
+done
+for v in "LAPB_DENOISE_FLAGS=0" "LAPB_DENOISE_CTAS=128"; do
+  name=$(echo "$v" | tr ' =' '__')
+  env $v timeout 300 python bench.py --mode infer > gpurun_out/r02w_infer_$name.json 2> gpurun_out/r02w_infer_$name.err
+  python -c "import json;d=json.load(open('gpurun_out/r02w_infer_$name.json'));print('$v',d['value'],d['device_ms'])" || tail -3 gpurun_out/r02w_infer_$name.err
+done
+timeout 300 python tools/denoise_prof.py full --no-per-op > gpurun_out/r02w_prof_v2.json 2> gpurun_out/r02w_prof_v2.err || tail -5 gpurun_out/r02w_prof_v2.err
