@@ -456,10 +456,19 @@ def infer_metrics(model, *, steps: int = 100, warmup: int = 10) -> dict:
                     "d2h_bytes_per_step": int(a_host.numel() * 4)},
             "floor_ms": 3.4,
             "roofline": None if not denoise_ms else {
-                "bound": "hbm", "kernel": "denoise_loop_kernel (K10: 10 Euler steps x 18 expert layers, one launch)",
+                "bound": "hbm", "kernel": "denoise_loop2_kernel (K10: 10 Euler steps x 18 expert layers, one launch)",
                 "achieved": dn_bytes / (denoise_ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                "frac": dn_bytes / (denoise_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                "frac": dn_bytes / (denoise_ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": _denoise_traffic(),
                 "algorithmic_bytes_per_launch": dn_bytes, "avg_launch_ms": denoise_ms}}
+
+
+def _denoise_traffic():
+    """DRAM bytes of one K10 launch from the committed `ncu --set full` capture (profiles/ncu_traffic.json), or None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            return json.load(f)["denoise_loop_per_launch"]["dram_bytes"]
+    except (OSError, KeyError, ValueError):
+        return None
 
 
 def run_infer(args) -> None:
