@@ -270,7 +270,10 @@ typedef struct {
                                         barrier, 4/5 P2, 6/7 P2b, 8/9 P3, 10/11 P4, 12/13 P5, 14 final); NULL = off */
   int32_t packed;                    /* 1: qkv_w / o_w / gu_w / down_w, Kc ([Tpad, HD] per layer) and VcT ([HD, TpadK] per layer)
                                         are TILE-MAJOR copies made by lapb200_pack_tiles (cluster kernel only); 0: row-major */
-  int32_t flags;                     /* bit 0: grid kernel without the layer-ahead L2 prefetch of the weights (experiment) */
+  int32_t flags;                     /* experiments / tests, 0 = product path.  v2 loop kernel: bit 1 = fence.sc + ld.acquire
+                                        grid barrier.  bit 7 = round-1 kernel layout (also the fallback when v2's shared
+                                        memory does not fit), which reads bit 0 = layer-ahead L2 prefetch burst, bit 1 =
+                                        fence after the register preloads, bit 2 = per-phase L2 prefetch */
 } lapb_denoise_params_t;
 /* 1 if the shape is supported by the persistent kernel (B == 1, A <= 16, num_steps <= 16, head_dim <= 256 ...). */
 int lapb200_denoise_supported(int64_t B, int64_t A, int64_t ad, int64_t D1, int64_t NH, int64_t HD, int64_t F1,

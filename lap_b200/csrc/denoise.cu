@@ -2181,7 +2181,7 @@ int lapb200_denoise_loop(const lapb_denoise_params_t* params, lapb_stream_t s) {
     mode = 0;
   }
   const size_t smem2 = dn2_smem_bytes(p.A, p.num_steps, p.D1, p.HD, p.NH * p.HD, p.F1);
-  const bool v2 = mode != 2 && smem2 <= (size_t)227 * 1024;
+  const bool v2 = mode != 2 && !(p.flags & 128) && smem2 <= (size_t)227 * 1024;  // flags bit 7: round-1 layout (tests)
   const size_t smem = v2 ? smem2 : dn_smem_bytes(p.D1, p.HD, p.NH * p.HD, p.F1);
   LAPB_REQUIRE(smem <= 227 * 1024, "denoise_loop: needs %zu bytes of shared memory (> 227 KB)", smem);
   const void* kern = v2 ? (p.prof ? (const void*)denoise_loop2_kernel<true> : (const void*)denoise_loop2_kernel<false>)

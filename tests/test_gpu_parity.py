@@ -189,10 +189,14 @@ def test_batch1_sampling_uses_streaming_kernels_and_matches_oracle():
     assert torch.equal(a1, a2) and torch.equal(a2, a3)
 
 
+@pytest.mark.parametrize("flags", [0, 2, 128], ids=["v2", "v2_strong_barrier", "round1_layout"])
 @pytest.mark.parametrize("which", ["debug_small", "expert_full_size"])
-def test_fused_denoise_loop_matches_per_op_path(which):
+def test_fused_denoise_loop_matches_per_op_path(which, flags, monkeypatch):
     """K10: the persistent Euler-loop kernel (csrc/denoise.cu) against the kernel-per-op path it replaces, on the same
-    prefix cache.  Differences: summation order and the bf16 rounding grid of the attention probabilities."""
+    prefix cache.  Differences: summation order and the bf16 rounding grid of the attention probabilities.  `flags`
+    (lapb_denoise_params_t.flags): 0 = the v2 kernel, 2 = v2 with the fence.sc / ld.acquire grid barrier, 128 = the
+    round-1 layout that remains the fallback when v2's shared memory does not fit."""
+    monkeypatch.setenv("LAPB_DENOISE_FLAGS", str(flags))
     from lap_b200.config import LAPConfig
     from lap_b200.model import LAP
     from lap_b200.observation import Observation
