@@ -916,7 +916,7 @@ __host__ __device__ inline size_t dn2_act_bytes(int A, int S, int D1, int HD, in
 __host__ __device__ inline size_t dn2_smem_bytes(int A, int S, int D1, int HD, int OD, int F1) {
   // xe_s | big | wbuf | red | x_s | rope table | mod rows (attn + ffn) | mask bits
   const size_t act = dn2_act_bytes(A, S, D1, HD, OD, F1);
-  return act + DN2_WBUF + (size_t)8 * 4 * 32 * 4 * 4 + (size_t)16 * 32 * 4 + (size_t)16 * (HD / 2) * 8 + (size_t)6 * D1 * 2 +
+  return act + DN2_WBUF + (size_t)8 * 4 * 32 * 4 * 4 + (size_t)16 * 32 * 4 + (size_t)A * (HD / 2) * 8 + (size_t)6 * D1 * 2 +
          (size_t)16 * 32 * 4 + 16;
 }
 
@@ -1015,8 +1015,8 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
   uint4* wme2 = reinterpret_cast<uint4*>(big + dn2_h_bytes(A, D1)) + warp * 128 + lane;                // second buffer
   float* red = reinterpret_cast<float*>(wbuf_b + DN2_WBUF);                           // [8][4][32][4]
   float* x_s = red + 8 * 4 * 32 * 4;                                                  // [16*32] x_t
-  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);                          // [16][HD/2] (cos, sin)
-  bf16* mod_sm = reinterpret_cast<bf16*>(rope_s + 16 * half);                         // [2][3*D1]: attn-norm, ffn-norm rows
+  float2* rope_s = reinterpret_cast<float2*>(x_s + 16 * 32);                          // [A][HD/2] (cos, sin)
+  bf16* mod_sm = reinterpret_cast<bf16*>(rope_s + A * half);                          // [2][3*D1]: attn-norm, ffn-norm rows
   uint32_t* bits_s = reinterpret_cast<uint32_t*>(mod_sm + 6 * D1);                    // [16][32]
   float* te_s = reinterpret_cast<float*>(dn_smem);                                    // prologue only
   // attention scratch (inside `big`)
