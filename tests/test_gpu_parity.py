@@ -189,8 +189,13 @@ def test_batch1_sampling_uses_streaming_kernels_and_matches_oracle():
     assert torch.equal(a1, a2) and torch.equal(a2, a3)
 
 
-@pytest.mark.parametrize("flags", [0, 2, 128], ids=["v2", "v2_strong_barrier", "round1_layout"])
-@pytest.mark.parametrize("which", ["debug_small", "expert_full_size"])
+@pytest.mark.parametrize("which,flags", [
+    ("debug_small", 0), ("debug_small", 2), ("debug_small", 128),
+    ("expert_full_size", 0), ("expert_full_size", 2), ("expert_full_size", 128),
+    # 16 action rows: every row of the m16 mma tiles is live (and 32-bit action vectors); at full width the v2 layout no
+    # longer fits the shared memory, so this case also covers the automatic fall-back to the round-1 layout
+    ("debug_small_a16", 0), ("expert_full_size_a16", 0),
+], ids=lambda v: {0: "v2", 2: "v2_strong_barrier", 128: "round1_layout"}.get(v, v))
 def test_fused_denoise_loop_matches_per_op_path(which, flags, monkeypatch):
     """K10: the persistent Euler-loop kernel (csrc/denoise.cu) against the kernel-per-op path it replaces, on the same
     prefix cache.  Differences: summation order and the bf16 rounding grid of the attention probabilities.  `flags`
@@ -200,12 +205,15 @@ def test_fused_denoise_loop_matches_per_op_path(which, flags, monkeypatch):
     from lap_b200.config import LAPConfig
     from lap_b200.model import LAP
     from lap_b200.observation import Observation
-    if which == "debug_small":
+    import dataclasses
+    if which.startswith("debug_small"):
         cfg = get_config("debug_small").model
     else:  # the real action expert (gemma_300m: 18 x [1024 / 4096 / 8 x 256]) and the real prefix length (692 keys)
         cfg = LAPConfig(paligemma_variant="mid_2b", action_expert_variant="gemma_300m", siglip_variant="tiny72/14",
                         action_dim=7, action_horizon=10, max_token_len=180, enable_action_training=True,
                         enable_image_augmentation=False, vocab_size=4096)
+    if which.endswith("_a16"):
+        cfg = dataclasses.replace(cfg, action_horizon=16, action_dim=32)
     ref = P.init_reference_params(cfg, 3, reference_zero_init=False)
     model = LAP(cfg, init=False)
     model.load_params(ref)
