@@ -1024,9 +1024,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
   float* s_s = reinterpret_cast<float*>(q_s + 16 * ldq);                              // [16][64]
   bf16* p_s = reinterpret_cast<bf16*>(s_s + 16 * DN_CK);                              // [16][72]
   float* ks_s = reinterpret_cast<float*>(p_s + 16 * ldp);                             // [16][HD]
-  bf16* qraw = reinterpret_cast<bf16*>(ks_s + 16 * HD);                               // [16][HD] x3
-  bf16* kraw = qraw + 16 * HD;
-  bf16* vraw = kraw + 16 * HD;
+  bf16* vraw = reinterpret_cast<bf16*>(ks_s + 16 * HD) + 2 * 16 * HD;                 // [16][HD] staged suffix v rows
   float* sp_s = reinterpret_cast<float*>(vraw + 16 * HD);                             // [4][16][64] S partials (K quarters)
 
   const int g = lane >> 2, t4 = lane & 3;
