@@ -241,6 +241,8 @@ __device__ __forceinline__ void dn_ada_norm(const bf16* xe_s, bf16* h_s, int ldh
 }
 
 // fp32 GEMV block used by the time MLP: out[r, n] = swish( sum_k W[n,k] * in_s[r,k] + bias[n] ), warp per column
+// (~40 us per call at LAP-3B size, and 8 weight loads in flight per lane change that by 6 us only: the prologue runs each
+// of its code paths once, instruction-cache cold — the 4 GB prefix pass before it leaves none of the kernel's code in L2)
 __device__ __noinline__ void dn_time_mlp(const float* in_s, int R, int D1, const float* W, const float* bias, float* out_f32,
                                          bf16* out_bf16) {
   const int lane = threadIdx.x & 31;
@@ -1109,11 +1111,13 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
     __syncthreads();
     dn_time_mlp(te_s, S, D1, p.tin_w, p.tin_b, p.s1, nullptr);
     bar.sync();
+    tick(15);
     // T2: cond = swish(time_mlp_out(s1)) -> cond16
     for (int i = threadIdx.x; i < S * D1; i += DN_THREADS) te_s[i] = __ldcg(p.s1 + i);
     __syncthreads();
     dn_time_mlp(te_s, S, D1, p.tout_w, p.tout_b, nullptr, reinterpret_cast<bf16*>(p.cond16));
     bar.sync();
+    tick(23);
     // T3: mod = cond16 @ mod_w^T + mod_b  (rows = steps); passes alternate between the two weight buffers, two in flight
     bf16* h3 = reinterpret_cast<bf16*>(dn_smem);                                      // [S][D1+PAD] staged cond16
     uint4* wme3 = reinterpret_cast<uint4*>(dn_smem + dn2_h_bytes(S, D1)) + warp * 128 + lane;

@@ -45,7 +45,8 @@ prof = prof[used]
 out["ctas_profiled"] = int(used.sum())
 LS = 10 * cfg.gemma.depth
 # slot -> name, in program order; the interval a slot measures ends at the tick of that number (denoise.cu)
-slots = [(0, "prologue (total)"), (1, "action_in (per step)"),
+slots = [(15, "prologue T1 time_mlp_in"), (23, "prologue T2 time_mlp_out"), (0, "prologue T3 modulation + init"),
+         (1, "action_in (per step)"),
          (16, "P1 stage XE+mod"), (17, "P1 norm"), (18, "P1 mma (all passes)"), (19, "P1 epilogues"), (20, "P1 K/V preload issue"),
          (2, "P1 -"), (3, "P1->P2 wait"),
          (24, "P2 stage q"), (25, "P2 rope"), (26, "P2 S mma"), (27, "P2 softmax"), (4, "P2 PV+store"), (5, "P2->P2b wait"),
@@ -57,10 +58,10 @@ tab = {}
 tot0 = 0.0
 for i, name in slots:
     col = prof[:, i] / 1e3
-    div = 1 if i == 0 else (10 if i in (1, 14) else LS)
+    div = 1 if i in (0, 15, 23) else (10 if i in (1, 14) else LS)
     tab[name] = {"cta0": float(col[0]) / div, "min": float(col.min()) / div, "median": float(col.median()) / div,
                  "max": float(col.max()) / div}
-    if i not in (0, 1, 14):
+    if i not in (0, 1, 14, 15, 23):
         tot0 += float(col[0]) / div
 out["us_per_layer_step"] = tab
 out["cta0_layer_step_us"] = tot0
