@@ -1133,6 +1133,11 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
     int pass = 0;
     for (int t0 = tb; t0 < te; t0 += 4, ++pass) {
       uint4* wb = (pass & 1) ? wme3 : wme;
+      float bias_v = 0.f;  // this thread's output column of the pass: its bias is in flight during the product
+      {
+        const int e = threadIdx.x, c = e & 31, tile = c >> 3, cc = c & 7;
+        if (e < 16 * 32 && (e >> 5) < S && t0 + tile < te) bias_v = __ldg(p.mod_b + (t0 + tile) * 8 + cc);
+      }
       dn2_mma_warp<4>(h3, ldh, S, ng1, kpart, 8, wb, mod_tile(t0), D1, red);
       if (t0 + 8 < te) dn2_issue_w<4>(wb, mod_tile(t0 + 8), D1, ng1, kpart, 8);  // refill: consumed two passes from now
       __syncthreads();
@@ -1140,7 +1145,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
         const int e = threadIdx.x, m = e >> 5, c = e & 31, tile = c >> 3, cc = c & 7;
         if (m < S && t0 + tile < te) {
           const int n = (t0 + tile) * 8 + cc;
-          const float v = bf16r(dn_tile_val(red, tile, m, cc, false)) + bf16r(p.mod_b[n]);
+          const float v = bf16r(dn_tile_val(red, tile, m, cc, false)) + bf16r(bias_v);
           reinterpret_cast<bf16*>(p.mod)[(long)m * nm3 + n] = __float2bfloat16_rn(v);
         }
       }
@@ -1592,6 +1597,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
     __syncthreads();
     for (int o = warp; o < A * ad; o += DN_WARPS) {
       const int m = o / ad, j = o % ad;
+      const float ob = __ldg(p.aout_b + j);  // (in flight during the dot product, not behind the reduction)
       float acc = 0.f;
 #pragma unroll 8
       for (int k = lane * 4; k < D1; k += 128) {
@@ -1601,7 +1607,7 @@ __global__ void __launch_bounds__(DN_THREADS, 1) denoise_loop2_kernel(const lapb
         acc += wv.x * h01.x + wv.y * h01.y + wv.z * h23.x + wv.w * h23.y;
       }
       acc = warp_sum(acc);
-      if (lane == 0) x_s[o] += p.dt * (acc + __ldg(p.aout_b + j));
+      if (lane == 0) x_s[o] += p.dt * (acc + ob);
     }
     __syncthreads();
     tick(14);
