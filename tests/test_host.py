@@ -944,3 +944,19 @@ def test_orbax_plain_layout_round_trip(tmp_path):
     (oc / "manifest.ocdbt").write_bytes(b"\x0c\xdb\x3a\x2a")
     with pytest.raises(NotImplementedError, match="convert_orbax_checkpoint"):
         orbax_io.read_params(oc)
+
+
+def test_denoise_loop_shape_dispatch_is_host_logic():
+    """lapb200_denoise_supported (csrc/denoise.cu) is pure host arithmetic over the two shared-memory layouts of K10: the
+    serving shape of LAP-3B (10 action rows, 692 prefix keys) and its 16-row variant (round-1 layout only: the v2 buffers
+    no longer fit) are taken by the persistent kernel, the 50-row BASELINE.json variant and batches > 1 are not."""
+    from lap_b200 import ops
+    e = get_config("lap_libero").model.expert
+    dims = (e.width, e.num_heads, e.head_dim, e.mlp_dim)
+    assert dims == (1024, 8, 256, 4096)
+    ok = lambda B, A, ad, Pn, steps=10: ops.denoise_supported(B, A, ad, *dims, Pn, ((Pn + A + 63) // 64) * 64, steps)
+    assert ok(1, 10, 7, 692) and ok(1, 10, 32, 692) and ok(1, 16, 32, 692) and ok(1, 10, 7, 692, steps=16)
+    assert not ok(1, 50, 32, 560)        # BJ shape: 50 action rows -> kernel-per-op path
+    assert not ok(2, 10, 7, 692)         # the loop kernel is the batch-1 serving path
+    assert not ok(1, 10, 7, 692, steps=17)
+    assert not ok(1, 10, 7, 1100)        # key padding beyond 1024
